@@ -1,0 +1,58 @@
+"""Shared helpers for the test-suite (golden loading, error metrics, case construction)."""
+import ast
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import enf_ref as R
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "ref_*.npz")))
+
+
+def load_golden(name, dtype=torch.float64):
+    z = np.load(os.path.join(GOLDEN_DIR, f"ref_{name}.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    cfg = R.EnfConfig(num_in=meta["num_in"], num_hidden=meta["d"], num_heads=meta["H"], num_out=meta["O"],
+                      latent_dim=meta["L"], invariant_type=meta["invariant_type"],
+                      embedding_freq_multiplier=tuple(meta["freq"]), use_gaussian_window=meta["window"])
+    t = lambda k: torch.tensor(z[k], dtype=dtype)
+    params = {"params": R.tree_unflatten({k[6:]: t(k) for k in z.files if k.startswith("param:")})}
+    direction = R.tree_unflatten({k[4:]: t(k) for k in z.files if k.startswith("dir:")})
+    rec = {k: t(k) for k in ("x", "p", "a", "sigma", "out", "cot", "dp", "da", "dsigma")}
+    rec["dtheta_dir"] = float(z["dtheta_dir"])
+    return cfg, params, direction, rec
+
+
+def rel_err(got, want):
+    """max |got - want| / max |want|  (the metric every tolerance in tests/ refers to)."""
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    denom = want.abs().max().item()
+    if denom == 0.0:
+        return (got - want).abs().max().item()
+    return (got - want).abs().max().item() / denom
+
+
+def make_case(cfg, B, C, Z, seed=0, dtype=torch.float64, polar_grid=None, perturb=0.1, jitter=0.05):
+    """Seeded synthetic inputs + weights for a config (poses from the reference's initialisers, jittered)."""
+    g = torch.Generator().manual_seed(seed)
+    params = R.nef_init(cfg, seed=seed, dtype=dtype, perturb=perturb)
+    p, a, sigma = R.init_latents(cfg, B, Z, polar_grid=polar_grid, dtype=dtype, jitter=jitter, seed=seed)
+    t = cfg.invariant_type
+    if t in ("polar_periodic", "latitude_periodic"):
+        x = torch.stack([torch.rand(B, C, generator=g, dtype=dtype) * 2 * np.pi,
+                         0.05 + torch.rand(B, C, generator=g, dtype=dtype) * (np.pi - 0.1)], -1)
+    elif t in ("ball", "ball_lat"):
+        x = torch.stack([torch.rand(B, C, generator=g, dtype=dtype) * 2 * np.pi,
+                         0.05 + torch.rand(B, C, generator=g, dtype=dtype) * (np.pi - 0.1),
+                         torch.rand(B, C, generator=g, dtype=dtype)], -1)
+    else:
+        x = torch.rand(B, C, cfg.num_in, generator=g, dtype=dtype) * 2 - 1
+    d_out = torch.randn(B, C, cfg.num_out, generator=g, dtype=dtype) / (B * C)
+    return params, x, p, a, sigma, d_out

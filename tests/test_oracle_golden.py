@@ -1,0 +1,43 @@
+"""The oracle restatement against golden vectors produced by the reference's own source
+(tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle import enf_ref as R
+from helpers import golden_names, load_golden, rel_err
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_matches_reference_source(name):
+    cfg, params, _, rec = load_golden(name)
+    out = R.nef_apply(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"])
+    assert out.shape == rec["out"].shape
+    assert rel_err(out, rec["out"]) < 1e-11        # both float64
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_autograd_matches_reference_finite_differences(name):
+    cfg, params, direction, rec = load_golden(name)
+    out, dtheta, dp, da, dsigma = R.fwd_bwd(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
+    # central differences with step 1e-6 in float64: ~1e-8 absolute noise on O(1) derivatives
+    assert rel_err(dp, rec["dp"]) < 2e-6
+    assert rel_err(da, rec["da"]) < 2e-6
+    if cfg.use_gaussian_window:
+        assert rel_err(dsigma, rec["dsigma"]) < 2e-6
+    flat_g = R.tree_flatten(dtheta["params"])
+    flat_d = R.tree_flatten(direction)
+    ddir = sum(float((flat_g[k] * flat_d[k]).sum()) for k in flat_g)
+    assert abs(ddir - rec["dtheta_dir"]) < 2e-6 * max(1.0, abs(rec["dtheta_dir"]))
+    # frozen RFF coefficients: stop_gradient (rff.py:90)
+    for k, g in flat_g.items():
+        if k.endswith("coefficients"):
+            assert float(g.abs().max()) == 0.0
+
+
+def test_param_tree_names_match_reference_module_structure():
+    cfg, params, _, _ = load_golden("rel_pos_periodic")
+    ours = R.tree_flatten(R.nef_init(cfg)["params"])
+    theirs = R.tree_flatten(params["params"])
+    assert sorted(ours) == sorted(theirs)
+    for k in ours:
+        assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
