@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the ENF steerable cross-attention hot path (forward + backward), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config ns64] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic fields: `nef.apply` (fused cross
+attention + decode MLP) followed by the full reverse pass (latent gradients dp, da, dsigma AND all
+weight gradients) for an MSE loss against synthetic targets.  Prints ONE JSON line (rank 0).
+
+  value     device-timed throughput, inputs resident in HBM                [coord-queries / s, whole job]
+  e2e       same, through the public API from pinned HOST buffers, H2D of the step's inputs and D2H of
+            loss + latent gradients inside the timed region
+  roofline  the dominant kernel (fused pair backward): algorithmic FLOP / live CUDA-event kernel time,
+            against the measured dense bf16 tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (PyTorch-CPU fp32 restatement of the reference graph; JAX is not installable in
+            this image) timed on this box's host cores on a bounded sample of the same workload
+
+N > 1 (torchrun, one process per GPU): fields shard across ranks with no data-path collective (weak scaling,
+per-rank batch fixed); the outer-loop weight gradients are all-reduced with NCCL inside the timed step.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "coord-queries/sec (ENF cross-attn fwd+bwd)"
+UNIT = "queries/s"
+
+# BASELINE.json configs.  configs[1] (ns64) is the one the metric is quoted on.
+CONFIGS = {
+    "plane64": dict(label="2D planar heat diffusion 64x64, 25 latents", invariant_type="ponita", num_in=2, d=64, H=2, L=16, O=1,
+                    B=32, grid=(64, 64), Z=25, freq=(0.05, 0.01), window=True, polar_grid=None),
+    "ns64": dict(label="2D Navier-Stokes 64x64 vorticity, 64 latents, batch 32 fields", invariant_type="rel_pos_periodic",
+                 num_in=2, d=128, H=2, L=16, O=1, B=32, grid=(64, 64), Z=64, freq=(0.05, 0.1), window=True, polar_grid=None),
+    "sphere": dict(label="spherical diffusion 128x64 lat-lon, 18 latents", invariant_type="polar_periodic", num_in=2, d=16, H=2,
+                   L=4, O=1, B=8, grid=(128, 64), Z=18, freq=(0.01, 0.01), window=False, polar_grid=(6, 3)),
+    "sw192": dict(label="shallow water 192x96 sphere, 144 latents", invariant_type="latitude_periodic", num_in=2, d=128, H=2,
+                  L=32, O=3, B=4, grid=(192, 96), Z=144, freq=(0.05, 0.2), window=True, polar_grid=(16, 9)),
+    "ihc": dict(label="3D IHC ball 64x40x40 coords, 256 latents", invariant_type="ball", num_in=3, d=32, H=3, L=32, O=1,
+                B=1, grid=(64, 40, 40), Z=256, freq=(0.2, 0.5), window=True, polar_grid=None),
+}
+
+
+def flops_per_pair(cfg, I):
+    d, H = cfg["d"], cfg["H"]
+    alg = 2 * I * d + (6 + 6 * H) * d * d + 4 * H * d          # SURVEY 8d contract figure (after the survey's folds)
+    ref = 2 * I * d + (10 + 10 * H) * d * d                     # reference graph as written
+    return alg, ref
+
+
+def flops_per_query_tail(cfg):
+    d, H, O = cfg["d"], cfg["H"], cfg["O"]
+    return 2 * H * d * d + 6 * (H * d) ** 2 + 2 * H * d * d + 2 * d * d + 2 * d * O
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return dict(bf16_sustained=pk.get("bf16_tflops_sustained", 1400.0), bf16_burst=pk.get("bf16_tflops", 1590.0),
+                    hbm=pk.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+                self._stop.wait(0.1)
+        except Exception as e:          # noqa: BLE001
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle on host cores (cpu_baseline / --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+
+def cpu_leg(cfg, steps, warmup, budget_s=25.0):
+    import torch
+    from oracle import enf_ref as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ocfg = R.EnfConfig(num_in=cfg["num_in"], num_hidden=cfg["d"], num_heads=cfg["H"], num_out=cfg["O"], latent_dim=cfg["L"],
+                       invariant_type=cfg["invariant_type"], embedding_freq_multiplier=cfg["freq"],
+                       use_gaussian_window=cfg["window"])
+    # bounded sample of the same workload: same Z, d, H, invariant; fewer fields and queries (the unfused graph
+    # materialises ~20 (B,C,Z,2Hd) fp32 tensors; the reference itself sub-samples to 512..10000 queries per step)
+    Bs = min(cfg["B"], 2)
+    per_pair_bytes = 4 * 2 * cfg["H"] * cfg["d"] * 24
+    Cs = int(max(64, min(512, (3 << 30) // (per_pair_bytes * cfg["Z"] * Bs))))
+    dt = torch.float32
+    params = R.nef_init(ocfg, seed=0, dtype=dt)
+    p, a, sigma = R.init_latents(ocfg, Bs, cfg["Z"], polar_grid=cfg["polar_grid"], dtype=dt, jitter=0.02)
+    coords = R.make_coords(ocfg, cfg["grid"], dtype=dt)
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randperm(coords.shape[0], generator=g)[:Cs]
+    x = coords[idx][None].expand(Bs, -1, -1)
+    y = torch.randn(Bs, Cs, cfg["O"], generator=g, dtype=dt)
+
+    def step():
+        P = R.tree_map(lambda t: t.detach().requires_grad_(True), params)
+        pp, aa, ss = p.clone().requires_grad_(True), a.clone().requires_grad_(True), sigma.clone().requires_grad_(True)
+        out = R.nef_apply(ocfg, P, x, pp, aa, ss)
+        loss = ((out - y) ** 2).mean()
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and i >= 1:
+            break
+    tot = sum(times)
+    return dict(value=Bs * Cs * len(times) / tot, unit=UNIT, cores=cores, kind="port",
+                sample=f"{Bs} fields x {Cs} queries x {cfg['Z']} latents per step (same d,H,invariant), {len(times)} steps, "
+                       f"PyTorch-CPU fp32 restatement of the reference graph with autograd (JAX not installable here)",
+                ms_per_step=1e3 * tot / len(times), steps=len(times))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="ns64", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    C = int(math.prod(cfg["grid"]))
+    workload = {"workload": f"{args.config}: {cfg['label']}", "B_per_gpu": cfg["B"], "C": C, "Z": cfg["Z"], "d": cfg["d"],
+                "H": cfg["H"], "invariant": cfg["invariant_type"], "latent_dim": cfg["L"], "num_out": cfg["O"]}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_leg(cfg, max(1, args.steps), args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import enf_pde_b200 as E
+    from enf_pde_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = E.load_library()
+
+    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
+    nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True,
+                                         cfg["window"], precision="fp32")
+    B, Z = cfg["B"], cfg["Z"]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])
+    p_h = p_h + 0.02 * torch.randn(p_h.shape, generator=gen)
+    a_h = a_h + 0.1 * torch.randn(a_h.shape, generator=gen)
+    from enf_pde_b200.latents import make_coords
+    x_h = make_coords(inv, cfg["grid"]).contiguous()                              # (C, Dx), shared by all fields
+    y_h = torch.randn(B, C, cfg["O"], generator=gen)
+    variables = nef.init(0, x_h[None], p_h.to(dev), a_h.to(dev), s_h.to(dev))     # same weights on every rank
+    leaves = E.params_to_leaves(variables)
+    for t in leaves:
+        t.requires_grad_(True)
+    use_sigma = cfg["window"]
+
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    p_d, a_d, s_d = (t.to(dev).requires_grad_(True) for t in (p_h, a_h, s_h))
+    n_out = B * C * cfg["O"]
+
+    def step_device(x, y, p, a, s):
+        for t in leaves:
+            t.grad = None
+        p.grad = a.grad = None
+        if s is not None:
+            s.grad = None
+        out = nef.apply(variables, x[None].expand(B, -1, -1), p, a, s if use_sigma else None)
+        diff = out.detach() - y
+        loss = (diff * diff).mean()
+        out.backward(diff * (2.0 / n_out))
+        if world > 1:
+            flat = torch.cat([t.grad.reshape(-1) for t in leaves])
+            dist.all_reduce(flat)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device(x_d, y_d, p_d, a_d, s_d)
+    lib.enf_profile_enable(1)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            step_device(x_d, y_d, p_d, a_d, s_d)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    buf = (ctypes.c_float * 256)()
+    n_f = lib.enf_profile_collect(0, buf, 256); fwd_ms = [buf[i] for i in range(max(n_f, 0))]
+    n_b = lib.enf_profile_collect(1, buf, 256); bwd_ms = [buf[i] for i in range(max(n_b, 0))]
+    lib.enf_profile_enable(0)
+    launches = sum(E.last_launch_counts()) * args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end from pinned host buffers ----------------------------------------------------------------
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    xh, yh, ph, ah, sh = pin(x_h), pin(y_h), pin(p_h), pin(a_h), pin(s_h)
+    dp_host, da_host, ds_host = (torch.empty_like(t).pin_memory() for t in (p_h, a_h, s_h))
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in (xh, yh, ph, ah)) + (sh.numel() * 4 if use_sigma else 0)
+    d2h = 4 + sum(t.numel() * 4 for t in (dp_host, da_host)) + (ds_host.numel() * 4 if use_sigma else 0)
+
+    def step_e2e():
+        x = xh.to(dev, non_blocking=True); y = yh.to(dev, non_blocking=True)
+        p = ph.to(dev, non_blocking=True).requires_grad_(True); a = ah.to(dev, non_blocking=True).requires_grad_(True)
+        s = sh.to(dev, non_blocking=True).requires_grad_(True) if use_sigma else None
+        loss = step_device(x, y, p, a, s)
+        loss_host.copy_(loss, non_blocking=True)
+        dp_host.copy_(p.grad, non_blocking=True); da_host.copy_(a.grad, non_blocking=True)
+        if use_sigma:
+            ds_host.copy_(s.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the loss / latent gradients every step
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused pair backward) ----------------------------------------------
+    peaks = read_peaks()
+    I = inv.dim
+    f_alg, f_ref = flops_per_pair(cfg, I)
+    pairs = B * C * Z
+    bwd_avg = sum(bwd_ms) / len(bwd_ms) if bwd_ms else float("nan")
+    fwd_avg = sum(fwd_ms) / len(fwd_ms) if fwd_ms else float("nan")
+    achieved = 2.0 * f_alg * pairs / (bwd_avg * 1e-3) / 1e12 if bwd_ms else None
+    roofline = {"bound": "tensor", "kernel": "pairs_bwd_kernel (fused pair backward)", "achieved": achieved,
+                "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
+                "traffic": None, "peak_source": peaks["source"] + ", dense bf16 sustained",
+                "algorithmic_flop_per_launch": 2.0 * f_alg * pairs, "kernel_ms_avg": bwd_avg, "kernel_share_of_step": bwd_avg * args.steps / ms if bwd_ms else None,
+                "fwd_kernel_ms_avg": fwd_avg, "fwd_achieved": (f_alg * pairs / (fwd_avg * 1e-3) / 1e12) if fwd_ms else None,
+                "note": "arithmetic on this path is fp32 FMA (precision mode fp32); FLOP count is SURVEY 8d's contract figure "
+                        "F_pair_alg per (query, latent) pair, x2 for the backward (dgrad + wgrad, recompute not counted)"}
+    total_flop_step = 3.0 * (f_alg * pairs + flops_per_query_tail(cfg) * B * C)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_leg(cfg, 6, 1, budget_s=20.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    q_total = world * B * C * args.steps
+    line = {"metric": METRIC, "value": q_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload, "global_fields": world * B, "parallelism": f"dp{world} over fields",
+                       "l2": "per-step working set (~2.5 GB workspace at ns64) >> 126 MB L2; no explicit flush",
+                       "step": "fwd + bwd incl. all weight grads" + (" + NCCL all-reduce of weight grads" if world > 1 else ""),
+                       "step_tflop_contract": total_flop_step / 1e12},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "e2e": {"value": q_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

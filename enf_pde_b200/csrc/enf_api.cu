@@ -1,0 +1,469 @@
+// C ABI (include/enf_b200.h) and stage orchestration of the ENF cross-attention path.
+//
+//   W  fold weights            (A_q, c_q, W', b', W2g, b2g, M2g, c2g)
+//   L  per-latent folds        (pose record Lam, ahat, k, v0, U, kappa, Weff, W3, b3)
+//   X  per-query record xi
+//   P  fused pair kernel       -> nbar, lse                    [the hot kernel]
+//   Q  per-query tail          M2g, out_proj, block FFN, decode MLP -> out
+// and the reverse of each for enf_xattn_bwd.  The algebra is tests/folded_model.py (validated on CPU
+// against the unfused oracle); DESIGN.md lists every buffer.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "enf_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+struct Buf { const char* name; size_t off; size_t n; };
+
+struct Layout {
+  std::vector<Buf> bufs;
+  size_t total = 0;          // floats
+  size_t acc_begin = 0, acc_end = 0;   // zeroed at the start of every bwd
+  size_t add(const char* name, size_t n) {
+    size_t off = total;
+    bufs.push_back({name, off, n});
+    total += (n + 63) & ~size_t(63);    // 256-byte granularity
+    return off;
+  }
+  size_t off(const char* name) const {
+    for (auto& b : bufs) if (!strcmp(b.name, name)) return b.off;
+    return (size_t)-1;
+  }
+};
+
+const char* kLeafNames[ENF_NUM_WEIGHT_LEAVES] = {
+    "stem_w", "stem_b", "ln_attn_g", "ln_attn_b", "q_omega", "q_w1", "q_b1", "q_wf", "q_bf", "v_omega", "v_w1", "v_b1",
+    "v_wf", "v_bf", "wq", "bq", "wk", "bk", "wv", "bv", "fv_w1", "fv_b1", "fv_g", "fv_beta", "fv_w2", "fv_b2", "mx_w1",
+    "mx_b1", "mx_g", "mx_beta", "mx_w2", "mx_b2", "wo", "bo", "fb_w1", "fb_b1", "fb_g", "fb_beta", "fb_w2", "fb_b2",
+    "m0_w", "m0_b", "m1_w", "m1_b", "m2_w", "m2_b"};
+
+void leaf_sizes(const EnfDesc& D, int I, size_t* n) {
+  const size_t d = D.d, H = D.H, L = D.L, O = D.O, Hd = H * d;
+  size_t v[ENF_NUM_WEIGHT_LEAVES] = {
+      L * d, d, d, d, I * (d / 2), d * d, d, d * d, d, I * (d / 2), d * d, d, d * d, d, d * Hd, Hd, d * Hd, Hd, d * Hd, Hd,
+      d * d, d, d, d, d * 2 * Hd, 2 * Hd, d * d, d, d, d, d * d, d, Hd * Hd, Hd, Hd * Hd, Hd, Hd, Hd, Hd * Hd, Hd,
+      Hd * d, d, d * d, d, d * O, O};
+  memcpy(n, v, sizeof(v));
+}
+
+int validate(const EnfDesc* D, EnfRecordLayout* rl) {
+  if (!D) return fail(ENF_ERR_NULL_POINTER, "desc is NULL");
+  if (D->B <= 0 || D->C <= 0 || D->Z <= 0 || D->L <= 0 || D->O <= 0) return fail(ENF_ERR_BAD_DESC, "B, C, Z, L, O must be positive");
+  if (!(D->d == 16 || D->d == 32 || D->d == 64 || D->d == 128)) return fail(ENF_ERR_UNSUPPORTED, "num_hidden must be 16, 32, 64 or 128");
+  if (D->H < 1 || D->H > 4) return fail(ENF_ERR_UNSUPPORTED, "num_heads must be 1..4");
+  EnfRecordLayout r = enf_record_layout(D->invariant_kind, D->Dx, D->use_window);
+  if (r.I < 0) return fail(ENF_ERR_BAD_DESC, "unknown invariant_kind");
+  int k = D->invariant_kind;
+  bool dx_ok = (k <= ENF_INV_ABS_POS) ? (D->Dx >= 1 && D->Dx <= 3)
+               : (k == ENF_INV_BALL || k == ENF_INV_BALL_LAT) ? (D->Dx == 3) : (D->Dx == 2);
+  if (!dx_ok) return fail(ENF_ERR_BAD_DESC, "num_in (Dx) does not match the invariant (rel/norm/abs: 1..3, ball*: 3, others: 2)");
+  if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
+  if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
+  if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
+  if (rl) *rl = r;
+  return ENF_OK;
+}
+
+Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
+  Layout Y;
+  const size_t d = D.d, H = D.H, Hd = H * d, d2 = d * d;
+  const size_t BZ = (size_t)D.B * D.Z, BC = (size_t)D.B * D.C;
+  Y.add("A_q", d * Hd); Y.add("c_q", Hd); Y.add("Wp", d2); Y.add("bp", d); Y.add("W2g", d * 2 * Hd); Y.add("b2g", 2 * Hd);
+  Y.add("M2g", d2); Y.add("c2g", d); Y.add("q_w1T", d2); Y.add("v_w1T", d2); Y.add("WpT", d2);
+  Y.add("lam", BZ * ENF_LAM_SIZE); Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
+  Y.add("k", BZ * Hd); Y.add("v0", BZ * Hd); Y.add("U", BZ * Hd); Y.add("kappa", BZ * H);
+  Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
+  Y.add("xi", BC * ENF_F_XI);
+  Y.add("nbar", BC * Hd); Y.add("lse", BC * H);
+  Y.add("y", BC * Hd); Y.add("y2", BC * Hd); Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
+  Y.add("fo", BC * Hd); Y.add("o1p", BC * d); Y.add("o2p", BC * d);
+  Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("s2", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
+  Y.add("dbeff", BZ * Hd); Y.add("dk", BZ * Hd); Y.add("dv0", BZ * Hd); Y.add("dahat", BZ * d); Y.add("da0", BZ * d);
+  // ---- accumulators, zeroed at the start of each bwd ----
+  Y.acc_begin = Y.total;
+  Y.add("g_W3", BZ * H * d2); Y.add("g_b3", BZ * Hd); Y.add("g_U", BZ * Hd); Y.add("g_kappa", BZ * H);
+  Y.add("g_lam", BZ * ENF_LAM_SIZE); Y.add("g_sigma", BZ);
+  Y.add("gf_A_q", d * Hd); Y.add("gf_c_q", Hd); Y.add("gf_Wp", d2); Y.add("gf_bp", d); Y.add("gf_W2g", d * 2 * Hd);
+  Y.add("gf_b2g", 2 * Hd); Y.add("gf_M2g", d2); Y.add("gf_c2g", d);
+  size_t n[ENF_NUM_WEIGHT_LEAVES];
+  leaf_sizes(D, rl.I, n);
+  static const std::vector<std::string> names = [] {
+    std::vector<std::string> v;
+    for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) v.push_back(std::string("gw_") + kLeafNames[i]);
+    return v;
+  }();
+  for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) Y.add(names[i].c_str(), n[i]);
+  Y.acc_end = Y.total;
+  return Y;
+}
+
+std::mutex g_mu;
+std::map<void*, EnfDesc> g_fwd_state;     // workspaces that currently hold a forward
+
+// optional live timing of the two fused pair kernels (bench.py's roofline line): a ring of CUDA event
+// pairs per kernel, recorded on the call's stream; enf_profile_collect drains it.
+constexpr int kProfRing = 256;
+bool g_prof_on = false;
+cudaEvent_t g_prof_ev[2][kProfRing][2];
+bool g_prof_created[2][kProfRing];
+long g_prof_count[2] = {0, 0};
+void prof_mark(int which, int edge, cudaStream_t st) {
+  if (!g_prof_on) return;
+  int slot = (int)(g_prof_count[which] % kProfRing);
+  if (!g_prof_created[which][slot]) {
+    cudaEventCreate(&g_prof_ev[which][slot][0]);
+    cudaEventCreate(&g_prof_ev[which][slot][1]);
+    g_prof_created[which][slot] = true;
+  }
+  cudaEventRecord(g_prof_ev[which][slot][edge], st);
+  if (edge == 1) g_prof_count[which]++;
+}
+
+struct LeafCopy { const float* src[ENF_NUM_WEIGHT_LEAVES]; float* dst[ENF_NUM_WEIGHT_LEAVES]; int n[ENF_NUM_WEIGHT_LEAVES]; };
+__global__ void copy_leaves_kernel(LeafCopy t) {
+  const int leaf = blockIdx.y;
+  float* dst = t.dst[leaf];
+  if (!dst) return;
+  const float* src = t.src[leaf];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n[leaf]; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+struct Ctx {
+  cudaStream_t st;
+  float* ws;
+  const Layout* Y;
+  int launches = 0;
+  float* f(const char* name) const { return ws + Y->off(name); }
+  void gemm(int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o = EnfGemmOpts()) {
+    launches += enf_gemm(st, M, N, K, A, B, C, o);
+  }
+};
+
+EnfGemmOpts opt_bias(const float* bias) { EnfGemmOpts o; o.bias = bias; return o; }
+EnfGemmOpts opt_acc() { EnfGemmOpts o; o.accumulate = 1; return o; }
+
+EnfPairParams pair_params(const EnfDesc& D, const EnfRecordLayout& rl, const EnfWeights& w, const Ctx& c,
+                          const float* sigma, int64_t xi_bs) {
+  EnfPairParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = D.B; p.C = D.C; p.Z = D.Z; p.H = D.H; p.I = rl.I;
+  p.row_kind = rl.row_kind; p.win_kind = rl.win_kind; p.win_row = rl.win_row; p.nsq = rl.nsq;
+  p.xi = c.f("xi"); p.xi_bs = xi_bs; p.lam = c.f("lam"); p.sigma = sigma;
+  p.q_omega = w.q_omega; p.v_omega = w.v_omega;
+  p.q_w1 = w.q_w1; p.q_b1 = w.q_b1; p.v_w1 = w.v_w1; p.v_b1 = w.v_b1;
+  p.Wp = c.f("Wp"); p.bp = c.f("bp");
+  p.U = c.f("U"); p.kappa = c.f("kappa"); p.W3 = c.f("W3"); p.b3 = c.f("b3");
+  p.nbar = c.f("nbar"); p.lse = c.f("lse");
+  return p;
+}
+
+bool check_weights(const EnfWeights* w) {
+  const float* const* p = reinterpret_cast<const float* const*>(w);
+  for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) if (!p[i]) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int enf_abi_version(void) { return ENF_B200_ABI_VERSION; }
+
+int enf_invariant_dim(int kind, int Dx) { return enf_record_layout(kind, Dx, 1).I; }
+int enf_pose_dim(int kind, int Dx) { return enf_record_layout(kind, Dx, 1).P; }
+
+const char* enf_last_error(void) { return g_err.c_str(); }
+
+int enf_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_count[0] = g_prof_count[1] = 0;
+  return 0;
+}
+int enf_profile_collect(int which, float* ms_out, int max_out) {
+  if (which < 0 || which > 1 || !ms_out) return -1;
+  long n = g_prof_count[which];
+  if (n > kProfRing) n = kProfRing;
+  if (n > max_out) n = max_out;
+  long first = g_prof_count[which] - n;
+  for (long i = 0; i < n; ++i) {
+    int slot = (int)((first + i) % kProfRing);
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_prof_ev[which][slot][1]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[which][slot][0], g_prof_ev[which][slot][1]) != cudaSuccess) return -1;
+    ms_out[i] = ms;
+  }
+  g_prof_count[which] = 0;
+  return (int)n;
+}
+
+int enf_last_launch_count(void) { return g_launches; }
+
+size_t enf_xattn_workspace_bytes(const EnfDesc* desc) {
+  EnfRecordLayout rl;
+  if (validate(desc, &rl) != ENF_OK) return 0;
+  return make_layout(*desc, rl).total * sizeof(float);
+}
+
+int64_t enf_debug_ws_offset(const EnfDesc* desc, const char* name, int64_t* num_floats) {
+  EnfRecordLayout rl;
+  if (validate(desc, &rl) != ENF_OK || !name) return -1;
+  Layout Y = make_layout(*desc, rl);
+  for (auto& b : Y.bufs)
+    if (!strcmp(b.name, name)) { if (num_floats) *num_floats = (int64_t)b.n; return (int64_t)(b.off * sizeof(float)); }
+  return -1;
+}
+
+int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int64_t x_batch_stride, const float* p,
+                  const float* a, const float* sigma, float* out, void* workspace, size_t workspace_bytes,
+                  enf_stream_t stream) {
+  g_launches = 0;
+  EnfRecordLayout rl;
+  int rc = validate(desc, &rl);
+  if (rc != ENF_OK) return rc;
+  const EnfDesc& D = *desc;
+  if (!w || !x || !p || !a || !out || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
+  if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
+  if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
+  if (D.precision != ENF_PREC_FP32) return fail(ENF_ERR_UNSUPPORTED, "this build implements precision ENF_PREC_FP32 only");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
+  Layout Y = make_layout(D, rl);
+  if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small: see enf_xattn_workspace_bytes");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ENF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+
+  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y;
+  cudaStream_t st = c.st;
+  const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
+  const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
+  const int Bx = x_batch_stride == 0 ? 1 : D.B;
+
+  // ---- W: fold weights --------------------------------------------------------------------------
+  c.gemm(d, Hd, d, enf_mat(w->q_wf, d), enf_mat(w->wq, Hd), enf_mat(c.f("A_q"), Hd));
+  c.gemm(1, Hd, d, enf_mat(w->q_bf, d), enf_mat(w->wq, Hd), enf_mat(c.f("c_q"), Hd), opt_bias(w->bq));
+  c.gemm(d, d, d, enf_mat(w->v_wf, d), enf_mat(w->fv_w1, d), enf_mat(c.f("Wp"), d));
+  c.gemm(1, d, d, enf_mat(w->v_bf, d), enf_mat(w->fv_w1, d), enf_mat(c.f("bp"), d), opt_bias(w->fv_b1));
+  c.launches += enf_launch_rowscale(st, w->fv_w2, w->fv_g, c.f("W2g"), d, 2 * Hd);
+  c.gemm(1, 2 * Hd, d, enf_mat(w->fv_beta, d), enf_mat(w->fv_w2, 2 * Hd), enf_mat(c.f("b2g"), 2 * Hd), opt_bias(w->fv_b2));
+  c.launches += enf_launch_rowscale(st, w->mx_w2, w->mx_g, c.f("M2g"), d, d);
+  c.gemm(1, d, d, enf_mat(w->mx_beta, d), enf_mat(w->mx_w2, d), enf_mat(c.f("c2g"), d), opt_bias(w->mx_b2));
+
+  // ---- L: per-latent folds ----------------------------------------------------------------------
+  c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
+  c.gemm((int)BZ, d, L, enf_mat(a, L), enf_mat(w->stem_w, d), enf_mat(c.f("a0"), d), opt_bias(w->stem_b));
+  c.launches += enf_launch_ln_fwd(st, c.f("a0"), BZ, d, w->ln_attn_g, w->ln_attn_b, c.f("acore"), c.f("ahat"), c.f("arstd"), 0);
+  c.gemm((int)BZ, Hd, d, enf_mat(c.f("ahat"), d), enf_mat(w->wk, Hd), enf_mat(c.f("k"), Hd), opt_bias(w->bk));
+  c.gemm((int)BZ, Hd, d, enf_mat(c.f("ahat"), d), enf_mat(w->wv, Hd), enf_mat(c.f("v0"), Hd), opt_bias(w->bv));
+  {
+    EnfGemmOpts o; o.batch = H;     // U[bz,h,i] = sum_j A_q[i, h*d+j] k[bz,h,j]
+    c.gemm((int)BZ, d, d, enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("A_q"), 1, Hd, d), enf_mat(c.f("U"), Hd, 1, d), o);
+    // kappa[bz,h] = sum_j c_q[h*d+j] k[bz,h,j]
+    c.gemm((int)BZ, 1, d, enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("c_q"), 1, 0, d), enf_mat(c.f("kappa"), H, 1, 1), o);
+  }
+  c.launches += enf_launch_weff(st, D, c.f("W2g"), c.f("b2g"), c.f("v0"), c.f("Weff"), c.f("beff"));
+  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("Weff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("W3"), d));
+  c.gemm((int)(BZ * H), d, d, enf_mat(c.f("beff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("b3"), d), opt_bias(w->mx_b1));
+
+  // ---- X, P ---------------------------------------------------------------------------------------
+  c.launches += enf_launch_query_features(st, D, x, x_batch_stride, Bx, c.f("xi"));
+  EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
+  prof_mark(0, 0, st);
+  int nl = enf_launch_pairs_fwd_simt(st, d, pp);
+  prof_mark(0, 1, st);
+  if (nl < 0) return fail(ENF_ERR_CUDA, "pair forward kernel could not be configured");
+  c.launches += nl;
+
+  // ---- Q: per-query tail ----------------------------------------------------------------------------
+  c.gemm((int)(BC * H), d, d, enf_mat(c.f("nbar"), d), enf_mat(c.f("M2g"), d), enf_mat(c.f("y"), d), opt_bias(c.f("c2g")));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("y"), Hd), enf_mat(w->wo, Hd), enf_mat(c.f("y2"), Hd), opt_bias(w->bo));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("y2"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("e1"), Hd), opt_bias(w->fb_b1));
+  c.launches += enf_launch_ln_fwd(st, c.f("e1"), BC, Hd, w->fb_g, w->fb_beta, c.f("e3c"), c.f("e3"), c.f("erstd"), 1);
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), opt_bias(w->fb_b2));
+  {
+    EnfGemmOpts o; o.act_a = 1;
+    o.bias = w->m0_b; c.gemm((int)BC, d, Hd, enf_mat(c.f("fo"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
+    o.bias = w->m1_b; c.gemm((int)BC, d, d, enf_mat(c.f("o1p"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
+    o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing fwd: ") + cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_fwd_state[workspace] = D;
+  }
+  g_launches = c.launches;
+  return ENF_OK;
+}
+
+int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int64_t x_batch_stride, const float* p,
+                  const float* a, const float* sigma, const float* d_out, const EnfWeightGrads* dW, float* dp, float* da,
+                  float* dsigma, void* workspace, size_t workspace_bytes, enf_stream_t stream) {
+  g_launches = 0;
+  EnfRecordLayout rl;
+  int rc = validate(desc, &rl);
+  if (rc != ENF_OK) return rc;
+  const EnfDesc& D = *desc;
+  if (!w || !x || !p || !a || !d_out || !dp || !da || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
+  if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set");
+  if (D.precision != ENF_PREC_FP32) return fail(ENF_ERR_UNSUPPORTED, "this build implements precision ENF_PREC_FP32 only");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_fwd_state.find(workspace);
+    if (it == g_fwd_state.end() || memcmp(&it->second, &D, sizeof(EnfDesc)) != 0)
+      return fail(ENF_ERR_STATE, "enf_xattn_bwd needs the workspace of a matching enf_xattn_fwd call");
+  }
+  Layout Y = make_layout(D, rl);
+  if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small");
+
+  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y;
+  cudaStream_t st = c.st;
+  const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
+  const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
+  const int Bx = x_batch_stride == 0 ? 1 : D.B;
+  auto G = [&](const char* leaf) { return c.f((std::string("gw_") + leaf).c_str()); };
+  auto colsum = [&](const float* Gm, int64_t M, int N, float* out) { c.launches += enf_launch_colsum(st, Gm, M, N, N, out, nullptr, 0); };
+
+  if (cudaMemsetAsync(c.ws + Y.acc_begin, 0, (Y.acc_end - Y.acc_begin) * sizeof(float), st) != cudaSuccess)
+    return fail(ENF_ERR_CUDA, "memset of accumulators failed");
+
+  // ---- Q backward: decode MLP, block FFN, out_proj, M2g ------------------------------------------------
+  {
+    EnfGemmOpts wa = opt_acc(); wa.act_a = 1;                 // wgrad with gelu applied to the stored pre-activation
+    EnfGemmOpts o;
+    c.gemm(d, O, (int)BC, enf_mat(c.f("o2p"), 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
+    colsum(d_out, BC, O, G("m2_b"));
+    o.mul_gelu_grad = c.f("o2p");
+    c.gemm((int)BC, d, O, enf_mat(d_out, O), enf_mat(w->m2_w, 1, O), enf_mat(c.f("d_o2p"), d), o);
+    c.gemm(d, d, (int)BC, enf_mat(c.f("o1p"), 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
+    colsum(c.f("d_o2p"), BC, d, G("m1_b"));
+    o.mul_gelu_grad = c.f("o1p");
+    c.gemm((int)BC, d, d, enf_mat(c.f("d_o2p"), d), enf_mat(w->m1_w, 1, d), enf_mat(c.f("d_o1p"), d), o);
+    c.gemm(Hd, d, (int)BC, enf_mat(c.f("fo"), 1, Hd), enf_mat(c.f("d_o1p"), d), enf_mat(G("m0_w"), d), wa);
+    colsum(c.f("d_o1p"), BC, d, G("m0_b"));
+    o.mul_gelu_grad = c.f("fo");
+    c.gemm((int)BC, Hd, d, enf_mat(c.f("d_o1p"), d), enf_mat(w->m0_w, 1, d), enf_mat(c.f("s0"), Hd), o);      // dfo
+  }
+  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("e3"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("fb_w2"), Hd), opt_acc());
+  colsum(c.f("s0"), BC, Hd, G("fb_b2"));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->fb_w2, 1, Hd), enf_mat(c.f("s1"), Hd));           // de3
+  c.launches += enf_launch_ln_bwd(st, c.f("s1"), c.f("e3c"), c.f("erstd"), w->fb_g, c.f("e1"), BC, Hd, c.f("s1"),
+                                  G("fb_g"), G("fb_beta"), 1);                                                    // de1 (in place)
+  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("y2"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(G("fb_w1"), Hd), opt_acc());
+  colsum(c.f("s1"), BC, Hd, G("fb_b1"));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("s0"), Hd));           // dy2
+  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("y"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("wo"), Hd), opt_acc());
+  colsum(c.f("s0"), BC, Hd, G("bo"));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->wo, 1, Hd), enf_mat(c.f("s2"), Hd));              // dy
+  c.gemm(d, d, (int)(BC * H), enf_mat(c.f("nbar"), 1, d), enf_mat(c.f("s2"), d), enf_mat(c.f("gf_M2g"), d), opt_acc());
+  colsum(c.f("s2"), BC * H, d, c.f("gf_c2g"));
+  c.gemm((int)(BC * H), d, d, enf_mat(c.f("s2"), d), enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("s0"), d));        // dnbar
+
+  // ---- P backward --------------------------------------------------------------------------------------
+  c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
+  c.launches += enf_launch_transpose(st, w->v_w1, c.f("v_w1T"), d, d, 1);
+  c.launches += enf_launch_transpose(st, c.f("Wp"), c.f("WpT"), d, d, 1);
+  c.launches += enf_launch_transpose(st, c.f("W3"), c.f("W3T"), d, d, (int)(BZ * H));
+  EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
+  pp.q_w1T = c.f("q_w1T"); pp.v_w1T = c.f("v_w1T"); pp.WpT = c.f("WpT"); pp.W3T = c.f("W3T");
+  pp.dnbar = c.f("s0");
+  pp.g_q_w1 = G("q_w1"); pp.g_q_b1 = G("q_b1"); pp.g_v_w1 = G("v_w1"); pp.g_v_b1 = G("v_b1");
+  pp.g_Wp = c.f("gf_Wp"); pp.g_bp = c.f("gf_bp");
+  pp.g_W3 = c.f("g_W3"); pp.g_b3 = c.f("g_b3"); pp.g_U = c.f("g_U"); pp.g_kappa = c.f("g_kappa");
+  pp.g_lam = c.f("g_lam"); pp.g_sigma = c.f("g_sigma");
+  prof_mark(1, 0, st);
+  int nl = enf_launch_pairs_bwd_simt(st, d, pp);
+  prof_mark(1, 1, st);
+  if (nl < 0) return fail(ENF_ERR_CUDA, "pair backward kernel could not be configured");
+  c.launches += nl;
+
+  // ---- L backward ----------------------------------------------------------------------------------------
+  c.gemm(d, d, (int)(BZ * H * d), enf_mat(c.f("Weff"), 1, d), enf_mat(c.f("g_W3"), d), enf_mat(G("mx_w1"), d), opt_acc());
+  c.gemm(d, d, (int)(BZ * H), enf_mat(c.f("beff"), 1, d), enf_mat(c.f("g_b3"), d), enf_mat(G("mx_w1"), d), opt_acc());
+  colsum(c.f("g_b3"), BZ * H, d, G("mx_b1"));
+  float* dWeff = c.f("W3");       // W3 is dead after the pair backward
+  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("g_W3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(dWeff, d));
+  c.gemm((int)(BZ * H), d, d, enf_mat(c.f("g_b3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(c.f("dbeff"), d));
+  c.launches += enf_launch_weff_bwd(st, D, c.f("W2g"), c.f("b2g"), c.f("v0"), dWeff, c.f("dbeff"), c.f("gf_W2g"),
+                                    c.f("gf_b2g"), c.f("dv0"));
+  {
+    EnfGemmOpts o; o.batch = H;
+    // dk[bz,h,j] = sum_i A_q[i,h*d+j] dU[bz,h,i]  + dkappa[bz,h] c_q[h*d+j]
+    c.gemm((int)BZ, d, d, enf_mat(c.f("g_U"), Hd, 1, d), enf_mat(c.f("A_q"), Hd, 1, d), enf_mat(c.f("dk"), Hd, 1, d), o);
+    EnfGemmOpts oa = opt_acc(); oa.batch = H;
+    c.gemm((int)BZ, d, 1, enf_mat(c.f("g_kappa"), H, 1, 1), enf_mat(c.f("c_q"), 0, 1, d), enf_mat(c.f("dk"), Hd, 1, d), oa);
+    // dA_q[i,h*d+j] = sum_bz dU[bz,h,i] k[bz,h,j] ; dc_q[h*d+j] = sum_bz dkappa[bz,h] k[bz,h,j]
+    c.gemm(d, d, (int)BZ, enf_mat(c.f("g_U"), 1, Hd, d), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_A_q"), Hd, 1, d), oa);
+    c.gemm(1, d, (int)BZ, enf_mat(c.f("g_kappa"), 0, H, 1), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_c_q"), 0, 1, d), oa);
+  }
+  c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dk"), Hd), enf_mat(G("wk"), Hd), opt_acc());
+  colsum(c.f("dk"), BZ, Hd, G("bk"));
+  c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dv0"), Hd), enf_mat(G("wv"), Hd), opt_acc());
+  colsum(c.f("dv0"), BZ, Hd, G("bv"));
+  c.gemm((int)BZ, d, Hd, enf_mat(c.f("dk"), Hd), enf_mat(w->wk, 1, Hd), enf_mat(c.f("dahat"), d));
+  c.gemm((int)BZ, d, Hd, enf_mat(c.f("dv0"), Hd), enf_mat(w->wv, 1, Hd), enf_mat(c.f("dahat"), d), opt_acc());
+  c.launches += enf_launch_ln_bwd(st, c.f("dahat"), c.f("acore"), c.f("arstd"), w->ln_attn_g, nullptr, BZ, d, c.f("da0"),
+                                  G("ln_attn_g"), G("ln_attn_b"), 0);
+  c.gemm(L, d, (int)BZ, enf_mat(a, 1, L), enf_mat(c.f("da0"), d), enf_mat(G("stem_w"), d), opt_acc());
+  colsum(c.f("da0"), BZ, d, G("stem_b"));
+  c.gemm((int)BZ, L, d, enf_mat(c.f("da0"), d), enf_mat(w->stem_w, 1, d), enf_mat(da, L));
+  c.launches += enf_launch_latent_record_bwd(st, D, p, c.f("g_lam"), dp);
+  if (dsigma) {
+    if (cudaMemcpyAsync(dsigma, c.f("g_sigma"), BZ * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(ENF_ERR_CUDA, "copy of dsigma failed");
+  }
+
+  // ---- W backward: unfold the folded-weight gradients --------------------------------------------------------
+  if (dW) {
+    c.gemm(d, d, Hd, enf_mat(c.f("gf_A_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_wf"), d));
+    c.gemm(d, Hd, d, enf_mat(w->q_wf, 1, d), enf_mat(c.f("gf_A_q"), Hd), enf_mat(G("wq"), Hd));
+    c.launches += enf_launch_add_outer(st, G("wq"), Hd, w->q_bf, c.f("gf_c_q"), d, Hd);
+    c.gemm(1, d, Hd, enf_mat(c.f("gf_c_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_bf"), d));
+    c.gemm(d, d, d, enf_mat(c.f("gf_Wp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_wf"), d));
+    c.gemm(d, d, d, enf_mat(w->v_wf, 1, d), enf_mat(c.f("gf_Wp"), d), enf_mat(G("fv_w1"), d));
+    c.launches += enf_launch_add_outer(st, G("fv_w1"), d, w->v_bf, c.f("gf_bp"), d, d);
+    c.gemm(1, d, d, enf_mat(c.f("gf_bp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_bf"), d));
+    c.launches += enf_launch_rowdot(st, w->fv_w2, c.f("gf_W2g"), G("fv_g"), d, 2 * Hd);
+    c.launches += enf_launch_mul_rows(st, G("fv_w2"), c.f("gf_W2g"), w->fv_g, d, 2 * Hd, w->fv_beta, c.f("gf_b2g"));
+    c.gemm(1, d, 2 * Hd, enf_mat(c.f("gf_b2g"), 2 * Hd), enf_mat(w->fv_w2, 1, 2 * Hd), enf_mat(G("fv_beta"), d));
+    c.launches += enf_launch_rowdot(st, w->mx_w2, c.f("gf_M2g"), G("mx_g"), d, d);
+    c.launches += enf_launch_mul_rows(st, G("mx_w2"), c.f("gf_M2g"), w->mx_g, d, d, w->mx_beta, c.f("gf_c2g"));
+    c.gemm(1, d, d, enf_mat(c.f("gf_c2g"), d), enf_mat(w->mx_w2, 1, d), enf_mat(G("mx_beta"), d));
+
+    // scatter the internal leaves to the caller's EnfWeightGrads (bq, fv_b1, fv_b2, mx_b2 are the folded biases' grads)
+    LeafCopy t;
+    size_t n[ENF_NUM_WEIGHT_LEAVES];
+    leaf_sizes(D, rl.I, n);
+    float* const* dst = reinterpret_cast<float* const*>(dW);
+    int maxn = 0;
+    for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) {
+      const char* nm = kLeafNames[i];
+      const float* src = G(nm);
+      if (!strcmp(nm, "bq")) src = c.f("gf_c_q");
+      else if (!strcmp(nm, "fv_b1")) src = c.f("gf_bp");
+      else if (!strcmp(nm, "fv_b2")) src = c.f("gf_b2g");
+      else if (!strcmp(nm, "mx_b2")) src = c.f("gf_c2g");
+      t.src[i] = src; t.dst[i] = dst[i]; t.n[i] = (int)n[i];
+      if ((int)n[i] > maxn) maxn = (int)n[i];
+    }
+    int bx = (maxn + 255) / 256; if (bx > 64) bx = 64;
+    copy_leaves_kernel<<<dim3(bx, ENF_NUM_WEIGHT_LEAVES), 256, 0, st>>>(t);
+    c.launches += 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing bwd: ") + cudaGetErrorString(e));
+  g_launches = c.launches;
+  return ENF_OK;
+}
+
+}  // extern "C"

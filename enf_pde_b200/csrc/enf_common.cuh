@@ -1,0 +1,132 @@
+// Shared definitions for the ENF B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/enf_b200.h"
+
+#define ENF_F_XI 8    // width of the per-query feature record xi
+#define ENF_R_LAM 7   // rows of the per-latent pose record Lam (<= 6 invariant rows + 1 window row)
+#define ENF_LAM_SIZE (ENF_R_LAM * ENF_F_XI)
+
+enum { ENF_ROW_DOT = 0, ENF_ROW_SQDIST = 1, ENF_ROW_SQDIST_SQRT = 2 };
+enum { ENF_WIN_NONE = 0, ENF_WIN_NP = 1, ENF_WIN_PER = 2, ENF_WIN_SPH = 3 };
+
+// How the hot kernels evaluate invariants: u_r = post_r(row_r(Lam[z], xi[c])) (DESIGN.md "Invariant records").
+struct EnfRecordLayout {
+  int I;          // invariant width
+  int row_kind;   // kind of the invariant rows (all rows of one invariant share it)
+  int win_kind;   // ENF_WIN_*
+  int win_row;    // row of Lam holding the window's record (== I), or -1 when the window reads u[0]
+  int nsq;        // components compared by SQDIST rows
+  int P;          // raw pose width
+};
+
+__host__ __device__ inline EnfRecordLayout enf_record_layout(int kind, int Dx, int use_window) {
+  EnfRecordLayout r;
+  r.row_kind = ENF_ROW_DOT; r.nsq = Dx; r.win_row = -1;
+  int win = ENF_WIN_NP;
+  switch (kind) {
+    case ENF_INV_REL_POS: r.I = Dx; r.P = Dx; break;
+    case ENF_INV_NORM_REL_POS: r.I = 1; r.P = Dx; r.row_kind = ENF_ROW_SQDIST_SQRT; break;
+    case ENF_INV_ABS_POS: r.I = Dx; r.P = Dx; break;
+    case ENF_INV_REL_POS_PERIODIC: r.I = 4; r.P = 2; win = ENF_WIN_PER; break;
+    case ENF_INV_PONITA: r.I = 2; r.P = 3; r.nsq = 2; break;
+    case ENF_INV_POLAR_PERIODIC: r.I = 1; r.P = 2; win = ENF_WIN_SPH; break;
+    case ENF_INV_LATITUDE_PERIODIC: r.I = 4; r.P = 2; win = ENF_WIN_SPH; break;
+    case ENF_INV_BALL: r.I = 5; r.P = 4; win = ENF_WIN_SPH; break;
+    case ENF_INV_BALL_LAT: r.I = 6; r.P = 4; win = ENF_WIN_SPH; break;
+    default: r.I = -1; r.P = -1; break;
+  }
+  r.win_kind = use_window ? win : ENF_WIN_NONE;
+  if (r.win_kind == ENF_WIN_NP) r.win_row = r.I;
+  if (r.win_kind == ENF_WIN_SPH && kind != ENF_INV_POLAR_PERIODIC) r.win_row = r.I;
+  return r;
+}
+
+// jax.nn.gelu(approximate=True)
+__device__ __forceinline__ float enf_gelu(float x) {
+  const float c = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float enf_gelu_grad(float x) {
+  const float c = 0.7978845608028654f;
+  float x2 = x * x;
+  float t = tanhf(c * (x + 0.044715f * x * x2));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x2);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- generic strided GEMM (enf_gemm.cu) ------------------------------------------------------
+struct EnfMat {            // a strided 2-D view with an optional batch stride
+  const float* p;
+  int64_t rs, cs, bs;
+};
+static inline EnfMat enf_mat(const float* p, int64_t rs, int64_t cs = 1, int64_t bs = 0) {
+  EnfMat m; m.p = p; m.rs = rs; m.cs = cs; m.bs = bs; return m;
+}
+struct EnfGemmOpts {
+  int batch = 1;
+  const float* bias = nullptr;      // [N], added once
+  int64_t bias_bs = 0;              // batch stride of bias
+  int act_a = 0;                    // 1: A elements pass through gelu on load
+  const float* mul_gelu_grad = nullptr;  // epilogue: result *= gelu'(aux[m,n]) (aux has C's strides)
+  int accumulate = 0;               // 1: atomicAdd into C (C must hold the running sum); enables split-K
+  float alpha = 1.0f;
+};
+// C[M,N] (+)= alpha * act(A)[M,K] * B[K,N] (+ bias) (* gelu'(aux)); returns number of kernels launched.
+int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o);
+
+// ---- small stage kernels (enf_stages.cu) -------------------------------------------------------
+int enf_launch_rowscale(cudaStream_t st, const float* W, const float* g, float* out, int rows, int cols);
+int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t ld, float* out, const float* mul, int64_t ld_mul);
+int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
+                      float* out_core, float* out_affine, float* rstd, int gelu_in);
+int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,
+                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in);
+int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi);
+int enf_launch_latent_record(cudaStream_t st, const EnfDesc& d, const float* p, float* lam);
+int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float* p, const float* dlam, float* dp);
+int enf_launch_weff(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
+                    float* Weff, float* beff);
+int enf_launch_weff_bwd(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
+                        const float* dWeff, const float* dbeff, float* dW2g, float* db2g, float* dv0);
+int enf_launch_add_outer(cudaStream_t st, float* C, int64_t ldc, const float* u, const float* v, int M, int N);
+int enf_launch_rowdot(cudaStream_t st, const float* A, const float* Bm, float* out, int rows, int cols);
+int enf_launch_mul_rows(cudaStream_t st, float* out, const float* A, const float* g, int rows, int cols,
+                        const float* add_outer_u, const float* add_outer_v);
+int enf_launch_transpose(cudaStream_t st, const float* in, float* out, int rows, int cols, int batch);
+
+// ---- fused pair kernels (enf_pairs_simt.cu) ------------------------------------------------------
+struct EnfPairParams {
+  int B, C, Z, H, I;
+  int row_kind, win_kind, win_row, nsq;
+  const float* xi;  int64_t xi_bs;           // [Bx, C, 8]
+  const float* lam;                          // [B, Z, 7, 8]
+  const float* sigma;                        // [B, Z] or null
+  const float* q_omega; const float* v_omega;  // [I, d/2]
+  const float* q_w1; const float* q_b1;      // [d, d], [d]
+  const float* v_w1; const float* v_b1;
+  const float* Wp; const float* bp;          // folded linear_final_v o FFN_v.Dense_0
+  const float* U; const float* kappa;        // [B,Z,H,d], [B,Z,H]
+  const float* W3; const float* b3;          // [B,Z,H,d,d], [B,Z,H,d]
+  float* nbar; float* lse;                   // [B,C,H,d], [B,C,H]
+  // backward only
+  const float* q_w1T; const float* v_w1T; const float* WpT; const float* W3T;   // transposed copies
+  const float* dnbar;                        // [B,C,H,d]
+  float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // accumulated (atomics)
+  float* g_W3; float* g_b3; float* g_U; float* g_kappa; float* g_lam; float* g_sigma;      // per-latent, accumulated
+};
+int enf_launch_pairs_fwd_simt(cudaStream_t st, int d, const EnfPairParams& p);
+int enf_launch_pairs_bwd_simt(cudaStream_t st, int d, const EnfPairParams& p);

@@ -512,6 +512,7 @@ class Folded:
         G.update(G2); G.update(G3)
         G.update(self.weights_unfold_bwd(Gf))
         G["q_omega"] = torch.zeros_like(self.w["q_omega"]); G["v_omega"] = torch.zeros_like(self.w["v_omega"])
+        self.G, self.Gf, self.GL = G, Gf, GL
         return G, dp, da, GL["sigma"]
 
 

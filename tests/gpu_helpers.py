@@ -1,0 +1,91 @@
+"""GPU-side helpers: call the C ABI directly (ctypes) and compare every internal stage buffer of the
+library's workspace with the float64 folded model, so a failing parity test names the first stage
+that diverges."""
+import ctypes
+
+import numpy as np
+import torch
+
+from enf_pde_b200 import _lib
+from enf_pde_b200.nef import _weights_struct, params_to_leaves
+from folded_model import Folded, LEAF_PATHS
+from helpers import rel_err
+
+
+def desc_for(cfg, B, C, Z, precision=0):
+    return _lib.EnfDesc(B=B, C=C, Z=Z, d=cfg.num_hidden, H=cfg.num_heads, L=cfg.latent_dim, O=cfg.num_out, Dx=cfg.num_in,
+                        invariant_kind=_lib.INVARIANT_KINDS[cfg.invariant_type], use_window=int(cfg.use_gaussian_window),
+                        precision=precision, reserved=0)
+
+
+def ws_view(lib, desc, ws, name):
+    n = ctypes.c_int64(0)
+    off = lib.enf_debug_ws_offset(ctypes.byref(desc), name.encode(), ctypes.byref(n))
+    assert off >= 0, name
+    return ws[off:off + 4 * n.value].view(torch.float32)
+
+
+def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False):
+    """Run fwd+bwd through the C ABI; return (results dict, per-stage error dict vs the folded fp64 model)."""
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    B, C = x.shape[:2]
+    Z = p.shape[1]
+    desc = desc_for(cfg, B, C, Z)
+    f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+    leaves64 = params_to_leaves(params)
+    leaves = [f32(t) for t in leaves64]
+    xg, pg, ag, sg, dg = f32(x[0] if shared_x else x), f32(p), f32(a), f32(sigma), f32(d_out)
+    nbytes = lib.enf_xattn_workspace_bytes(ctypes.byref(desc))
+    assert nbytes > 0, lib.enf_last_error()
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(B, C, cfg.num_out, device=dev)
+    w = _weights_struct(leaves)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xbs = 0 if shared_x else C * cfg.num_in
+    sig_ptr = ptr(sg) if cfg.use_gaussian_window else ctypes.c_void_p(0)
+    rc = lib.enf_xattn_fwd(ctypes.byref(desc), ctypes.byref(w), ptr(xg), xbs, ptr(pg), ptr(ag), sig_ptr, ptr(out), ptr(ws), nbytes, st)
+    assert rc == 0, lib.enf_last_error()
+    torch.cuda.synchronize()
+    grads = [torch.full_like(t, float("nan")) for t in leaves]
+    gw = _weights_struct(grads)
+    dp = torch.empty_like(pg); da = torch.empty_like(ag); dsig = torch.empty_like(sg)
+    # snapshot forward buffers before the backward recycles some of them
+    names_fwd = ["xi", "lam", "A_q", "c_q", "Wp", "bp", "W2g", "b2g", "M2g", "c2g", "a0", "acore", "ahat", "k", "v0", "U",
+                 "kappa", "Weff", "beff", "W3", "b3", "nbar", "lse", "y", "y2", "e1", "e3c", "e3", "fo", "o1p", "o2p"]
+    snap = {n: ws_view(lib, desc, ws, n).clone() for n in names_fwd}
+    rc = lib.enf_xattn_bwd(ctypes.byref(desc), ctypes.byref(w), ptr(xg), xbs, ptr(pg), ptr(ag), sig_ptr, ptr(dg), ctypes.byref(gw),
+                           ptr(dp), ptr(da), ptr(dsig), ptr(ws), nbytes, st)
+    assert rc == 0, lib.enf_last_error()
+    torch.cuda.synchronize()
+    names_bwd = ["g_W3", "g_b3", "g_U", "g_kappa", "g_sigma", "gf_A_q", "gf_c_q", "gf_Wp", "gf_bp", "gf_W2g", "gf_b2g",
+                 "gf_M2g", "gf_c2g"]
+    snap.update({n: ws_view(lib, desc, ws, n).clone() for n in names_bwd})
+
+    # float64 folded model
+    m = Folded(cfg, params)
+    xe = x if not shared_x else x[:1].expand(B, *x.shape[1:])
+    out_ref = m.forward(xe.double(), p.double(), a.double(), sigma.double())
+    G, dp_ref, da_ref, ds_ref = m.backward(xe.double(), p.double(), a.double(), sigma.double(), d_out.double())
+    ref = dict(xi=m.xi[:1] if shared_x else m.xi, lam=m.L["Lam"], A_q=m.f["A_q"], c_q=m.f["c_q"], Wp=m.f["Wp"], bp=m.f["bp"],
+               W2g=m.f["W2g"], b2g=m.f["b2g"], M2g=m.f["M2g"], c2g=m.f["c2g"], a0=m.L["a0"], acore=m.L["ahat_core"],
+               ahat=m.L["ahat"], k=m.L["k"], v0=m.L["v0"], U=m.L["U"], kappa=m.L["kappa"], Weff=m.L["Weff"], beff=m.L["beff"],
+               W3=m.L["W3"], b3=m.L["b3"], nbar=m.S["nbar"], lse=m.S["lse"], y=m.T["y"], y2=m.T["y2"], e1=m.T["e1"],
+               e3c=m.T["e3c"], e3=m.T["e3"], fo=m.T["fo"], o1p=m.T["o1p"], o2p=m.T["o2p"],
+               g_W3=m.GL["W3"], g_b3=m.GL["b3"], g_U=m.GL["U"], g_kappa=m.GL["kappa"], g_sigma=m.GL["sigma"],
+               gf_A_q=m.Gf["A_q"], gf_c_q=m.Gf["c_q"], gf_Wp=m.Gf["Wp"], gf_bp=m.Gf["bp"], gf_W2g=m.Gf["W2g"],
+               gf_b2g=m.Gf["b2g"], gf_M2g=m.Gf["M2g"], gf_c2g=m.Gf["c2g"])
+    errs = {}
+    for n in names_fwd + names_bwd:
+        r = ref[n].reshape(-1)
+        errs[n] = rel_err(snap[n].cpu()[: r.numel()], r)
+    errs["out"] = rel_err(out.cpu(), out_ref)
+    errs["dp"] = rel_err(dp.cpu(), dp_ref)
+    errs["da"] = rel_err(da.cpu(), da_ref)
+    errs["dsigma"] = rel_err(dsig.cpu(), ds_ref) if cfg.use_gaussian_window else 0.0
+    gscale = max(float(G[k].abs().max()) for k in G)
+    for leaf, g in zip(_lib.LEAVES, grads):
+        errs["gw_" + leaf] = float((g.cpu().double() - G[leaf]).abs().max()) / max(gscale, 1e-30)
+    res = dict(out=out, dp=dp, da=da, dsigma=dsig, grads=grads, launches=lib.enf_last_launch_count())
+    return res, errs

@@ -1,0 +1,90 @@
+"""CPU-side checks of the C-ABI library and the host mirror (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import enf_pde_b200 as E
+from enf_pde_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = E.load_library()
+    header = open(os.path.join(ROOT, "include", "enf_b200.h")).read()
+    declared = set(re.findall(r"\b(enf_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.enf_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    header = open(os.path.join(ROOT, "include", "enf_b200.h")).read()
+    body = header.split("typedef struct EnfWeights {")[1].split("} EnfWeights;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\*\s*([a-z0-9_]+)", body)
+    assert tuple(names) == _lib.LEAVES
+    assert len(_lib.LEAVES) == 46 and set(_lib.LEAF_PATHS) == set(_lib.LEAVES)
+    assert ctypes.sizeof(_lib.EnfDesc) == 48 and ctypes.sizeof(_lib.EnfWeights) == 46 * 8
+
+
+def test_invariant_dims_match_reference_classes():
+    lib = E.load_library()
+    import types
+    for t, kind in _lib.INVARIANT_KINDS.items():
+        dx = 3 if t.startswith("ball") else 2
+        inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=t, num_in=dx))
+        assert lib.enf_invariant_dim(kind, dx) == inv.dim
+        assert lib.enf_pose_dim(kind, dx) == inv.pose_dim
+    assert lib.enf_invariant_dim(99, 2) < 0
+
+
+def test_bad_descriptions_are_rejected_without_a_gpu():
+    lib = E.load_library()
+    ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, reserved=0)
+    assert lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**ok))) > 0
+    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7)):
+        d = _lib.EnfDesc(**{**ok, **bad})
+        assert lib.enf_xattn_workspace_bytes(ctypes.byref(d)) == 0, bad
+        assert lib.enf_last_error() != b""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_fails_loudly_without_a_device():
+    """no CPU fallback: the public API refuses CPU tensors, and the C ABI reports ENF_ERR_NO_DEVICE."""
+    import types
+    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type="rel_pos_periodic", num_in=2))
+    nef = E.EquivariantCrossAttentionNeF(32, 2, 0, 1, 8, inv)
+    p, a, s = E.init_latents(inv, 1, 4, 8)
+    x = torch.zeros(1, 5, 2)
+    params = nef.init(0, x, p, a, s)
+    with pytest.raises(RuntimeError):
+        nef.apply(params, x, p, a, s)
+    lib = E.load_library()
+    d = _lib.EnfDesc(B=1, C=5, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, reserved=0)
+    w = _lib.EnfWeights(**{n: 16 for n in _lib.LEAVES})
+    rc = lib.enf_xattn_fwd(ctypes.byref(d), ctypes.byref(w), 16, 10, 16, 16, 16, 16, 256, 1 << 40, None)
+    assert rc == -6 and b"no CUDA device" in lib.enf_last_error()
+
+
+def test_init_tree_matches_reference_names_and_shapes():
+    import types
+    from helpers import load_golden
+    from oracle import enf_ref as R
+    cfg, params, _, rec = load_golden("ball")
+    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type="ball", num_in=3))
+    nef = E.EquivariantCrossAttentionNeF(cfg.num_hidden, cfg.num_heads, 0, cfg.num_out, cfg.latent_dim, inv,
+                                         embedding_freq_multiplier=cfg.embedding_freq_multiplier)
+    ours = R.tree_flatten(nef.init(0, rec["x"], rec["p"], rec["a"], rec["sigma"])["params"])
+    theirs = R.tree_flatten(params["params"])
+    assert sorted(ours) == sorted(theirs)
+    for k in ours:
+        assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
+    # round trip through the flat leaf order of the C ABI
+    leaves = E.params_to_leaves({"params": R.tree_unflatten(ours)})
+    back = R.tree_flatten(E.leaves_to_params(leaves)["params"])
+    assert all(back[k] is ours[k] for k in ours)

@@ -1,0 +1,166 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on a B200.  `-m gpu`.
+
+Tolerance: BASELINE.json's fp32 bucket, 1e-4, on the metric max|got-want| / max|want| (helpers.rel_err),
+for the decoded field and for the latent gradients; weight gradients are held to the same number
+relative to the largest weight-gradient entry."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import enf_ref as R
+from helpers import golden_names, load_golden, rel_err, make_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _nef_for(cfg, precision="fp32"):
+    import enf_pde_b200 as E
+    import types
+    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg.invariant_type, num_in=cfg.num_in))
+    return E.EquivariantCrossAttentionNeF(
+        num_hidden=cfg.num_hidden, num_heads=cfg.num_heads, num_layers=0, num_out=cfg.num_out, latent_dim=cfg.latent_dim,
+        cross_attn_invariant=inv, self_attn_invariant=inv, embedding_type="rff",
+        embedding_freq_multiplier=cfg.embedding_freq_multiplier, condition_value_transform=True,
+        use_gaussian_window=cfg.use_gaussian_window, precision=precision)
+
+
+def _to_cuda(tree):
+    return R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous().requires_grad_(True), tree)
+
+
+def _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out):
+    nef = _nef_for(cfg)
+    P = _to_cuda(params)
+    pg = p.to("cuda", torch.float32).requires_grad_(True)
+    ag = a.to("cuda", torch.float32).requires_grad_(True)
+    sg = sigma.to("cuda", torch.float32).requires_grad_(True) if cfg.use_gaussian_window else None
+    out = nef.apply(P, x.to("cuda", torch.float32), pg, ag, sg)
+    out.backward(d_out.to("cuda", torch.float32))
+    g = R.tree_map(lambda t: t.grad, P)
+    return out.detach(), g, pg.grad, ag.grad, (sg.grad if sg is not None else None)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_stage_by_stage(name):
+    """every internal stage buffer against the float64 folded model (names the first diverging stage)."""
+    from gpu_helpers import run_stages
+    cfg, params, _, rec = load_golden(name)
+    _, errs = run_stages(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
+    bad = {k: v for k, v in errs.items() if not (v < TOL)}
+    assert not bad, f"stages over tolerance (in pipeline order): {bad}"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_through_public_api(name):
+    """reference-source golden outputs + oracle gradients, through EquivariantCrossAttentionNeF.apply + autograd."""
+    cfg, params, _, rec = load_golden(name)
+    out_ref, dth_ref, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
+    assert rel_err(out, rec["out"]) < TOL
+    assert rel_err(dp, dp_ref) < TOL
+    assert rel_err(da, da_ref) < TOL
+    if cfg.use_gaussian_window:
+        assert rel_err(ds, ds_ref) < TOL
+    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
+    scale = max(float(v.abs().max()) for v in fr.values())
+    for k in fr:
+        err = float((fg[k].double().cpu() - fr[k]).abs().max()) / scale
+        assert err < TOL, (k, err)
+
+
+CASES = [
+    # (name, cfg kwargs, B, C, Z, polar_grid)    sizes the fp64 oracle finishes in seconds
+    ("ns_d128", dict(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                     embedding_freq_multiplier=(0.05, 0.1)), 2, 75, 16, None),
+    ("plane_d64", dict(num_in=2, num_hidden=64, num_heads=2, num_out=1, latent_dim=16, invariant_type="ponita",
+                       embedding_freq_multiplier=(0.05, 0.01)), 3, 100, 25, None),
+    ("sphere_d16", dict(num_in=2, num_hidden=16, num_heads=2, num_out=1, latent_dim=4, invariant_type="polar_periodic",
+                        embedding_freq_multiplier=(0.01, 0.01), use_gaussian_window=False), 2, 130, 18, (6, 3)),
+    ("sw_d128", dict(num_in=2, num_hidden=128, num_heads=2, num_out=3, latent_dim=32, invariant_type="latitude_periodic",
+                     embedding_freq_multiplier=(0.05, 0.2)), 1, 90, 18, (6, 3)),
+    ("ihc_d32_h3", dict(num_in=3, num_hidden=32, num_heads=3, num_out=1, latent_dim=32, invariant_type="ball",
+                        embedding_freq_multiplier=(0.2, 0.5)), 2, 200, 40, None),
+    ("ragged_tile", dict(num_in=2, num_hidden=32, num_heads=4, num_out=2, latent_dim=8, invariant_type="rel_pos",
+                         embedding_freq_multiplier=(0.2, 0.3)), 2, 33, 1, None),       # C % 32 = 1, single latent
+    ("one_query", dict(num_in=1, num_hidden=16, num_heads=1, num_out=1, latent_dim=1, invariant_type="norm_rel_pos",
+                       embedding_freq_multiplier=(0.2, 0.3)), 1, 1, 4, None),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_config_shapes_against_oracle(case):
+    """the reference configs' hidden sizes / invariants (reduced C, Z), seeded synthetic inputs."""
+    _, kw, B, C, Z, grid = case
+    cfg = R.EnfConfig(**kw)
+    params, x, p, a, sigma, d_out = make_case(cfg, B, C, Z, seed=3, polar_grid=grid)
+    out_ref, dth_ref, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    assert rel_err(out, out_ref) < TOL
+    assert rel_err(dp, dp_ref) < TOL
+    assert rel_err(da, da_ref) < TOL
+    if cfg.use_gaussian_window:
+        assert rel_err(ds, ds_ref) < TOL
+    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
+    scale = max(float(v.abs().max()) for v in fr.values())
+    for k in fr:
+        assert float((fg[k].double().cpu() - fr[k]).abs().max()) / scale < TOL, k
+
+
+def test_shared_coordinate_grid_matches_per_field_copy():
+    """x passed once with batch stride 0 (pde_trainer.py:197 broadcasts one grid) == explicit copies."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=32, num_heads=2, num_out=1, latent_dim=8, invariant_type="rel_pos_periodic")
+    params, x, p, a, sigma, d_out = make_case(cfg, 3, 70, 9, seed=5)
+    x = x[:1].expand(3, -1, -1)
+    o1, g1, dp1, da1, ds1 = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out)                # stride-0 view
+    o2, g2, dp2, da2, ds2 = _api_fwd_bwd(cfg, params, x.contiguous(), p, a, sigma, d_out)
+    assert torch.equal(o1, o2)
+    assert rel_err(dp1, dp2) < 1e-5 and rel_err(da1, da2) < 1e-5
+
+
+def test_full_size_ns_properties():
+    """BASELINE config 2 at full size (B=32, C=4096, Z=64, d=128, H=2): size-independent properties.
+    (1) queries are independent: a random subset of rows equals the oracle evaluated on that subset;
+    (2) a cotangent supported on that subset gives the oracle's latent gradients for the subset;
+    (3) permuting the latents leaves the decoded field unchanged;
+    (4) the domain is periodic: x + 2 decodes to the same field."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1))
+    B, C, Z = 32, 4096, 64
+    params, _, p, a, sigma, _ = make_case(cfg, B, 8, Z, seed=7)
+    x = R.make_coords(cfg, (64, 64))[None].expand(B, -1, -1)
+    g = torch.Generator().manual_seed(11)
+    sub = torch.randperm(C, generator=g)[:24]
+    bsel = [0, 13, 31]
+    d_out = torch.zeros(B, C, 1, dtype=torch.float64)
+    d_out[:, sub] = torch.randn(B, 24, 1, generator=g, dtype=torch.float64)
+    out, _, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    out_ref, _, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x[bsel][:, sub], p[bsel], a[bsel], sigma[bsel], d_out[bsel][:, sub])
+    assert rel_err(out[bsel][:, sub], out_ref) < TOL
+    assert rel_err(dp[bsel], dp_ref) < TOL and rel_err(da[bsel], da_ref) < TOL and rel_err(ds[bsel], ds_ref) < TOL
+    nef = _nef_for(cfg)
+    P = _to_cuda(params)
+    f = lambda t: t.to("cuda", torch.float32)
+    with torch.no_grad():
+        perm = torch.randperm(Z, generator=g)
+        o_perm = nef.apply(P, f(x), f(p[:, perm]), f(a[:, perm]), f(sigma[:, perm]))
+        o_shift = nef.apply(P, f(x + 2.0), f(p), f(a), f(sigma))
+    assert rel_err(o_perm, out) < 2e-5
+    assert rel_err(o_shift, out) < 2e-5
+
+
+def test_error_paths():
+    import enf_pde_b200 as E
+    cfg = R.EnfConfig(num_in=2, num_hidden=32, num_heads=2, num_out=1, latent_dim=8, invariant_type="rel_pos_periodic")
+    params, x, p, a, sigma, d_out = make_case(cfg, 1, 8, 4)
+    nef = _nef_for(cfg)
+    P = _to_cuda(params)
+    f = lambda t: t.to("cuda", torch.float32)
+    with pytest.raises(TypeError):
+        nef.apply(P, f(x), f(p), f(a), None)                       # window on, sigma missing
+    with pytest.raises(ValueError):
+        nef.apply(P, f(x), f(p)[:, :, :1], f(a), f(sigma))         # wrong pose width
+    with pytest.raises(RuntimeError):
+        nef.apply(P, x.float(), f(p), f(a), f(sigma))              # CPU tensor: no CPU path
+    with pytest.raises(NotImplementedError):
+        E.EquivariantCrossAttentionNeF(32, 2, 1, 1, 8, nef.cross_attn_invariant)   # num_layers > 0
