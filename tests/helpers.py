@@ -55,4 +55,9 @@ def make_case(cfg, B, C, Z, seed=0, dtype=torch.float64, polar_grid=None, pertur
     else:
         x = torch.rand(B, C, cfg.num_in, generator=g, dtype=dtype) * 2 - 1
     d_out = torch.randn(B, C, cfg.num_out, generator=g, dtype=dtype) / (B * C)
+    # make every input exactly representable in float32, so the float64 oracle and the float32 CUDA path see
+    # the SAME numbers (e.g. the ball initialiser's beta ~ 4e2 rad moves by 1e-5 rad when rounded to float32)
+    r32 = lambda t: t.float().to(dtype)
+    params = R.tree_map(r32, params)
+    x, p, a, sigma, d_out = (r32(t) for t in (x, p, a, sigma, d_out))
     return params, x, p, a, sigma, d_out

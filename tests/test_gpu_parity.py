@@ -100,7 +100,12 @@ def test_config_shapes_against_oracle(case):
     assert rel_err(dp, dp_ref) < TOL
     assert rel_err(da, da_ref) < TOL
     if cfg.use_gaussian_window:
-        assert rel_err(ds, ds_ref) < TOL
+        if C == 1:
+            # a single query: sum_z ds = 0 makes dsigma a difference of O(|d_out|) terms that cancel to ~1e-5 of
+            # their size; float32 (the reference's dtype too) resolves it to eps * |d_out|, not to 1e-4 of the result
+            assert float((ds.double().cpu() - ds_ref).abs().max()) < 2e-7 * float(d_out.abs().max())
+        else:
+            assert rel_err(ds, ds_ref) < TOL
     fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
     scale = max(float(v.abs().max()) for v in fr.values())
     for k in fr:
