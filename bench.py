@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--config", default="ns64", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="fp32: FMA kernels (<=1e-4 bucket); bf16: tcgen05 kernels with 16-bit operands (<=2e-3 bucket)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +216,7 @@ def main():
 
     inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
     nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True,
-                                         cfg["window"], precision="fp32")
+                                         cfg["window"], precision=args.precision)
     B, Z = cfg["B"], cfg["Z"]
     gen = torch.Generator().manual_seed(1234 + rank)
     p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])
@@ -340,8 +342,9 @@ def main():
     q_total = world * B * C * args.steps
     line = {"metric": METRIC, "value": q_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {**workload, "global_fields": world * B, "parallelism": f"dp{world} over fields",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate (tcgen05) + f32",
+            "data": "synthetic",
+            "config": {**workload, "precision": args.precision, "global_fields": world * B, "parallelism": f"dp{world} over fields",
                        "l2": "per-step working set (~2.5 GB workspace at ns64) >> 126 MB L2; no explicit flush",
                        "step": "fwd + bwd incl. all weight grads" + (" + NCCL all-reduce of weight grads" if world > 1 else ""),
                        "step_tflop_contract": total_flop_step / 1e12},

@@ -83,6 +83,10 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("lam", BZ * ENF_LAM_SIZE); Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
   Y.add("k", BZ * Hd); Y.add("v0", BZ * Hd); Y.add("U", BZ * Hd); Y.add("kappa", BZ * H);
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
+  if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
+    Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
+    Y.add("cw3", BZ * Hd); Y.add("slog", BC * (size_t)D.Z * H);
+  }
   Y.add("xi", BC * ENF_F_XI);
   Y.add("nbar", BC * Hd); Y.add("lse", BC * H);
   Y.add("y", BC * Hd); Y.add("y2", BC * Hd); Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
@@ -235,7 +239,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
   if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
   if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
-  if (D.precision != ENF_PREC_FP32) return fail(ENF_ERR_UNSUPPORTED, "this build implements precision ENF_PREC_FP32 only");
+  const bool use_tc = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);   // other shapes: fp32 kernels
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
   Layout Y = make_layout(D, rl);
@@ -277,9 +281,34 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   // ---- X, P ---------------------------------------------------------------------------------------
   c.launches += enf_launch_query_features(st, D, x, x_batch_stride, Bx, c.f("xi"));
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
-  prof_mark(0, 0, st);
-  int nl = enf_launch_pairs_fwd_simt(st, d, pp);
-  prof_mark(0, 1, st);
+  int nl;
+  if (use_tc) {
+    // operand images: bf16, pre-swizzled, of the TRANSPOSED weights ([out][in]) = K-major B tiles
+    c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
+    c.launches += enf_launch_transpose(st, w->v_w1, c.f("v_w1T"), d, d, 1);
+    c.launches += enf_launch_transpose(st, c.f("Wp"), c.f("WpT"), d, d, 1);
+    c.launches += enf_launch_transpose(st, c.f("W3"), c.f("W3T"), d, d, (int)(BZ * H));
+    c.launches += enf_launch_weight_image(st, c.f("q_w1T"), c.f("img_q_w1"), nullptr, d, d, 1);
+    c.launches += enf_launch_weight_image(st, c.f("v_w1T"), c.f("img_v_w1"), nullptr, d, d, 1);
+    c.launches += enf_launch_weight_image(st, c.f("WpT"), c.f("img_Wp"), nullptr, d, d, 1);
+    c.launches += enf_launch_weight_image(st, c.f("W3T"), c.f("img_W3"), c.f("cw3"), d, d, (int)(BZ * H));
+    EnfPairTcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = D.B; tp.C = D.C; tp.Z = D.Z; tp.I = rl.I;
+    tp.row_kind = rl.row_kind; tp.win_kind = rl.win_kind; tp.win_row = rl.win_row; tp.nsq = rl.nsq;
+    tp.xi = pp.xi; tp.xi_bs = pp.xi_bs; tp.lam = pp.lam; tp.sigma = pp.sigma;
+    tp.q_omega = w->q_omega; tp.v_omega = w->v_omega; tp.q_b1 = w->q_b1; tp.v_b1 = w->v_b1; tp.bp = c.f("bp");
+    tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
+    tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3"); tp.cw3 = c.f("cw3");
+    tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = c.f("slog");
+    prof_mark(0, 0, st);
+    nl = enf_launch_pairs_fwd_tc(st, d, H, tp);
+    prof_mark(0, 1, st);
+  } else {
+    prof_mark(0, 0, st);
+    nl = enf_launch_pairs_fwd_simt(st, d, pp);
+    prof_mark(0, 1, st);
+  }
   if (nl < 0) return fail(ENF_ERR_CUDA, "pair forward kernel could not be configured");
   c.launches += nl;
 
@@ -316,7 +345,6 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (!w || !x || !p || !a || !d_out || !dp || !da || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
   if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
   if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set");
-  if (D.precision != ENF_PREC_FP32) return fail(ENF_ERR_UNSUPPORTED, "this build implements precision ENF_PREC_FP32 only");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_fwd_state.find(workspace);
@@ -377,6 +405,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
   pp.q_w1T = c.f("q_w1T"); pp.v_w1T = c.f("v_w1T"); pp.WpT = c.f("WpT"); pp.W3T = c.f("W3T");
   pp.dnbar = c.f("s0");
+  if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) pp.slog = c.f("slog");
   pp.g_q_w1 = G("q_w1"); pp.g_q_b1 = G("q_b1"); pp.g_v_w1 = G("v_w1"); pp.g_v_b1 = G("v_b1");
   pp.g_Wp = c.f("gf_Wp"); pp.g_bp = c.f("gf_bp");
   pp.g_W3 = c.f("g_W3"); pp.g_b3 = c.f("g_b3"); pp.g_U = c.f("g_U"); pp.g_kappa = c.f("g_kappa");

@@ -108,6 +108,8 @@ int enf_launch_mul_rows(cudaStream_t st, float* out, const float* A, const float
                         const float* add_outer_u, const float* add_outer_v);
 int enf_launch_transpose(cudaStream_t st, const float* in, float* out, int rows, int cols, int batch);
 
+int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch);
+
 // ---- fused pair kernels (enf_pairs_simt.cu) ------------------------------------------------------
 struct EnfPairParams {
   int B, C, Z, H, I;
@@ -125,8 +127,26 @@ struct EnfPairParams {
   // backward only
   const float* q_w1T; const float* v_w1T; const float* WpT; const float* W3T;   // transposed copies
   const float* dnbar;                        // [B,C,H,d]
+  const float* slog;                         // [B,C,Z,H] logits saved by the tensor-core forward (or null: recompute)
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // accumulated (atomics)
   float* g_W3; float* g_b3; float* g_U; float* g_kappa; float* g_lam; float* g_sigma;      // per-latent, accumulated
 };
 int enf_launch_pairs_fwd_simt(cudaStream_t st, int d, const EnfPairParams& p);
 int enf_launch_pairs_bwd_simt(cudaStream_t st, int d, const EnfPairParams& p);
+
+// ---- tensor-core pair kernels (enf_pairs_tc.cu) ----------------------------------------------------
+struct EnfPairTcParams {
+  int B, C, Z, I;
+  int row_kind, win_kind, win_row, nsq;
+  const float* xi;  int64_t xi_bs;
+  const float* lam; const float* sigma;
+  const float* q_omega; const float* v_omega;
+  const float* q_b1; const float* v_b1; const float* bp;
+  const uint8_t* img_q_w1; const uint8_t* img_v_w1; const uint8_t* img_Wp;   // bf16 operand images of W^T ([n][k])
+  const uint8_t* img_W3;                     // [B*Z*H] images of W3^T
+  const float* cw3;                          // [B,Z,H,d] column sums of the bf16-rounded W3
+  const float* U; const float* kappa; const float* b3;
+  float* nbar; float* lse; float* slog;      // slog [B,C,Z,H]: logits incl. window (saved for the backward), may be null
+};
+bool enf_pairs_fwd_tc_supported(int d, int H);
+int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p);

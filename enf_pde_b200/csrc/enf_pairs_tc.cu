@@ -1,0 +1,429 @@
+// Fused (query, latent)-pair FORWARD kernel on the 5th-gen tensor cores (EnfPrecision::ENF_PREC_BF16).
+//
+// One CTA owns 128 coordinate queries of one field (= the 128 TMEM lanes / UMMA M) and loops over the
+// field's Z latents.  Per latent the chain of equivariant_cross_attention.py:86-144 runs as
+//     E0q  gamma_q -> smem A0 (bf16, 128B swizzle)        GEMM1  A0 x W1_q      -> TMEM T0
+//     E0v  gamma_v -> smem A1                             GEMM2  A1 x W1_v      -> TMEM T1
+//     E1   T0: relu, dot with folded U[z,h] -> logits s ; online-softmax statistics
+//     E2   T1: relu -> A0                                 GEMM3  A0 x W'        -> T0
+//     E3   T0: gelu, LN statistics -> A1 (un-normalised)  GEMM4h A1 x W3[z,h]   -> T0 / T1
+//     E4h  Th: LN of E3 applied as a rank-1 correction, gelu, LN, acc_h += p * n      (registers)
+// with tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM) issued by one thread, weights
+// resident in shared memory as pre-swizzled images, the per-latent W3 images streamed by the bulk-copy
+// (TMA) engine, tcgen05.ld feeding the elementwise epilogues, and D/32 threads per query row so that
+// the softmax accumulators (H x d fp32 per row) stay in registers.  Nothing per-pair touches HBM except
+// the logits saved for the backward.  MMA and epilogues overlap where the chain allows it
+// (GEMM1 | E0v, GEMM2 | E1, GEMM3 | softmax update, GEMM4_1 | E4_0).
+#include "enf_common.cuh"
+#include "enf_tc.cuh"
+
+namespace {
+
+constexpr int ROWS = 128;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float x2 = x * x;
+  float t = tanh_fast(x * fmaf(c1, x2, c0));
+  float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int D, int H> struct TcCfg {
+  static constexpr int NQ = D / 32;                    // threads per query row (32 columns each)
+  static constexpr int NT = ROWS * NQ;                 // threads per CTA
+  static constexpr uint32_t WIMG = D * D * 2;          // bytes of one weight image
+  static constexpr uint32_t WBLK = D * 128;            // bytes of one 64-feature block of a weight image
+  static constexpr uint32_t ABLK = ROWS * 128;         // bytes of one 64-feature block of an activation tile
+  static constexpr uint32_t ATILE = (D / 64) * ABLK;
+  static constexpr int TMEM_COLS = 2 * D;              // T0 | T1   (power of two: 128 or 256)
+  // byte offsets inside the 1024-aligned dynamic shared memory
+  static constexpr uint32_t OFF_W = 0;                 // W1_q, W1_v, W' images
+  static constexpr uint32_t OFF_S = 3 * WIMG;          // W3[z,0] stage
+  static constexpr uint32_t OFF_A0 = OFF_S + WIMG;
+  static constexpr uint32_t OFF_A1 = OFF_A0 + ATILE;
+  static constexpr uint32_t OFF_F = OFF_A1 + ATILE;    // float arrays start here
+  // float arrays (counts)
+  static constexpr int F_XI = ROWS * 8, F_LAM = 64, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_CW = H * D, F_BIAS = 3 * D,
+                       F_OM = 2 * 6 * (D / 2), F_SPART = NQ * ROWS * H, F_ST3 = NQ * ROWS * 2, F_ST4 = H * NQ * ROWS * 2;
+  static constexpr int F_TOTAL = F_XI + F_LAM + F_UZ + F_KAP + F_B3 + F_CW + F_BIAS + F_OM + F_SPART + F_ST3 + F_ST4;
+  static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+struct Rec { float u[6]; float w; };
+
+__device__ __forceinline__ Rec pair_record(const EnfPairTcParams& P, const float* lam, const float* xi, float sigma) {
+  Rec r;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r.u[i] = 0.f;
+  float x[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) x[f] = xi[f];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (i < P.I) {
+      const float* L = lam + i * ENF_F_XI;
+      float v = 0.f;
+      if (P.row_kind == ENF_ROW_DOT) {
+#pragma unroll
+        for (int f = 0; f < 8; ++f) v = fmaf(L[f], x[f], v);
+      } else {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
+        if (P.row_kind == ENF_ROW_SQDIST_SQRT) v = sqrtf(v);
+      }
+      r.u[i] = v;
+    }
+  }
+  float w = 0.f;
+  if (P.win_kind != ENF_WIN_NONE) {
+    const float* L = lam + P.I * ENF_F_XI;
+    float inv_s2 = 1.f / (sigma * sigma);
+    if (P.win_kind == ENF_WIN_NP) {
+      float v = 0.f;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
+      w = -v * inv_s2;
+    } else if (P.win_kind == ENF_WIN_PER) {
+      w = (r.u[0] * r.u[0] + r.u[1] * r.u[1]) * inv_s2;
+    } else {
+      float c = r.u[0];
+      if (P.win_row >= 0) {
+        c = 0.f;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) c = fmaf(L[f], x[f], c);
+      }
+      float cl = fminf(fmaxf(c, -1.f + 1e-6f), 1.f - 1e-6f);
+      float ac = acosf(cl);
+      w = __expf(-ac * ac * 0.5f * inv_s2);
+    }
+  }
+  r.w = w;
+  return r;
+}
+
+// my 32 columns of gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)] -> bf16 into the swizzled A tile
+template <int D>
+__device__ __forceinline__ void rff_to_tile(const Rec& r, int I, const float* om /*[6][D/2], pre-scaled by 2 pi*/, uint8_t* tile,
+                                            uint32_t ablk, int row, int col0) {
+  constexpr int HD = D / 2;
+  const bool is_cos = col0 >= HD;
+  const int j0 = is_cos ? col0 - HD : col0;
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = j0 + c8 + t;
+      float proj = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
+      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
+    }
+    tc::st_row8_bf16(tile, ablk, row, col0 + c8, v);
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk) {
+  constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 0);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk)
+    tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + (kk >> 2) * ablk + (kk & 3) * 32),
+                tc::desc_kmajor(b_addr + (kk >> 2) * wblk + (kk & 3) * 32), idesc, kk > 0);
+}
+
+template <int D, int H>
+__global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
+  using C = TcCfg<D, H>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = base + C::OFF_W;
+  uint8_t* sS = base + C::OFF_S;
+  uint8_t* sA0 = base + C::OFF_A0;
+  uint8_t* sA1 = base + C::OFF_A1;
+  float* f = reinterpret_cast<float*>(base + C::OFF_F);
+  float* s_xi = f; f += C::F_XI;
+  float* s_lam = f; f += C::F_LAM;
+  float* s_uz = f; f += C::F_UZ;
+  float* s_kap = f; f += C::F_KAP;
+  float* s_b3 = f; f += C::F_B3;
+  float* s_cw = f; f += C::F_CW;
+  float* s_bias = f; f += C::F_BIAS;          // b1q | b1v | bp
+  float* s_om = f; f += C::F_OM;              // omega_q | omega_v, scaled by 2 pi
+  float* s_spart = f; f += C::F_SPART;        // [NQ][ROWS][H]
+  float* s_st3 = f; f += C::F_ST3;            // [NQ][ROWS][2]
+  float* s_st4 = f; f += C::F_ST4;            // [H][NQ][ROWS][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(f);
+  uint64_t* bar_w = bars + 0;
+  uint64_t* bar_g1 = bars + 1;
+  uint64_t* bar_g2 = bars + 2;
+  uint64_t* bar_g3 = bars + 3;
+  uint64_t* bar_g4 = bars + 4;                // [2]
+  uint64_t* bar_w3 = bars + 6;                // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lq = warp & 3, cq = warp >> 2;
+  const int row = lq * 32 + lane, col0 = cq * 32;
+  const int b = blockIdx.y, c0 = blockIdx.x * ROWS;
+  const bool row_valid = c0 + row < P.C;
+  const float scale = rsqrtf((float)D);
+  constexpr int HD = D / 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) tc::mbar_init(bars + i, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
+  // per-CTA constants
+  for (int e = tid; e < ROWS * 8; e += C::NT) {
+    int r = e >> 3;
+    s_xi[e] = (c0 + r < P.C) ? P.xi[(int64_t)b * P.xi_bs + (int64_t)(c0 + r) * 8 + (e & 7)] : 0.f;
+  }
+  for (int e = tid; e < D; e += C::NT) { s_bias[e] = P.q_b1[e]; s_bias[D + e] = P.v_b1[e]; s_bias[2 * D + e] = P.bp[e]; }
+  for (int e = tid; e < 6 * HD; e += C::NT) {
+    const float two_pi = 6.283185307179586f;
+    s_om[e] = e < P.I * HD ? two_pi * P.q_omega[e] : 0.f;
+    s_om[6 * HD + e] = e < P.I * HD ? two_pi * P.v_omega[e] : 0.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = *s_tmem;
+  const uint32_t t0 = tm, t1 = tm + D;
+  const uint32_t my_t = ((uint32_t)(lq * 32) << 16) + col0;      // lane-quadrant / column offset of this warp
+
+  if (tid == 0) {
+    tc::mbar_expect_tx(bar_w, 3 * C::WIMG);
+    tc::bulk_g2s(sW, P.img_q_w1, C::WIMG, bar_w);
+    tc::bulk_g2s(sW + C::WIMG, P.img_v_w1, C::WIMG, bar_w);
+    tc::bulk_g2s(sW + 2 * C::WIMG, P.img_Wp, C::WIMG, bar_w);
+    tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
+    tc::bulk_g2s(sS, P.img_W3 + ((int64_t)b * P.Z * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+  }
+
+  float acc[H][32];
+  float m_run[H], l_run[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    m_run[h] = -INFINITY; l_run[h] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[h][j] = 0.f;
+  }
+
+  const uint32_t aA0 = tc::smem_u32(sA0), aA1 = tc::smem_u32(sA1), aS = tc::smem_u32(sS), aW = tc::smem_u32(sW);
+
+  for (int z = 0; z < P.Z; ++z) {
+    const uint32_t par = z & 1;
+    const int64_t bz = (int64_t)b * P.Z + z;
+    // ---- (a) per-latent vectors, invariants, gamma_q ----------------------------------------------------
+    if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[bz * ENF_LAM_SIZE + tid];
+    if (tid < H) s_kap[tid] = P.kappa[bz * H + tid];
+    for (int e = tid; e < H * D; e += C::NT) {
+      s_uz[e] = P.U[bz * H * D + e];
+      s_b3[e] = P.b3[bz * H * D + e];
+      s_cw[e] = P.cw3[bz * H * D + e];
+    }
+    __syncthreads();
+    const Rec rec = pair_record(P, s_lam, s_xi + row * 8, P.sigma ? P.sigma[bz] : 1.f);
+    rff_to_tile<D>(rec, P.I, s_om, sA0, C::ABLK, row, col0);
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      if (z == 0) tc::mbar_wait(bar_w, 0);
+      tc::tc_fence_after();
+      issue_gemm<D>(t0, aA0, aW, C::ABLK, C::WBLK);
+      tc::mma_commit(bar_g1);
+    }
+    // ---- (b) gamma_v (overlaps GEMM1) -------------------------------------------------------------------
+    rff_to_tile<D>(rec, P.I, s_om + 6 * HD, sA1, C::ABLK, row, col0);
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      issue_gemm<D>(t1, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
+      tc::mma_commit(bar_g2);
+    }
+    // ---- (c) E1: h1q = relu(T0 + b1q); logit partials (overlaps GEMM2) -------------------------------------
+    float v[32];
+    tc::mbar_wait(bar_g1, par);
+    tc::tc_fence_after();
+    tc::tmem_ld32(t0 + my_t, v);
+    tc::tmem_ld_wait();
+    {
+      float part[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float hq = fmaxf(v[j] + s_bias[col0 + j], 0.f);
+#pragma unroll
+        for (int h = 0; h < H; ++h) part[h] = fmaf(hq, s_uz[h * D + col0 + j], part[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) s_spart[(cq * ROWS + row) * H + h] = part[h];
+    }
+    // ---- (d) E2: h1v = relu(T1 + b1v) -> A0 ----------------------------------------------------------------
+    tc::mbar_wait(bar_g2, par);
+    tc::tc_fence_after();
+    tc::tmem_ld32(t1 + my_t, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c8 = 0; c8 < 32; c8 += 8) {
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = fmaxf(v[c8 + t] + s_bias[D + col0 + c8 + t], 0.f);
+      tc::st_row8_bf16(sA0, C::ABLK, row, col0 + c8, o);
+    }
+    tc::tc_fence_before();
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      issue_gemm<D>(t0, aA0, aW + 2 * C::WIMG, C::ABLK, C::WBLK);
+      tc::mma_commit(bar_g3);
+    }
+    // softmax statistics for this latent (every thread of the row, redundantly; overlaps GEMM3)
+    float pw[H], corr[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < C::NQ; ++q) dot += s_spart[(q * ROWS + row) * H + h];
+      float sv = scale * (dot + s_kap[h]) + rec.w;
+      if (cq == 0 && row_valid && P.slog) P.slog[(((int64_t)b * P.C + c0 + row) * P.Z + z) * H + h] = sv;
+      float m_new = fmaxf(m_run[h], sv);
+      corr[h] = __expf(m_run[h] - m_new);
+      pw[h] = __expf(sv - m_new);
+      l_run[h] = l_run[h] * corr[h] + pw[h];
+      m_run[h] = m_new;
+    }
+    // ---- (e) E3: g = gelu(T0 + b'), row statistics, g -> A1 (LayerNorm applied after GEMM4 as a correction) ----
+    tc::mbar_wait(bar_g3, par);
+    tc::tc_fence_after();
+    if (H > 1 && tid == 0) {          // A0 is free again: stream W3[z,1] into it
+      tc::mbar_expect_tx(&bar_w3[1], C::WIMG);
+      tc::bulk_g2s(sA0, P.img_W3 + (bz * H + 1) * C::WIMG, C::WIMG, &bar_w3[1]);
+    }
+    tc::tmem_ld32(t0 + my_t, v);
+    tc::tmem_ld_wait();
+    {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < 32; c8 += 8) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float g = gelu_fast(v[c8 + t] + s_bias[2 * D + col0 + c8 + t]);
+          o[t] = g; s1 += g; s2 = fmaf(g, g, s2);
+        }
+        tc::st_row8_bf16(sA1, C::ABLK, row, col0 + c8, o);
+      }
+      s_st3[(cq * ROWS + row) * 2 + 0] = s1;
+      s_st3[(cq * ROWS + row) * 2 + 1] = s2;
+    }
+    tc::tc_fence_before();
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc::mbar_wait(&bar_w3[0], par);
+      tc::tc_fence_after();
+      issue_gemm<D>(t0, aA1, aS, C::ABLK, C::WBLK);
+      tc::mma_commit(&bar_g4[0]);
+      if (H > 1) {
+        tc::mbar_wait(&bar_w3[1], par);
+        issue_gemm<D>(t1, aA1, aA0, C::ABLK, C::WBLK);
+        tc::mma_commit(&bar_g4[1]);
+      }
+    }
+    float mu_t, rstd_t;
+    {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < C::NQ; ++q) { s1 += s_st3[(q * ROWS + row) * 2]; s2 += s_st3[(q * ROWS + row) * 2 + 1]; }
+      mu_t = s1 * (1.f / D);
+      rstd_t = rsqrtf(fmaxf(s2 * (1.f / D) - mu_t * mu_t, 0.f) + 1e-6f);
+    }
+    // ---- (f) E4: per head  m = rstd_t (T - mu_t colsum(W3)) + b3 ; n = LN(gelu(m)) ; acc += p n ------------------
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      tc::mbar_wait(&bar_g4[h], par);
+      tc::tc_fence_after();
+      if (h == 0 && tid == 0 && z + 1 < P.Z) {       // stage buffer is free: prefetch next latent's W3[.,0]
+        tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
+        tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+      }
+      tc::tmem_ld32((h == 0 ? t0 : t1) + my_t, v);
+      tc::tmem_ld_wait();
+      float s1 = 0.f, s2 = 0.f;
+      const float nm = -rstd_t * mu_t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float cj = fmaf(nm, s_cw[h * D + col0 + j], s_b3[h * D + col0 + j]);
+        float g = gelu_fast(fmaf(v[j], rstd_t, cj));
+        v[j] = g; s1 += g; s2 = fmaf(g, g, s2);
+      }
+      float* st = s_st4 + ((h * C::NQ + cq) * ROWS + row) * 2;
+      st[0] = s1; st[1] = s2;
+      // the NQ warps that share this lane quadrant exchange their partial statistics
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + lq), "r"(32 * C::NQ) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < C::NQ; ++q) {
+        const float* sq = s_st4 + ((h * C::NQ + q) * ROWS + row) * 2;
+        s1 += sq[0]; s2 += sq[1];
+      }
+      float mu = s1 * (1.f / D);
+      float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mu * mu, 0.f) + 1e-6f);
+      float pr = pw[h] * rstd;
+      float tz = -pr * mu;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[h][j] = fmaf(v[j], pr, fmaf(acc[h][j], corr[h], tz));
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+
+  if (row_valid) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float inv_l = 1.f / l_run[h];
+      float* o = P.nbar + (((int64_t)b * P.C + c0 + row) * H + h) * D + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(acc[h][j] * inv_l, acc[h][j + 1] * inv_l, acc[h][j + 2] * inv_l, acc[h][j + 3] * inv_l);
+      if (cq == 0) P.lse[((int64_t)b * P.C + c0 + row) * H + h] = m_run[h] + logf(l_run[h]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tm);
+}
+
+template <int D, int H>
+int launch_tc(cudaStream_t st, const EnfPairTcParams& p) {
+  using C = TcCfg<D, H>;
+  if (cudaFuncSetAttribute(pairs_fwd_tc_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
+    return -1;
+  dim3 grid((p.C + ROWS - 1) / ROWS, p.B);
+  pairs_fwd_tc_kernel<D, H><<<grid, C::NT, C::SMEM_BYTES, st>>>(p);
+  return 1;
+}
+
+}  // namespace
+
+bool enf_pairs_fwd_tc_supported(int d, int H) { return (d == 128 || d == 64) && (H == 1 || H == 2); }
+
+int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p) {
+  if (d == 128 && H == 2) return launch_tc<128, 2>(st, p);
+  if (d == 128 && H == 1) return launch_tc<128, 1>(st, p);
+  if (d == 64 && H == 2) return launch_tc<64, 2>(st, p);
+  if (d == 64 && H == 1) return launch_tc<64, 1>(st, p);
+  return -1;
+}

@@ -3,6 +3,7 @@
 // Everything here is inline PTX; no CUTLASS dependency.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,9 +112,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // byte offset of the 16-byte chunk holding features [8*chunk, 8*chunk+8) of `row` inside a 64-feature block
 __device__ __forceinline__ uint32_t swz_chunk_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+// 16-bit operand format of every tcgen05.mma in this library.  fp16 (10-bit mantissa) rather than bf16 (7-bit):
+// same tensor-core rate, 8x smaller rounding error; all operands here (RFF features, relu / gelu / LayerNorm
+// activations, weights) are O(1) so fp16's range is ample.  kOperandFmt is the a/b format field of the idesc.
+constexpr int kOperandFmt = 0;     // 0 = f16, 1 = bf16
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {      // (name kept: packs two floats to the operand format)
+  if (kOperandFmt == 1) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  } else {
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+}
+__device__ __forceinline__ float round_operand(float a) {
+  return kOperandFmt == 1 ? __bfloat162float(__float2bfloat16_rn(a)) : __half2float(__float2half_rn(a));
 }
 // store 8 consecutive features (col0 % 8 == 0) of `row` as bf16; tile = [D/64 blocks][rows][64], block_bytes = rows*128
 __device__ __forceinline__ void st_row8_bf16(uint8_t* tile, uint32_t block_bytes, int row, int col0, const float* v) {

@@ -164,6 +164,12 @@ const char* enf_last_error(void);
  * (e.g. "xi", "lam", "U", "W3", "nbar", "lse"); returns -1 if unknown. */
 int64_t enf_debug_ws_offset(const EnfDesc* desc, const char* name, int64_t* num_floats);
 
+/* Test hook: one 128-row tcgen05 tile GEMM with bf16 operands (D = 64 or 128 features), pinning the
+ * shared-memory descriptor / swizzle conventions of the tensor-core kernels on hardware.
+ *   mode 0: out[r][n] = sum_k X[r][k] Y[n][k];  mode 1: out[r][k] = sum_n X[r][n] Y[n][k];
+ *   mode 2: out[i][j] = sum_r X[r][i] Y[r][j].   X, Y, out: device float32 [128][D]; scratch >= D*D*2 bytes. */
+int enf_debug_tc_gemm(int mode, int D, const float* X, const float* Y, float* out, void* scratch, enf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

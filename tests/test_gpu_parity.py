@@ -29,8 +29,8 @@ def _to_cuda(tree):
     return R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous().requires_grad_(True), tree)
 
 
-def _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out):
-    nef = _nef_for(cfg)
+def _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="fp32"):
+    nef = _nef_for(cfg, precision)
     P = _to_cuda(params)
     pg = p.to("cuda", torch.float32).requires_grad_(True)
     ag = a.to("cuda", torch.float32).requires_grad_(True)
@@ -169,3 +169,42 @@ def test_error_paths():
         nef.apply(P, x.float(), f(p), f(a), f(sigma))              # CPU tensor: no CPU path
     with pytest.raises(NotImplementedError):
         E.EquivariantCrossAttentionNeF(32, 2, 1, 1, 8, nef.cross_attn_invariant)   # num_layers > 0
+
+
+TOL_BF16 = 2e-3     # BASELINE.json's bf16/tf32 bucket
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[1]["num_hidden"] in (64, 128)], ids=lambda c: c[0])
+def test_tensor_core_path_against_oracle(case):
+    """precision='bf16': tcgen05 pair kernel (bf16 operands, fp32 accumulate); tolerance 2e-3."""
+    _, kw, B, C, Z, grid = case
+    cfg = R.EnfConfig(**kw)
+    params, x, p, a, sigma, d_out = make_case(cfg, B, C, Z, seed=3, polar_grid=grid)
+    out_ref, dth_ref, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="bf16")
+    errs = dict(out=rel_err(out, out_ref), dp=rel_err(dp, dp_ref), da=rel_err(da, da_ref),
+                ds=rel_err(ds, ds_ref) if cfg.use_gaussian_window else 0.0)
+    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
+    scale = max(float(v.abs().max()) for v in fr.values())
+    errs["dtheta"] = max(float((fg[k].double().cpu() - fr[k]).abs().max()) / scale for k in fr)
+    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < TOL_BF16 for v in errs.values()), errs
+
+
+def test_tensor_core_full_size_ns_subset():
+    """BASELINE config 2 at full size through the tensor-core forward: random rows against the oracle."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1))
+    B, C, Z = 32, 4096, 64
+    params, _, p, a, sigma, _ = make_case(cfg, B, 8, Z, seed=7)
+    x = R.make_coords(cfg, (64, 64)).float().double()[None].expand(B, -1, -1)
+    g = torch.Generator().manual_seed(11)
+    sub = torch.randperm(C, generator=g)[:24]
+    bsel = [0, 13, 31]
+    nef = _nef_for(cfg, "bf16")
+    P = _to_cuda(params)
+    f = lambda t: t.to("cuda", torch.float32)
+    with torch.no_grad():
+        out = nef.apply(P, f(x), f(p), f(a), f(sigma))
+    out_ref = R.nef_apply(cfg, params, x[bsel][:, sub], p[bsel], a[bsel], sigma[bsel])
+    assert rel_err(out[bsel][:, sub], out_ref) < TOL_BF16
