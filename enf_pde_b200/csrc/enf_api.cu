@@ -86,6 +86,10 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
     Y.add("cw3", BZ * Hd); Y.add("slog", BC * (size_t)D.Z * H);
+    if (enf_pairs_bwd_tc_supported(D.d, D.H)) {
+      Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
+      Y.add("dthat", BC * (size_t)D.Z * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
+    }
   }
   Y.add("xi", BC * ENF_F_XI);
   Y.add("nbar", BC * Hd); Y.add("lse", BC * H);
@@ -96,7 +100,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   // ---- accumulators, zeroed at the start of each bwd ----
   Y.acc_begin = Y.total;
   Y.add("g_W3", BZ * H * d2); Y.add("g_b3", BZ * Hd); Y.add("g_U", BZ * Hd); Y.add("g_kappa", BZ * H);
-  Y.add("g_lam", BZ * ENF_LAM_SIZE); Y.add("g_sigma", BZ);
+  Y.add("g_lam", BZ * ENF_LAM_SIZE); Y.add("g_sigma", BZ); Y.add("gmax", 64);
   Y.add("gf_A_q", d * Hd); Y.add("gf_c_q", Hd); Y.add("gf_Wp", d2); Y.add("gf_bp", d); Y.add("gf_W2g", d * 2 * Hd);
   Y.add("gf_b2g", 2 * Hd); Y.add("gf_M2g", d2); Y.add("gf_c2g", d);
   size_t n[ENF_NUM_WEIGHT_LEAVES];
@@ -398,21 +402,48 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm((int)(BC * H), d, d, enf_mat(c.f("s2"), d), enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("s0"), d));        // dnbar
 
   // ---- P backward --------------------------------------------------------------------------------------
-  c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
-  c.launches += enf_launch_transpose(st, w->v_w1, c.f("v_w1T"), d, d, 1);
-  c.launches += enf_launch_transpose(st, c.f("Wp"), c.f("WpT"), d, d, 1);
-  c.launches += enf_launch_transpose(st, c.f("W3"), c.f("W3T"), d, d, (int)(BZ * H));
+  const bool tc_fwd = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);
+  const bool tc_bwd = tc_fwd && enf_pairs_bwd_tc_supported(D.d, D.H);
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
-  pp.q_w1T = c.f("q_w1T"); pp.v_w1T = c.f("v_w1T"); pp.WpT = c.f("WpT"); pp.W3T = c.f("W3T");
-  pp.dnbar = c.f("s0");
-  if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) pp.slog = c.f("slog");
-  pp.g_q_w1 = G("q_w1"); pp.g_q_b1 = G("q_b1"); pp.g_v_w1 = G("v_w1"); pp.g_v_b1 = G("v_b1");
-  pp.g_Wp = c.f("gf_Wp"); pp.g_bp = c.f("gf_bp");
-  pp.g_W3 = c.f("g_W3"); pp.g_b3 = c.f("g_b3"); pp.g_U = c.f("g_U"); pp.g_kappa = c.f("g_kappa");
-  pp.g_lam = c.f("g_lam"); pp.g_sigma = c.f("g_sigma");
-  prof_mark(1, 0, st);
-  int nl = enf_launch_pairs_bwd_simt(st, d, pp);
-  prof_mark(1, 1, st);
+  int nl;
+  if (tc_bwd) {
+    EnfPairTcBwdParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = D.B; tp.C = D.C; tp.Z = D.Z; tp.I = rl.I;
+    tp.row_kind = rl.row_kind; tp.win_kind = rl.win_kind; tp.win_row = rl.win_row; tp.nsq = rl.nsq;
+    tp.xi = pp.xi; tp.xi_bs = pp.xi_bs; tp.lam = pp.lam; tp.sigma = pp.sigma;
+    tp.q_omega = w->q_omega; tp.v_omega = w->v_omega; tp.q_b1 = w->q_b1; tp.v_b1 = w->v_b1; tp.bp = c.f("bp");
+    tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
+    tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
+    c.launches += enf_launch_weight_image(st, c.f("q_w1T"), c.f("img_q_w1_lo"), nullptr, d, d, 1, 1);
+    c.launches += enf_launch_weight_image(st, c.f("v_w1T"), c.f("img_v_w1_lo"), nullptr, d, d, 1, 1);
+    tp.img_q_w1_lo = (const uint8_t*)c.f("img_q_w1_lo"); tp.img_v_w1_lo = (const uint8_t*)c.f("img_v_w1_lo");
+    tp.U = pp.U; tp.b3 = pp.b3; tp.slog = c.f("slog"); tp.lse = pp.lse; tp.nbar = pp.nbar;
+    tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax");
+    tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc");
+    tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
+    tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");
+    tp.g_Wp = c.f("gf_Wp"); tp.g_bp = c.f("gf_bp");
+    tp.g_U = c.f("g_U"); tp.g_kappa = c.f("g_kappa"); tp.g_lam = c.f("g_lam"); tp.g_sigma = c.f("g_sigma");
+    prof_mark(1, 0, st);
+    nl = enf_launch_pairs_bwd_tc(st, d, H, tp);
+    prof_mark(1, 1, st);
+  } else {
+    c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
+    c.launches += enf_launch_transpose(st, w->v_w1, c.f("v_w1T"), d, d, 1);
+    c.launches += enf_launch_transpose(st, c.f("Wp"), c.f("WpT"), d, d, 1);
+    c.launches += enf_launch_transpose(st, c.f("W3"), c.f("W3T"), d, d, (int)(BZ * H));
+    pp.q_w1T = c.f("q_w1T"); pp.v_w1T = c.f("v_w1T"); pp.WpT = c.f("WpT"); pp.W3T = c.f("W3T");
+    pp.dnbar = c.f("s0");
+    if (tc_fwd) pp.slog = c.f("slog");
+    pp.g_q_w1 = G("q_w1"); pp.g_q_b1 = G("q_b1"); pp.g_v_w1 = G("v_w1"); pp.g_v_b1 = G("v_b1");
+    pp.g_Wp = c.f("gf_Wp"); pp.g_bp = c.f("gf_bp");
+    pp.g_W3 = c.f("g_W3"); pp.g_b3 = c.f("g_b3"); pp.g_U = c.f("g_U"); pp.g_kappa = c.f("g_kappa");
+    pp.g_lam = c.f("g_lam"); pp.g_sigma = c.f("g_sigma");
+    prof_mark(1, 0, st);
+    nl = enf_launch_pairs_bwd_simt(st, d, pp);
+    prof_mark(1, 1, st);
+  }
   if (nl < 0) return fail(ENF_ERR_CUDA, "pair backward kernel could not be configured");
   c.launches += nl;
 

@@ -108,7 +108,7 @@ int enf_launch_mul_rows(cudaStream_t st, float* out, const float* A, const float
                         const float* add_outer_u, const float* add_outer_v);
 int enf_launch_transpose(cudaStream_t st, const float* in, float* out, int rows, int cols, int batch);
 
-int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch);
+int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual = 0);
 
 // ---- fused pair kernels (enf_pairs_simt.cu) ------------------------------------------------------
 struct EnfPairParams {
@@ -150,3 +150,27 @@ struct EnfPairTcParams {
 };
 bool enf_pairs_fwd_tc_supported(int d, int H);
 int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p);
+
+struct __half;
+struct EnfPairTcBwdParams {
+  int B, C, Z, I;
+  int row_kind, win_kind, win_row, nsq;
+  const float* xi;  int64_t xi_bs;
+  const float* lam; const float* sigma;
+  const float* q_omega; const float* v_omega;
+  const float* q_b1; const float* v_b1; const float* bp;
+  const uint8_t* img_q_w1; const uint8_t* img_v_w1; const uint8_t* img_Wp; const uint8_t* img_W3;
+  const uint8_t* img_q_w1_lo; const uint8_t* img_v_w1_lo;   // images of W - round16(W) (two-term split of the relu layers)
+  const float* U; const float* b3;
+  const float* slog; const float* lse; const float* nbar;   // forward state
+  const float* dnbar;                        // [B,C,H,d] cotangent of nbar
+  float* Dg;                                 // [B,C,H]   dnbar . nbar                (written by the prep kernel)
+  float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernel)
+  __half* dthat;                             // [B,Z,C,d] scaled cotangent of that    (A -> B)
+  float* ds;                                 // [B,Z,C,H] scaled cotangent of logits  (A -> B)
+  float* g_W3; float* g_b3;                  // per-latent outputs of A
+  float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // shared-weight grads (atomics)
+  float* g_U; float* g_kappa; float* g_lam; float* g_sigma;                                // per-latent outputs of B
+};
+bool enf_pairs_bwd_tc_supported(int d, int H);
+int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);

@@ -6,33 +6,19 @@
 //     E0v  gamma_v -> smem A1                             GEMM2  A1 x W1_v      -> TMEM T1
 //     E1   T0: relu, dot with folded U[z,h] -> logits s ; online-softmax statistics
 //     E2   T1: relu -> A0                                 GEMM3  A0 x W'        -> T0
-//     E3   T0: gelu, LN statistics -> A1 (un-normalised)  GEMM4h A1 x W3[z,h]   -> T0 / T1
-//     E4h  Th: LN of E3 applied as a rank-1 correction, gelu, LN, acc_h += p * n      (registers)
-// with tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM) issued by one thread, weights
+//     E3   T0: gelu, LayerNorm -> A1                      GEMM4h A1 x W3[z,h]   -> T0 / T1
+//     E4h  Th: gelu, LayerNorm, acc_h += p * n                                       (registers)
+// with tcgen05.mma (kind::f16, fp16 operands, fp32 accumulators in TMEM) issued by one thread, weights
 // resident in shared memory as pre-swizzled images, the per-latent W3 images streamed by the bulk-copy
 // (TMA) engine, tcgen05.ld feeding the elementwise epilogues, and D/32 threads per query row so that
 // the softmax accumulators (H x d fp32 per row) stay in registers.  Nothing per-pair touches HBM except
 // the logits saved for the backward.  MMA and epilogues overlap where the chain allows it
 // (GEMM1 | E0v, GEMM2 | E1, GEMM3 | softmax update, GEMM4_1 | E4_0).
-#include "enf_common.cuh"
-#include "enf_tc.cuh"
+#include "enf_pairs_tc_common.cuh"
 
 namespace {
 
-constexpr int ROWS = 128;
-
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
-  float x2 = x * x;
-  float t = tanh_fast(x * fmaf(c1, x2, c0));
-  float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
+using namespace tcp;
 
 template <int D, int H> struct TcCfg {
   static constexpr int NQ = D / 32;                    // threads per query row (32 columns each)
@@ -49,94 +35,11 @@ template <int D, int H> struct TcCfg {
   static constexpr uint32_t OFF_A1 = OFF_A0 + ATILE;
   static constexpr uint32_t OFF_F = OFF_A1 + ATILE;    // float arrays start here
   // float arrays (counts)
-  static constexpr int F_XI = ROWS * 8, F_LAM = 64, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_CW = H * D, F_BIAS = 3 * D,
-                       F_OM = 2 * 6 * (D / 2), F_SPART = NQ * ROWS * H, F_ST3 = NQ * ROWS * 2, F_ST4 = H * NQ * ROWS * 2;
-  static constexpr int F_TOTAL = F_XI + F_LAM + F_UZ + F_KAP + F_B3 + F_CW + F_BIAS + F_OM + F_SPART + F_ST3 + F_ST4;
+  static constexpr int F_XI = ROWS * 8, F_LAM = 64, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_BIAS = 3 * D,
+                       F_OM = 2 * 6 * (D / 2), F_SPART = NQ * ROWS * H, F_EXCH = 2 * NQ * ROWS * 2;
+  static constexpr int F_TOTAL = F_XI + F_LAM + F_UZ + F_KAP + F_B3 + F_BIAS + F_OM + F_SPART + F_EXCH;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 /*barriers*/ + 1024 /*alignment slack*/;
 };
-
-struct Rec { float u[6]; float w; };
-
-__device__ __forceinline__ Rec pair_record(const EnfPairTcParams& P, const float* lam, const float* xi, float sigma) {
-  Rec r;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) r.u[i] = 0.f;
-  float x[8];
-#pragma unroll
-  for (int f = 0; f < 8; ++f) x[f] = xi[f];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    if (i < P.I) {
-      const float* L = lam + i * ENF_F_XI;
-      float v = 0.f;
-      if (P.row_kind == ENF_ROW_DOT) {
-#pragma unroll
-        for (int f = 0; f < 8; ++f) v = fmaf(L[f], x[f], v);
-      } else {
-#pragma unroll
-        for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
-        if (P.row_kind == ENF_ROW_SQDIST_SQRT) v = sqrtf(v);
-      }
-      r.u[i] = v;
-    }
-  }
-  float w = 0.f;
-  if (P.win_kind != ENF_WIN_NONE) {
-    const float* L = lam + P.I * ENF_F_XI;
-    float inv_s2 = 1.f / (sigma * sigma);
-    if (P.win_kind == ENF_WIN_NP) {
-      float v = 0.f;
-#pragma unroll
-      for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
-      w = -v * inv_s2;
-    } else if (P.win_kind == ENF_WIN_PER) {
-      w = (r.u[0] * r.u[0] + r.u[1] * r.u[1]) * inv_s2;
-    } else {
-      float c = r.u[0];
-      if (P.win_row >= 0) {
-        c = 0.f;
-#pragma unroll
-        for (int f = 0; f < 8; ++f) c = fmaf(L[f], x[f], c);
-      }
-      float cl = fminf(fmaxf(c, -1.f + 1e-6f), 1.f - 1e-6f);
-      float ac = acosf(cl);
-      w = __expf(-ac * ac * 0.5f * inv_s2);
-    }
-  }
-  r.w = w;
-  return r;
-}
-
-// my 32 columns of gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)] -> bf16 into the swizzled A tile
-template <int D>
-__device__ __forceinline__ void rff_to_tile(const Rec& r, int I, const float* om /*[6][D/2], pre-scaled by 2 pi*/, uint8_t* tile,
-                                            uint32_t ablk, int row, int col0) {
-  constexpr int HD = D / 2;
-  const bool is_cos = col0 >= HD;
-  const int j0 = is_cos ? col0 - HD : col0;
-#pragma unroll
-  for (int c8 = 0; c8 < 32; c8 += 8) {
-    float v[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = j0 + c8 + t;
-      float proj = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
-      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
-    }
-    tc::st_row8_bf16(tile, ablk, row, col0 + c8, v);
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk) {
-  constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 0);
-#pragma unroll
-  for (int kk = 0; kk < D / 16; ++kk)
-    tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + (kk >> 2) * ablk + (kk & 3) * 32),
-                tc::desc_kmajor(b_addr + (kk >> 2) * wblk + (kk & 3) * 32), idesc, kk > 0);
-}
 
 template <int D, int H>
 __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
@@ -153,12 +56,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   float* s_uz = f; f += C::F_UZ;
   float* s_kap = f; f += C::F_KAP;
   float* s_b3 = f; f += C::F_B3;
-  float* s_cw = f; f += C::F_CW;
   float* s_bias = f; f += C::F_BIAS;          // b1q | b1v | bp
   float* s_om = f; f += C::F_OM;              // omega_q | omega_v, scaled by 2 pi
   float* s_spart = f; f += C::F_SPART;        // [NQ][ROWS][H]
-  float* s_st3 = f; f += C::F_ST3;            // [NQ][ROWS][2]
-  float* s_st4 = f; f += C::F_ST4;            // [H][NQ][ROWS][2]
+  float* s_exch = f; f += C::F_EXCH;          // two alternating [NQ][ROWS][2] exchange buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
   uint64_t* bar_w = bars + 0;
   uint64_t* bar_g1 = bars + 1;
@@ -208,6 +109,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::bulk_g2s(sS, P.img_W3 + ((int64_t)b * P.Z * H) * C::WIMG, C::WIMG, &bar_w3[0]);
   }
 
+  int xw = 0;                                  // which exchange buffer is next
   float acc[H][32];
   float m_run[H], l_run[H];
 #pragma unroll
@@ -228,7 +130,6 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     for (int e = tid; e < H * D; e += C::NT) {
       s_uz[e] = P.U[bz * H * D + e];
       s_b3[e] = P.b3[bz * H * D + e];
-      s_cw[e] = P.cw3[bz * H * D + e];
     }
     __syncthreads();
     const Rec rec = pair_record(P, s_lam, s_xi + row * 8, P.sigma ? P.sigma[bz] : 1.f);
@@ -314,19 +215,23 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::tmem_ld32(t0 + my_t, v);
     tc::tmem_ld_wait();
     {
-      float s1 = 0.f, s2 = 0.f;
+      float st[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float g = gelu_fast(v[j] + s_bias[2 * D + col0 + j]);
+        v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+      }
+      row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
+      const float mu = st[0] * (1.f / D);
+      const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
+      const float nm = -mu * rstd;
 #pragma unroll
       for (int c8 = 0; c8 < 32; c8 += 8) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          float g = gelu_fast(v[c8 + t] + s_bias[2 * D + col0 + c8 + t]);
-          o[t] = g; s1 += g; s2 = fmaf(g, g, s2);
-        }
+        for (int t = 0; t < 8; ++t) o[t] = fmaf(v[c8 + t], rstd, nm);
         tc::st_row8_bf16(sA1, C::ABLK, row, col0 + c8, o);
       }
-      s_st3[(cq * ROWS + row) * 2 + 0] = s1;
-      s_st3[(cq * ROWS + row) * 2 + 1] = s2;
     }
     tc::tc_fence_before();
     tc::fence_proxy_async();
@@ -342,15 +247,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         tc::mma_commit(&bar_g4[1]);
       }
     }
-    float mu_t, rstd_t;
-    {
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < C::NQ; ++q) { s1 += s_st3[(q * ROWS + row) * 2]; s2 += s_st3[(q * ROWS + row) * 2 + 1]; }
-      mu_t = s1 * (1.f / D);
-      rstd_t = rsqrtf(fmaxf(s2 * (1.f / D) - mu_t * mu_t, 0.f) + 1e-6f);
-    }
-    // ---- (f) E4: per head  m = rstd_t (T - mu_t colsum(W3)) + b3 ; n = LN(gelu(m)) ; acc += p n ------------------
+    // ---- (f) E4: per head  m = T + b3 ; n = LN(gelu(m)) ; acc += p n --------------------------------------------
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       tc::mbar_wait(&bar_g4[h], par);
@@ -361,26 +258,15 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       }
       tc::tmem_ld32((h == 0 ? t0 : t1) + my_t, v);
       tc::tmem_ld_wait();
-      float s1 = 0.f, s2 = 0.f;
-      const float nm = -rstd_t * mu_t;
+      float st[2] = {0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float cj = fmaf(nm, s_cw[h * D + col0 + j], s_b3[h * D + col0 + j]);
-        float g = gelu_fast(fmaf(v[j], rstd_t, cj));
-        v[j] = g; s1 += g; s2 = fmaf(g, g, s2);
+        float g = gelu_fast(v[j] + s_b3[h * D + col0 + j]);
+        v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
       }
-      float* st = s_st4 + ((h * C::NQ + cq) * ROWS + row) * 2;
-      st[0] = s1; st[1] = s2;
-      // the NQ warps that share this lane quadrant exchange their partial statistics
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + lq), "r"(32 * C::NQ) : "memory");
-      s1 = 0.f; s2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < C::NQ; ++q) {
-        const float* sq = s_st4 + ((h * C::NQ + q) * ROWS + row) * 2;
-        s1 += sq[0]; s2 += sq[1];
-      }
-      float mu = s1 * (1.f / D);
-      float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mu * mu, 0.f) + 1e-6f);
+      row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
+      float mu = st[0] * (1.f / D);
+      float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
       float pr = pw[h] * rstd;
       float tz = -pr * mu;
 #pragma unroll

@@ -1,0 +1,197 @@
+// Device code shared by the tensor-core pair kernels (forward + the two backward kernels), so that the
+// backward's recompute reproduces the forward's operand roundings bit for bit.
+//
+// Thread layout of every kernel here: a CTA owns 128 query rows (= the 128 TMEM lanes).  NQ = D/32 threads
+// serve one row, 32 accumulator columns each: warp w -> lane quadrant lq = w & 3 (rows 32*lq .. +31, the only
+// TMEM lanes that warp may touch), column quarter cq = w >> 2 (columns 32*cq .. +31).
+#pragma once
+#include "enf_common.cuh"
+#include "enf_tc.cuh"
+
+namespace tcp {
+
+constexpr int ROWS = 128;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// jax.nn.gelu(approximate=True) and its derivative, sharing one tanh
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float t = tanh_fast(x * fmaf(c1, x * x, c0));
+  float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+__device__ __forceinline__ void gelu_fast_both(float x, float& g, float& dg) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float x2 = x * x;
+  float t = tanh_fast(x * fmaf(c1, x2, c0));
+  float hx = 0.5f * x;
+  g = fmaf(hx, t, hx);
+  // d/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2)
+  dg = fmaf(hx * fmaf(-t, t, 1.f), fmaf(3.f * c1, x2, c0), fmaf(0.5f, t, 0.5f));
+}
+
+struct Rec { float u[6]; float w; float c; };   // invariants, window value, raw cosine (spherical windows)
+
+template <class Params>
+__device__ __forceinline__ Rec pair_record(const Params& P, const float* lam, const float* xi, float sigma) {
+  Rec r;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r.u[i] = 0.f;
+  float x[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) x[f] = xi[f];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (i < P.I) {
+      const float* L = lam + i * ENF_F_XI;
+      float v = 0.f;
+      if (P.row_kind == ENF_ROW_DOT) {
+#pragma unroll
+        for (int f = 0; f < 8; ++f) v = fmaf(L[f], x[f], v);
+      } else {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
+        if (P.row_kind == ENF_ROW_SQDIST_SQRT) v = sqrtf(v);
+      }
+      r.u[i] = v;
+    }
+  }
+  float w = 0.f, c = 0.f;
+  if (P.win_kind != ENF_WIN_NONE) {
+    const float* L = lam + P.I * ENF_F_XI;
+    float inv_s2 = 1.f / (sigma * sigma);
+    if (P.win_kind == ENF_WIN_NP) {
+      float v = 0.f;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) if (f < P.nsq) { float dl = L[f] - x[f]; v = fmaf(dl, dl, v); }
+      w = -v * inv_s2;
+    } else if (P.win_kind == ENF_WIN_PER) {
+      w = (r.u[0] * r.u[0] + r.u[1] * r.u[1]) * inv_s2;
+    } else {
+      c = r.u[0];
+      if (P.win_row >= 0) {
+        c = 0.f;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) c = fmaf(L[f], x[f], c);
+      }
+      float cl = fminf(fmaxf(c, -1.f + 1e-6f), 1.f - 1e-6f);
+      float ac = acosf(cl);
+      w = __expf(-ac * ac * 0.5f * inv_s2);
+    }
+  }
+  r.w = w; r.c = c;
+  return r;
+}
+
+// my 32 columns of gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)] (rff.py:84-93) -> 16-bit, swizzled A tile.
+// om = Omega pre-scaled by 2 pi, [6][D/2].
+template <int D>
+__device__ __forceinline__ void rff_to_tile(const Rec& r, int I, const float* om, uint8_t* tile, uint32_t ablk, int row, int col0) {
+  constexpr int HD = D / 2;
+  const bool is_cos = col0 >= HD;
+  const int j0 = is_cos ? col0 - HD : col0;
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = j0 + c8 + t;
+      float proj = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
+      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
+    }
+    tc::st_row8_bf16(tile, ablk, row, col0 + c8, v);
+  }
+}
+
+// same, as a two-term 16-bit split: tile_hi gets round16(gamma), tile_lo gets round16(gamma - round16(gamma))
+template <int D>
+__device__ __forceinline__ void rff_to_tile_split(const Rec& r, int I, const float* om, uint8_t* tile_hi, uint8_t* tile_lo,
+                                                  uint32_t ablk, int row, int col0) {
+  constexpr int HD = D / 2;
+  const bool is_cos = col0 >= HD;
+  const int j0 = is_cos ? col0 - HD : col0;
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float v[8], lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = j0 + c8 + t;
+      float proj = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
+      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
+      lo[t] = v[t] - tc::round_operand(v[t]);
+    }
+    tc::st_row8_bf16(tile_hi, ablk, row, col0 + c8, v);
+    tc::st_row8_bf16(tile_lo, ablk, row, col0 + c8, lo);
+  }
+}
+
+// D[128 x N=D] = A[128 x K=D] (K-major activation tile) * B (K-major weight image: rows = output feature)
+template <int D>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate = 0) {
+  constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 0);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk)
+    tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + (kk >> 2) * ablk + (kk & 3) * 32),
+                tc::desc_kmajor(b_addr + (kk >> 2) * wblk + (kk & 3) * 32), idesc, (kk > 0) | accumulate);
+}
+// dgrad: D[128 x D] (+)= G[128 x D] * W^T, with the SAME weight image read MN-major (rows = reduction index)
+template <int D>
+__device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, uint32_t g_addr, uint32_t w_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate) {
+  constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 1);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk)
+    tc::mma_f16(d_tmem, tc::desc_kmajor(g_addr + (kk >> 2) * ablk + (kk & 3) * 32), tc::desc_mnmajor(w_addr + kk * 2048, wblk), idesc,
+                (kk > 0) | accumulate);
+}
+// wgrad: dW[D x D] (+)= Act[128 x D]^T * G[128 x D]; both activation tiles read MN-major (rows = reduction index)
+template <int D>
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t act_addr, uint32_t g_addr, uint32_t ablk, uint32_t accumulate) {
+  constexpr uint32_t idesc = tc::make_idesc(D, D, tc::kOperandFmt, 1, 1);
+#pragma unroll
+  for (int kk = 0; kk < ROWS / 16; ++kk)
+    tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_mnmajor(g_addr + kk * 2048, ablk), idesc, (kk > 0) | accumulate);
+}
+
+// Sum NV per-thread partials over the NQ threads that share a query row.  `buf` = two alternating
+// [NQ][ROWS][NV] buffers (toggle `which` on every call); the NQ warps of a lane quadrant meet on named barrier 1+lq.
+template <int NQ, int NV>
+__device__ __forceinline__ void row_exchange(float* buf, int& which, int cq, int row, int lq, float (&v)[NV]) {
+  float* b = buf + which * (NQ * ROWS * NV);
+  which ^= 1;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) b[(cq * ROWS + row) * NV + i] = v[i];
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + lq), "r"(32 * NQ) : "memory");
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) s += b[(q * ROWS + row) * NV + i];
+    v[i] = s;
+  }
+}
+
+// v[j] = this lane's (row's) value for column j of its 32-column slab.  Returns, in lane l, the sum over the
+// warp's 32 rows of column l (a transposing butterfly: 31 shuffles).  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float send = upper ? v[i] : v[i + half];
+      float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+}  // namespace tcp

@@ -9,7 +9,7 @@ namespace {
 // K-major B operand tile occupies in shared memory, so the hot kernels fetch it with one bulk copy).
 // cw [batch][N] (optional) = sum_k of the bf16-ROUNDED values (column sums of W as the MMA sees it).
 __global__ void __launch_bounds__(256) weight_image_kernel(const float* __restrict__ Wt, uint8_t* __restrict__ img,
-                                                           float* __restrict__ cw, int N, int K) {
+                                                           float* __restrict__ cw, int N, int K, int residual) {
   const int64_t b = blockIdx.x;
   const float* src = Wt + b * (int64_t)N * K;
   uint8_t* dst = img + b * (int64_t)N * K * 2;
@@ -20,6 +20,10 @@ __global__ void __launch_bounds__(256) weight_image_kernel(const float* __restri
     const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)n * K + k0);
     float4 a = __ldg(s4), c = __ldg(s4 + 1);
     float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    if (residual) {            // image of W - round16(W): the low part of a two-term 16-bit split
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] -= tc::round_operand(v[i]);
+    }
     uint4 q;
     q.x = tc::pack_bf16(v[0], v[1]); q.y = tc::pack_bf16(v[2], v[3]); q.z = tc::pack_bf16(v[4], v[5]); q.w = tc::pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(dst + (size_t)(k0 >> 6) * N * 128 + tc::swz_chunk_off(n, (k0 & 63) >> 3)) = q;
@@ -113,15 +117,15 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(int mode, const float
 
 }  // namespace
 
-int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch) {
-  weight_image_kernel<<<batch, 256, 0, st>>>(Wt, (uint8_t*)img, cw, N, K);
+int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual) {
+  weight_image_kernel<<<batch, 256, 0, st>>>(Wt, (uint8_t*)img, cw, N, K, residual);
   return 1;
 }
 
 extern "C" int enf_debug_tc_gemm(int mode, int D, const float* X, const float* Y, float* out, void* scratch, enf_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (D != 64 && D != 128) return ENF_ERR_UNSUPPORTED;
-  if (mode != 2) enf_launch_weight_image(st, Y, scratch, nullptr, D, D, 1);
+  if (mode != 2) enf_launch_weight_image(st, Y, scratch, nullptr, D, D, 1, 0);
   size_t smem = 2 * (size_t)(D / 64) * 128 * 128 + 1024;
   if (D == 128) {
     cudaFuncSetAttribute(tc_gemm_test_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

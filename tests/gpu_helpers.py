@@ -25,13 +25,13 @@ def ws_view(lib, desc, ws, name):
     return ws[off:off + 4 * n.value].view(torch.float32)
 
 
-def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False):
+def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
     """Run fwd+bwd through the C ABI; return (results dict, per-stage error dict vs the folded fp64 model)."""
     lib = _lib.load()
     dev = torch.device("cuda:0")
     B, C = x.shape[:2]
     Z = p.shape[1]
-    desc = desc_for(cfg, B, C, Z)
+    desc = desc_for(cfg, B, C, Z, precision)
     f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
     leaves64 = params_to_leaves(params)
     leaves = [f32(t) for t in leaves64]
@@ -87,5 +87,6 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False):
     gscale = max(float(G[k].abs().max()) for k in G)
     for leaf, g in zip(_lib.LEAVES, grads):
         errs["gw_" + leaf] = float((g.cpu().double() - G[leaf]).abs().max()) / max(gscale, 1e-30)
+        errs["self_" + leaf] = rel_err(g.cpu(), G[leaf])
     res = dict(out=out, dp=dp, da=da, dsigma=dsig, grads=grads, launches=lib.enf_last_launch_count())
     return res, errs
