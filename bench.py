@@ -204,6 +204,7 @@ def main():
     import torch
     import enf_pde_b200 as E
     from enf_pde_b200 import _lib
+    from enf_pde_b200.dist import allreduce_weight_grads
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
@@ -246,8 +247,7 @@ def main():
         loss = (diff * diff).mean()
         out.backward(diff * (2.0 / n_out))
         if world > 1:
-            flat = torch.cat([t.grad.reshape(-1) for t in leaves])
-            dist.all_reduce(flat)
+            allreduce_weight_grads([t.grad for t in leaves])
         return loss
 
     def barrier():
