@@ -66,7 +66,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 
 EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_fwd",
            "enf_xattn_bwd", "enf_last_launch_count", "enf_last_error", "enf_debug_ws_offset", "enf_profile_enable",
-           "enf_profile_collect", "enf_debug_tc_gemm")
+           "enf_profile_collect", "enf_debug_tc_gemm", "enf_debug_gemm")
 
 
 class EnfDesc(ctypes.Structure):
@@ -119,6 +119,8 @@ def load():
     lib.enf_profile_collect.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.enf_debug_tc_gemm.restype = ctypes.c_int
     lib.enf_debug_tc_gemm.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.enf_debug_gemm.restype = ctypes.c_int
+    lib.enf_debug_gemm.argtypes = [ctypes.c_int] * 4 + [vp, i64, i64, vp, i64, i64, vp, vp, i64, vp, vp, vp, ctypes.c_int, vp]
     if lib.enf_abi_version() != 1:
         raise EnfLibraryError("libenf_b200.so ABI version mismatch")
     _lib = lib

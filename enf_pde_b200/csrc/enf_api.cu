@@ -79,13 +79,18 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   const size_t d = D.d, H = D.H, Hd = H * d, d2 = d * d;
   const size_t BZ = (size_t)D.B * D.Z, BC = (size_t)D.B * D.C;
   Y.add("A_q", d * Hd); Y.add("c_q", Hd); Y.add("Wp", d2); Y.add("bp", d); Y.add("W2g", d * 2 * Hd); Y.add("b2g", 2 * Hd);
-  Y.add("M2g", d2); Y.add("c2g", d); Y.add("q_w1T", d2); Y.add("v_w1T", d2); Y.add("WpT", d2);
+  Y.add("M2g", d2); Y.add("c2g", d); Y.add("P1", Hd * Hd); Y.add("b1", Hd); Y.add("W_A", Hd * Hd); Y.add("b_A", Hd);
+  Y.add("dP1", Hd * Hd); Y.add("db1", Hd); Y.add("q_w1T", d2); Y.add("v_w1T", d2); Y.add("WpT", d2);
   Y.add("lam", BZ * ENF_LAM_SIZE); Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
   Y.add("k", BZ * Hd); Y.add("v0", BZ * Hd); Y.add("U", BZ * Hd); Y.add("kappa", BZ * H);
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
     Y.add("cw3", BZ * Hd); Y.add("slog", BC * (size_t)D.Z * H);
+    // tf32 stage GEMMs: activated copies of the decode-MLP pre-activations (their A operands arrive by TMA) and the
+    // low parts W - trunc_tf32(W) of the weights those GEMMs multiply by (3-term split product)
+    Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
+    Y.add("lo_W_A", Hd * Hd); Y.add("lo_fb_w2", Hd * Hd); Y.add("lo_m0_w", Hd * d); Y.add("lo_m1_w", d2); Y.add("lo_mx_w1", d2);
     if (enf_pairs_bwd_tc_supported(D.d, D.H)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       Y.add("dthat", BC * (size_t)D.Z * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
@@ -93,7 +98,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   }
   Y.add("xi", BC * ENF_F_XI);
   Y.add("nbar", BC * Hd); Y.add("lse", BC * H);
-  Y.add("y", BC * Hd); Y.add("y2", BC * Hd); Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
+  Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
   Y.add("fo", BC * Hd); Y.add("o1p", BC * d); Y.add("o2p", BC * d);
   Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("s2", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
   Y.add("dbeff", BZ * Hd); Y.add("dk", BZ * Hd); Y.add("dv0", BZ * Hd); Y.add("dahat", BZ * d); Y.add("da0", BZ * d);
@@ -102,7 +107,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("g_W3", BZ * H * d2); Y.add("g_b3", BZ * Hd); Y.add("g_U", BZ * Hd); Y.add("g_kappa", BZ * H);
   Y.add("g_lam", BZ * ENF_LAM_SIZE); Y.add("g_sigma", BZ); Y.add("gmax", 64);
   Y.add("gf_A_q", d * Hd); Y.add("gf_c_q", Hd); Y.add("gf_Wp", d2); Y.add("gf_bp", d); Y.add("gf_W2g", d * 2 * Hd);
-  Y.add("gf_b2g", 2 * Hd); Y.add("gf_M2g", d2); Y.add("gf_c2g", d);
+  Y.add("gf_b2g", 2 * Hd); Y.add("gf_M2g", d2); Y.add("gf_c2g", d); Y.add("gf_W_A", Hd * Hd); Y.add("gf_b_A", Hd);
   size_t n[ENF_NUM_WEIGHT_LEAVES];
   leaf_sizes(D, rl.I, n);
   static const std::vector<std::string> names = [] {
@@ -151,13 +156,22 @@ struct Ctx {
   float* ws;
   const Layout* Y;
   int launches = 0;
+  bool tc = false;           // tensor-core precision mode: big stage GEMMs run on the tf32 kernels
+  bool gemm_failed = false;
   float* f(const char* name) const { return ws + Y->off(name); }
   void gemm(int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o = EnfGemmOpts()) {
-    launches += enf_gemm(st, M, N, K, A, B, C, o);
+    EnfGemmOpts oo = o;
+    if (!tc) oo.tc = 0;       // callers mark the big tail / W3 products (with_lo, opt_acc_big); honoured in tensor-core mode only
+    int r = enf_gemm(st, M, N, K, A, B, C, oo);
+    if (r < 0) gemm_failed = true; else launches += r;
   }
 };
 
 EnfGemmOpts opt_bias(const float* bias) { EnfGemmOpts o; o.bias = bias; return o; }
+// big-M product by a small weight: tf32 3-term split kernel when the weight's low part is available
+EnfGemmOpts with_lo(EnfGemmOpts o, const float* b_lo) { o.b_lo = b_lo; o.tc = b_lo ? 1 : 0; return o; }
+// weight gradient reduced over all queries / all W3 rows: tf32 kernel in tensor-core mode
+EnfGemmOpts opt_acc_big() { EnfGemmOpts o; o.accumulate = 1; o.tc = 1; return o; }
 EnfGemmOpts opt_acc() { EnfGemmOpts o; o.accumulate = 1; return o; }
 
 EnfPairParams pair_params(const EnfDesc& D, const EnfRecordLayout& rl, const EnfWeights& w, const Ctx& c,
@@ -216,6 +230,18 @@ int enf_profile_collect(int which, float* ms_out, int max_out) {
 
 int enf_last_launch_count(void) { return g_launches; }
 
+int enf_debug_gemm(int use_tc, int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                   int64_t b_cs, const float* B_lo, float* C, int64_t c_rs, const float* bias, const float* aux, float* gelu_out,
+                   int accumulate, enf_stream_t stream) {
+  if (!A || !B || !C) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  EnfGemmOpts o;
+  o.b_lo = B_lo;
+  o.bias = bias; o.mul_gelu_grad = aux; o.gelu_out = gelu_out; o.accumulate = accumulate; o.tc = use_tc;
+  int r = enf_gemm((cudaStream_t)stream, M, N, K, enf_mat(A, a_rs, a_cs), enf_mat(B, b_rs, b_cs), enf_mat(C, c_rs), o);
+  if (r < 0) return fail(ENF_ERR_CUDA, "GEMM could not be configured");
+  return r;
+}
+
 size_t enf_xattn_workspace_bytes(const EnfDesc* desc) {
   EnfRecordLayout rl;
   if (validate(desc, &rl) != ENF_OK) return 0;
@@ -250,12 +276,11 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small: see enf_xattn_workspace_bytes");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ENF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
 
-  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y;
+  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y; c.tc = use_tc;
   cudaStream_t st = c.st;
   const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
   const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
   const int Bx = x_batch_stride == 0 ? 1 : D.B;
-
   // ---- W: fold weights --------------------------------------------------------------------------
   c.gemm(d, Hd, d, enf_mat(w->q_wf, d), enf_mat(w->wq, Hd), enf_mat(c.f("A_q"), Hd));
   c.gemm(1, Hd, d, enf_mat(w->q_bf, d), enf_mat(w->wq, Hd), enf_mat(c.f("c_q"), Hd), opt_bias(w->bq));
@@ -265,6 +290,27 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm(1, 2 * Hd, d, enf_mat(w->fv_beta, d), enf_mat(w->fv_w2, 2 * Hd), enf_mat(c.f("b2g"), 2 * Hd), opt_bias(w->fv_b2));
   c.launches += enf_launch_rowscale(st, w->mx_w2, w->mx_g, c.f("M2g"), d, d);
   c.gemm(1, d, d, enf_mat(w->mx_beta, d), enf_mat(w->mx_w2, d), enf_mat(c.f("c2g"), d), opt_bias(w->mx_b2));
+  // tail fold (exact algebra, tests/folded_model.py): mixer Dense_1, out_proj and the block FFN's Dense_0 are three
+  // linear maps in a row:  e1 = nbar W_A + b_A,  W_A = blockdiag(M2g) wo fb_w1,  b_A = (tile(c2g) wo + bo) fb_w1 + fb_b1
+  {
+    EnfGemmOpts ob; ob.batch = H;
+    c.gemm(d, Hd, d, enf_mat(c.f("M2g"), d), enf_mat(w->wo, Hd, 1, (int64_t)d * Hd), enf_mat(c.f("P1"), Hd, 1, (int64_t)d * Hd), ob);
+    if (cudaMemcpyAsync(c.f("b1"), w->bo, Hd * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(ENF_ERR_CUDA, "copy of out_proj bias failed");
+    for (int h = 0; h < H; ++h)      // head by head in stream order: a deterministic sum
+      c.gemm(1, Hd, d, enf_mat(c.f("c2g"), d), enf_mat(w->wo + (int64_t)h * d * Hd, Hd), enf_mat(c.f("b1"), Hd), opt_acc());
+    c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("W_A"), Hd));
+    c.gemm(1, Hd, Hd, enf_mat(c.f("b1"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("b_A"), Hd), opt_bias(w->fb_b1));
+  }
+  if (use_tc) {
+    EnfSplitList sl;
+    const float* src[5] = {c.f("W_A"), w->fb_w2, w->m0_w, w->m1_w, w->mx_w1};
+    float* dst[5] = {c.f("lo_W_A"), c.f("lo_fb_w2"), c.f("lo_m0_w"), c.f("lo_m1_w"), c.f("lo_mx_w1")};
+    const int nn[5] = {Hd * Hd, Hd * Hd, Hd * d, d * d, d * d};
+    for (int i = 0; i < 5; ++i) { sl.src[i] = src[i]; sl.dst[i] = dst[i]; sl.n[i] = nn[i]; }
+    sl.count = 5;
+    c.launches += enf_launch_split_lo(st, sl);
+  }
 
   // ---- L: per-latent folds ----------------------------------------------------------------------
   c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
@@ -279,7 +325,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm((int)BZ, 1, d, enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("c_q"), 1, 0, d), enf_mat(c.f("kappa"), H, 1, 1), o);
   }
   c.launches += enf_launch_weff(st, D, c.f("W2g"), c.f("b2g"), c.f("v0"), c.f("Weff"), c.f("beff"));
-  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("Weff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("W3"), d));
+  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("Weff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("W3"), d),
+         with_lo(EnfGemmOpts(), use_tc ? c.f("lo_mx_w1") : nullptr));
   c.gemm((int)(BZ * H), d, d, enf_mat(c.f("beff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("b3"), d), opt_bias(w->mx_b1));
 
   // ---- X, P ---------------------------------------------------------------------------------------
@@ -317,17 +364,28 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.launches += nl;
 
   // ---- Q: per-query tail ----------------------------------------------------------------------------
-  c.gemm((int)(BC * H), d, d, enf_mat(c.f("nbar"), d), enf_mat(c.f("M2g"), d), enf_mat(c.f("y"), d), opt_bias(c.f("c2g")));
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("y"), Hd), enf_mat(w->wo, Hd), enf_mat(c.f("y2"), Hd), opt_bias(w->bo));
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("y2"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("e1"), Hd), opt_bias(w->fb_b1));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("nbar"), Hd), enf_mat(c.f("W_A"), Hd), enf_mat(c.f("e1"), Hd),
+         with_lo(opt_bias(c.f("b_A")), use_tc ? c.f("lo_W_A") : nullptr));
   c.launches += enf_launch_ln_fwd(st, c.f("e1"), BC, Hd, w->fb_g, w->fb_beta, c.f("e3c"), c.f("e3"), c.f("erstd"), 1);
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), opt_bias(w->fb_b2));
-  {
+  if (use_tc) {
+    // the tf32 kernels read their A operand with TMA, so gelu is applied by the producer (second output)
+    EnfGemmOpts o;
+    o.tc = 1;
+    o.bias = w->fb_b2; o.gelu_out = c.f("fo_act"); o.b_lo = c.f("lo_fb_w2");
+    c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), o);
+    o.bias = w->m0_b; o.gelu_out = c.f("o1_act"); o.b_lo = c.f("lo_m0_w");
+    c.gemm((int)BC, d, Hd, enf_mat(c.f("fo_act"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
+    o.bias = w->m1_b; o.gelu_out = c.f("o2_act"); o.b_lo = c.f("lo_m1_w");
+    c.gemm((int)BC, d, d, enf_mat(c.f("o1_act"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
+    c.gemm((int)BC, O, d, enf_mat(c.f("o2_act"), d), enf_mat(w->m2_w, O), enf_mat(out, O), opt_bias(w->m2_b));
+  } else {
+    c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), opt_bias(w->fb_b2));
     EnfGemmOpts o; o.act_a = 1;
     o.bias = w->m0_b; c.gemm((int)BC, d, Hd, enf_mat(c.f("fo"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
     o.bias = w->m1_b; c.gemm((int)BC, d, d, enf_mat(c.f("o1p"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
     o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o);
   }
+  if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing fwd: ") + cudaGetErrorString(e));
   {
@@ -358,7 +416,9 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   Layout Y = make_layout(D, rl);
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small");
 
-  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y;
+  const bool tc_fwd = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);
+  const bool tc_bwd = tc_fwd && enf_pairs_bwd_tc_supported(D.d, D.H);
+  Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y; c.tc = tc_fwd;
   cudaStream_t st = c.st;
   const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
   const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
@@ -369,41 +429,42 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (cudaMemsetAsync(c.ws + Y.acc_begin, 0, (Y.acc_end - Y.acc_begin) * sizeof(float), st) != cudaSuccess)
     return fail(ENF_ERR_CUDA, "memset of accumulators failed");
 
-  // ---- Q backward: decode MLP, block FFN, out_proj, M2g ------------------------------------------------
+  // ---- Q backward: decode MLP, block FFN, folded (mixer Dense_1 . out_proj . FFN Dense_0) ---------------------
+  auto LO = [&](const char* name) { return tc_fwd ? c.f(name) : (const float*)nullptr; };
   {
-    EnfGemmOpts wa = opt_acc(); wa.act_a = 1;                 // wgrad with gelu applied to the stored pre-activation
+    // wgrad A operands: gelu of the stored pre-activation (fp32 mode: applied on load; tensor-core mode: the
+    // activated copies written by the forward)
+    EnfGemmOpts wa = opt_acc_big(); wa.act_a = tc_fwd ? 0 : 1;
+    const float* a_o2 = tc_fwd ? c.f("o2_act") : c.f("o2p");
+    const float* a_o1 = tc_fwd ? c.f("o1_act") : c.f("o1p");
+    const float* a_fo = tc_fwd ? c.f("fo_act") : c.f("fo");
     EnfGemmOpts o;
-    c.gemm(d, O, (int)BC, enf_mat(c.f("o2p"), 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
+    o.tc = 1;
+    c.gemm(d, O, (int)BC, enf_mat(a_o2, 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
     colsum(d_out, BC, O, G("m2_b"));
     o.mul_gelu_grad = c.f("o2p");
     c.gemm((int)BC, d, O, enf_mat(d_out, O), enf_mat(w->m2_w, 1, O), enf_mat(c.f("d_o2p"), d), o);
-    c.gemm(d, d, (int)BC, enf_mat(c.f("o1p"), 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
+    c.gemm(d, d, (int)BC, enf_mat(a_o1, 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
     colsum(c.f("d_o2p"), BC, d, G("m1_b"));
-    o.mul_gelu_grad = c.f("o1p");
+    o.mul_gelu_grad = c.f("o1p"); o.b_lo = LO("lo_m1_w");
     c.gemm((int)BC, d, d, enf_mat(c.f("d_o2p"), d), enf_mat(w->m1_w, 1, d), enf_mat(c.f("d_o1p"), d), o);
-    c.gemm(Hd, d, (int)BC, enf_mat(c.f("fo"), 1, Hd), enf_mat(c.f("d_o1p"), d), enf_mat(G("m0_w"), d), wa);
+    c.gemm(Hd, d, (int)BC, enf_mat(a_fo, 1, Hd), enf_mat(c.f("d_o1p"), d), enf_mat(G("m0_w"), d), wa);
     colsum(c.f("d_o1p"), BC, d, G("m0_b"));
-    o.mul_gelu_grad = c.f("fo");
+    o.mul_gelu_grad = c.f("fo"); o.b_lo = LO("lo_m0_w");
     c.gemm((int)BC, Hd, d, enf_mat(c.f("d_o1p"), d), enf_mat(w->m0_w, 1, d), enf_mat(c.f("s0"), Hd), o);      // dfo
   }
-  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("e3"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("fb_w2"), Hd), opt_acc());
+  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("e3"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("fb_w2"), Hd), opt_acc_big());
   colsum(c.f("s0"), BC, Hd, G("fb_b2"));
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->fb_w2, 1, Hd), enf_mat(c.f("s1"), Hd));           // de3
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->fb_w2, 1, Hd), enf_mat(c.f("s1"), Hd),
+         with_lo(EnfGemmOpts(), LO("lo_fb_w2")));                                                               // de3
   c.launches += enf_launch_ln_bwd(st, c.f("s1"), c.f("e3c"), c.f("erstd"), w->fb_g, c.f("e1"), BC, Hd, c.f("s1"),
                                   G("fb_g"), G("fb_beta"), 1);                                                    // de1 (in place)
-  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("y2"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(G("fb_w1"), Hd), opt_acc());
-  colsum(c.f("s1"), BC, Hd, G("fb_b1"));
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("s0"), Hd));           // dy2
-  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("y"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("wo"), Hd), opt_acc());
-  colsum(c.f("s0"), BC, Hd, G("bo"));
-  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->wo, 1, Hd), enf_mat(c.f("s2"), Hd));              // dy
-  c.gemm(d, d, (int)(BC * H), enf_mat(c.f("nbar"), 1, d), enf_mat(c.f("s2"), d), enf_mat(c.f("gf_M2g"), d), opt_acc());
-  colsum(c.f("s2"), BC * H, d, c.f("gf_c2g"));
-  c.gemm((int)(BC * H), d, d, enf_mat(c.f("s2"), d), enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("s0"), d));        // dnbar
+  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("nbar"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(c.f("gf_W_A"), Hd), opt_acc_big());
+  colsum(c.f("s1"), BC, Hd, c.f("gf_b_A"));
+  c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(c.f("W_A"), 1, Hd), enf_mat(c.f("s0"), Hd),
+         with_lo(EnfGemmOpts(), LO("lo_W_A")));                                                                  // dnbar
 
   // ---- P backward --------------------------------------------------------------------------------------
-  const bool tc_fwd = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);
-  const bool tc_bwd = tc_fwd && enf_pairs_bwd_tc_supported(D.d, D.H);
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
   int nl;
   if (tc_bwd) {
@@ -448,11 +509,13 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.launches += nl;
 
   // ---- L backward ----------------------------------------------------------------------------------------
-  c.gemm(d, d, (int)(BZ * H * d), enf_mat(c.f("Weff"), 1, d), enf_mat(c.f("g_W3"), d), enf_mat(G("mx_w1"), d), opt_acc());
+  if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
+  c.gemm(d, d, (int)(BZ * H * d), enf_mat(c.f("Weff"), 1, d), enf_mat(c.f("g_W3"), d), enf_mat(G("mx_w1"), d), opt_acc_big());
   c.gemm(d, d, (int)(BZ * H), enf_mat(c.f("beff"), 1, d), enf_mat(c.f("g_b3"), d), enf_mat(G("mx_w1"), d), opt_acc());
   colsum(c.f("g_b3"), BZ * H, d, G("mx_b1"));
   float* dWeff = c.f("W3");       // W3 is dead after the pair backward
-  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("g_W3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(dWeff, d));
+  c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("g_W3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(dWeff, d),
+         with_lo(EnfGemmOpts(), LO("lo_mx_w1")));
   c.gemm((int)(BZ * H), d, d, enf_mat(c.f("g_b3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(c.f("dbeff"), d));
   c.launches += enf_launch_weff_bwd(st, D, c.f("W2g"), c.f("b2g"), c.f("v0"), dWeff, c.f("dbeff"), c.f("gf_W2g"),
                                     c.f("gf_b2g"), c.f("dv0"));
@@ -485,6 +548,21 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
 
   // ---- W backward: unfold the folded-weight gradients --------------------------------------------------------
   if (dW) {
+    // tail fold: W_A = P1 fb_w1, b_A = b1 fb_w1 + fb_b1, P1 = blockdiag(M2g) wo, b1 = tile(c2g) wo + bo
+    c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), 1, Hd), enf_mat(c.f("gf_W_A"), Hd), enf_mat(G("fb_w1"), Hd));
+    c.launches += enf_launch_add_outer(st, G("fb_w1"), Hd, c.f("b1"), c.f("gf_b_A"), Hd, Hd);
+    c.gemm(Hd, Hd, Hd, enf_mat(c.f("gf_W_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("dP1"), Hd));
+    c.gemm(1, Hd, Hd, enf_mat(c.f("gf_b_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("db1"), Hd));
+    {
+      const int64_t hb = (int64_t)d * Hd;        // one head's block of rows of wo / P1
+      EnfGemmOpts ob; ob.batch = H;
+      c.gemm(d, Hd, d, enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("dP1"), Hd, 1, hb), enf_mat(G("wo"), Hd, 1, hb), ob);
+      for (int h = 0; h < H; ++h) c.launches += enf_launch_add_outer(st, G("wo") + h * hb, Hd, c.f("c2g"), c.f("db1"), d, Hd);
+      for (int h = 0; h < H; ++h) {
+        c.gemm(d, d, Hd, enf_mat(c.f("dP1") + h * hb, Hd), enf_mat(w->wo + h * hb, 1, Hd), enf_mat(c.f("gf_M2g"), d), opt_acc());
+        c.gemm(1, d, Hd, enf_mat(c.f("db1"), Hd), enf_mat(w->wo + h * hb, 1, Hd), enf_mat(c.f("gf_c2g"), d), opt_acc());
+      }
+    }
     c.gemm(d, d, Hd, enf_mat(c.f("gf_A_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_wf"), d));
     c.gemm(d, Hd, d, enf_mat(w->q_wf, 1, d), enf_mat(c.f("gf_A_q"), Hd), enf_mat(G("wq"), Hd));
     c.launches += enf_launch_add_outer(st, G("wq"), Hd, w->q_bf, c.f("gf_c_q"), d, Hd);
@@ -513,6 +591,8 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
       else if (!strcmp(nm, "fv_b1")) src = c.f("gf_bp");
       else if (!strcmp(nm, "fv_b2")) src = c.f("gf_b2g");
       else if (!strcmp(nm, "mx_b2")) src = c.f("gf_c2g");
+      else if (!strcmp(nm, "bo")) src = c.f("db1");
+      else if (!strcmp(nm, "fb_b1")) src = c.f("gf_b_A");
       t.src[i] = src; t.dst[i] = dst[i]; t.n[i] = (int)n[i];
       if ((int)n[i] > maxn) maxn = (int)n[i];
     }
@@ -520,6 +600,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     copy_leaves_kernel<<<dim3(bx, ENF_NUM_WEIGHT_LEAVES), 256, 0, st>>>(t);
     c.launches += 1;
   }
+  if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing bwd: ") + cudaGetErrorString(e));
   g_launches = c.launches;

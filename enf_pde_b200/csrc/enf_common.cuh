@@ -57,6 +57,14 @@ __device__ __forceinline__ float enf_gelu_grad(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x2);
 }
 
+// round-to-nearest to the 10-bit tf32 mantissa: what producers store for operands of the tf32 GEMMs (enf_gemm_tc.cu)
+__device__ __forceinline__ float enf_round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float enf_maybe_round(float x, int rnd) { return rnd ? enf_round_tf32(x) : x; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -84,22 +92,31 @@ struct EnfGemmOpts {
   const float* mul_gelu_grad = nullptr;  // epilogue: result *= gelu'(aux[m,n]) (aux has C's strides)
   int accumulate = 0;               // 1: atomicAdd into C (C must hold the running sum); enables split-K
   float alpha = 1.0f;
+  float* gelu_out = nullptr;        // optional second output gelu(C), laid out like C
+  int round_out = 0;                // 1: store C (and gelu_out) rounded to tf32
+  int tc = 0;                       // 1: use the tf32 tensor-core kernels (enf_gemm_tc.cu) when the shape allows
+  const float* b_lo = nullptr;      // tensor-core path: B - trunc_tf32(B), same strides as B (3-term split product)
 };
 // C[M,N] (+)= alpha * act(A)[M,K] * B[K,N] (+ bias) (* gelu'(aux)); returns number of kernels launched.
 int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o);
+// tf32 tensor-core path: 1 = launched, 0 = shape not taken (use the fp32 kernel), -1 = configuration error
+int enf_gemm_tc(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o);
+// dst[i] = src[i] - trunc_tf32(src[i]) for up to 8 (src, dst, n) triples in one launch (the B_lo operands)
+struct EnfSplitList { const float* src[8]; float* dst[8]; int n[8]; int count; };
+int enf_launch_split_lo(cudaStream_t st, const EnfSplitList& l);
 
 // ---- small stage kernels (enf_stages.cu) -------------------------------------------------------
 int enf_launch_rowscale(cudaStream_t st, const float* W, const float* g, float* out, int rows, int cols);
 int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t ld, float* out, const float* mul, int64_t ld_mul);
 int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
-                      float* out_core, float* out_affine, float* rstd, int gelu_in);
+                      float* out_core, float* out_affine, float* rstd, int gelu_in, int round_affine = 0);
 int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,
-                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in);
+                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx = 0);
 int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi);
 int enf_launch_latent_record(cudaStream_t st, const EnfDesc& d, const float* p, float* lam);
 int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float* p, const float* dlam, float* dp);
 int enf_launch_weff(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
-                    float* Weff, float* beff);
+                    float* Weff, float* beff, int round_weff = 0);
 int enf_launch_weff_bwd(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
                         const float* dWeff, const float* dbeff, float* dW2g, float* db2g, float* dv0);
 int enf_launch_add_outer(cudaStream_t st, float* C, int64_t ldc, const float* u, const float* v, int M, int N);

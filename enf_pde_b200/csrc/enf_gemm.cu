@@ -2,6 +2,8 @@
 // per-query tail (Q) stages.  These stages are a few percent of the work of the fused pair kernels;
 // this kernel favours generality (arbitrary strides => transposes and head-sliced views for free)
 // over peak throughput.  64x64x16 tiles, 256 threads, 4x4 register tile per thread.
+#include <cstdlib>
+
 #include "enf_common.cuh"
 
 namespace {
@@ -14,6 +16,8 @@ struct GemmKArgs {
   float* C; int64_t scm, scn, scb;
   const float* bias; int64_t bias_bs;
   const float* aux;
+  float* C2;
+  int round_out;
   int M, N, K, splitk, kchunk;
   int act_a, accumulate;
   float alpha;
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
       if (bias && ks == 0) v += bias[gn];
       int64_t off = (int64_t)gm * g.scm + (int64_t)gn * g.scn;
       if (g.aux) v *= enf_gelu_grad(g.aux[(int64_t)bz * g.scb + off]);
-      if (g.accumulate) atomicAdd(C + off, v); else C[off] = v;
+      if (g.accumulate) atomicAdd(C + off, v); else C[off] = enf_maybe_round(v, g.round_out);
+      if (g.C2) g.C2[(int64_t)bz * g.scb + off] = enf_maybe_round(enf_gelu(v), g.round_out);
     }
   }
 }
@@ -101,11 +106,16 @@ __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
 
 int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o) {
   if (M <= 0 || N <= 0 || o.batch <= 0) return 0;
+  static const bool no_tc = getenv("ENF_DEBUG_NO_TC_GEMM") != nullptr;     // A/B switch for numerics debugging
+  if (o.tc && !no_tc) {
+    int r = enf_gemm_tc(st, M, N, K, A, B, C, o);
+    if (r != 0) return r;
+  }
   GemmKArgs g;
   g.A = A.p; g.sam = A.rs; g.sak = A.cs; g.sab = A.bs;
   g.B = B.p; g.sbk = B.rs; g.sbn = B.cs; g.sbb = B.bs;
   g.C = const_cast<float*>(C.p); g.scm = C.rs; g.scn = C.cs; g.scb = C.bs;
-  g.bias = o.bias; g.bias_bs = o.bias_bs; g.aux = o.mul_gelu_grad;
+  g.bias = o.bias; g.bias_bs = o.bias_bs; g.aux = o.mul_gelu_grad; g.C2 = o.gelu_out; g.round_out = o.round_out;
   g.M = M; g.N = N; g.K = K; g.act_a = o.act_a; g.accumulate = o.accumulate; g.alpha = o.alpha;
   int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int64_t tiles = (int64_t)tiles_m * tiles_n * o.batch;

@@ -219,7 +219,7 @@ __global__ void latent_record_bwd_kernel(int kind, int Dx, int P, int I, int win
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ in, int64_t M, int N,
                                                      const float* __restrict__ g, const float* __restrict__ b,
                                                      float* __restrict__ out_core, float* __restrict__ out_aff,
-                                                     float* __restrict__ rstd_out, int gelu_in) {
+                                                     float* __restrict__ rstd_out, int gelu_in, int rnd) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ i
       if (gelu_in) v = enf_gelu(v);
       float c = (v - mu) * rstd;
       if (out_core) out_core[r * N + j] = c;
-      if (out_aff) out_aff[r * N + j] = c * g[j] + b[j];
+      if (out_aff) out_aff[r * N + j] = enf_maybe_round(c * g[j] + b[j], rnd);
     }
   }
 }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* dy, const floa
                                                      const float* __restrict__ rstd, const float* __restrict__ g,
                                                      const float* __restrict__ pre, int64_t M, int N,
                                                      float* dx, float* __restrict__ dg,
-                                                     float* __restrict__ db, int gelu_in) {
+                                                     float* __restrict__ db, int gelu_in, int rnd) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* dy, const floa
         float d = dy[r * N + j], c = core[r * N + j];
         float v = rs * (d * g[j] - m1 - c * m2);
         if (gelu_in) v *= enf_gelu_grad(pre[r * N + j]);
-        dx[r * N + j] = v;
+        dx[r * N + j] = enf_maybe_round(v, rnd);
         pg[t] += d * c; pb[t] += d;
       }
     }
@@ -344,7 +344,7 @@ __global__ void rowdot_kernel(const float* __restrict__ A, const float* __restri
 // ---- FiLM effective weights: Weff[b,z,h] = W2g_gamma[:,h] diag(v0[b,z,h]) + W2g_beta[:,h] -----------
 __global__ void __launch_bounds__(256) weff_kernel(int d, int H, const float* __restrict__ W2g,
                                                    const float* __restrict__ b2g, const float* __restrict__ v0,
-                                                   float* __restrict__ Weff, float* __restrict__ beff) {
+                                                   float* __restrict__ Weff, float* __restrict__ beff, int rnd) {
   const int64_t bzh = blockIdx.x;
   const int h = bzh % H;
   const int64_t bz = bzh / H;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) weff_kernel(int d, int H, const float* __
   float* out = Weff + bzh * d * d;
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
     int i = e / d, j = e % d;
-    out[e] = W2g[(int64_t)i * 2 * Hd + h * d + j] * v[j] + W2g[(int64_t)i * 2 * Hd + Hd + h * d + j];
+    out[e] = enf_maybe_round(W2g[(int64_t)i * 2 * Hd + h * d + j] * v[j] + W2g[(int64_t)i * 2 * Hd + Hd + h * d + j], rnd);
   }
   for (int j = threadIdx.x; j < d; j += blockDim.x)
     beff[bzh * d + j] = v[j] * (1.f + b2g[h * d + j]) + b2g[Hd + h * d + j];
@@ -439,16 +439,16 @@ int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t
 }
 
 int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
-                      float* out_core, float* out_affine, float* rstd, int gelu_in) {
+                      float* out_core, float* out_affine, float* rstd, int gelu_in, int round_affine) {
   int blocks = (int)((M + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
-  ln_fwd_kernel<<<blocks, 256, 0, st>>>(in, M, N, g, b, out_core, out_affine, rstd, gelu_in);
+  ln_fwd_kernel<<<blocks, 256, 0, st>>>(in, M, N, g, b, out_core, out_affine, rstd, gelu_in, round_affine);
   return 1;
 }
 
 int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,
-                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in) {
+                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx) {
   int blocks = (int)((M + 7) / 8); if (blocks > 148 * 4) blocks = 148 * 4;
-  ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, N, dx, dg, db, gelu_in);
+  ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, N, dx, dg, db, gelu_in, round_dx);
   return 1;
 }
 
@@ -474,9 +474,9 @@ int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float*
 }
 
 int enf_launch_weff(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
-                    float* Weff, float* beff) {
+                    float* Weff, float* beff, int round_weff) {
   int64_t bzh = (int64_t)d.B * d.Z * d.H;
-  weff_kernel<<<(unsigned)bzh, 256, 0, st>>>(d.d, d.H, W2g, b2g, v0, Weff, beff);
+  weff_kernel<<<(unsigned)bzh, 256, 0, st>>>(d.d, d.H, W2g, b2g, v0, Weff, beff, round_weff);
   return 1;
 }
 
@@ -491,6 +491,23 @@ int enf_launch_weff_bwd(cudaStream_t st, const EnfDesc& d, const float* W2g, con
   return 2;
 }
 
+namespace {
+__global__ void split_lo_kernel(EnfSplitList l) {
+  const int k = blockIdx.y;
+  if (k >= l.count) return;
+  const float* src = l.src[k];
+  float* dst = l.dst[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < l.n[k]; i += gridDim.x * blockDim.x) {
+    float v = src[i];
+    dst[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  }
+}
+}  // namespace
+int enf_launch_split_lo(cudaStream_t st, const EnfSplitList& l) {
+  if (l.count <= 0) return 0;
+  split_lo_kernel<<<dim3(64, l.count), 256, 0, st>>>(l);
+  return 1;
+}
 int enf_launch_add_outer(cudaStream_t st, float* C, int64_t ldc, const float* u, const float* v, int M, int N) {
   add_outer_kernel<<<blocks_for((int64_t)M * N, 256), 256, 0, st>>>(C, ldc, u, v, M, N);
   return 1;

@@ -170,6 +170,15 @@ int64_t enf_debug_ws_offset(const EnfDesc* desc, const char* name, int64_t* num_
  *   mode 2: out[i][j] = sum_r X[r][i] Y[r][j].   X, Y, out: device float32 [128][D]; scratch >= D*D*2 bytes. */
 int enf_debug_tc_gemm(int mode, int D, const float* X, const float* Y, float* out, void* scratch, enf_stream_t stream);
 
+/* Test hook: one stage GEMM  C[M,N] (+)= A[M,K] B[K,N] (+bias) (*gelu'(aux)), optional gelu_out = gelu(C), through the
+ * library's own dispatcher (use_tc != 0: the tf32 tcgen05/TMA kernels when the shape qualifies, else the fp32 kernel).
+ * All matrices are device float32 with explicit (row, column) strides in elements.  B_lo (nullable) = B - trunc_tf32(B)
+ * with B's strides: required by the tensor-core product kernel (3-term split).  Returns the number of kernels
+ * launched, or a negative error code. */
+int enf_debug_gemm(int use_tc, int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                   int64_t b_cs, const float* B_lo, float* C, int64_t c_rs, const float* bias, const float* aux, float* gelu_out,
+                   int accumulate, enf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

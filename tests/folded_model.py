@@ -288,6 +288,12 @@ class Folded:
         f["b2g"] = w["fv_beta"] @ w["fv_w2"] + w["fv_b2"]
         f["M2g"] = w["mx_g"][:, None] * w["mx_w2"]           # (d, d)
         f["c2g"] = w["mx_beta"] @ w["mx_w2"] + w["mx_b2"]
+        # tail fold: mixer Dense_1 (per head), out_proj and the block FFN's Dense_0 are three linear maps in a row
+        H, d = self.cfg.num_heads, self.cfg.num_hidden
+        f["P1"] = torch.cat([f["M2g"] @ w["wo"][h * d:(h + 1) * d] for h in range(H)], 0)      # blockdiag(M2g) wo  (Hd, Hd)
+        f["b1"] = f["c2g"].repeat(H) @ w["wo"] + w["bo"]
+        f["W_A"] = f["P1"] @ w["fb_w1"]
+        f["b_A"] = f["b1"] @ w["fb_w1"] + w["fb_b1"]
         self.f = f
         return f
 
@@ -353,16 +359,14 @@ class Folded:
         H, d = cfg.num_heads, cfg.num_hidden
         B, C = nbar.shape[:2]
         T = {}
-        y = (nbar @ f["M2g"] + f["c2g"]).reshape(B, C, H * d)
-        y2 = y @ w["wo"] + w["bo"]
-        e1 = y2 @ w["fb_w1"] + w["fb_b1"]
+        e1 = nbar.reshape(B, C, H * d) @ f["W_A"] + f["b_A"]
         e3c, e_rstd = ln_core(gelu(e1))
         e3 = e3c * w["fb_g"] + w["fb_beta"]
         fo = e3 @ w["fb_w2"] + w["fb_b2"]
         o1p = gelu(fo) @ w["m0_w"] + w["m0_b"]
         o2p = gelu(o1p) @ w["m1_w"] + w["m1_b"]
         out = gelu(o2p) @ w["m2_w"] + w["m2_b"]
-        T.update(y=y, y2=y2, e1=e1, e3c=e3c, e_rstd=e_rstd, e3=e3, fo=fo, o1p=o1p, o2p=o2p)
+        T.update(e1=e1, e3c=e3c, e_rstd=e_rstd, e3=e3, fo=fo, o1p=o1p, o2p=o2p)
         self.T = T
         return out
 
@@ -384,13 +388,9 @@ class Folded:
         G["fb_g"] = fl(de3 * T["e3c"]).sum(0); G["fb_beta"] = fl(de3).sum(0)
         de2 = ln_core_bwd(de3 * w["fb_g"], T["e3c"], T["e_rstd"])
         de1 = de2 * gelu_grad(T["e1"])
-        G["fb_w1"] = fl(T["y2"]).T @ fl(de1); G["fb_b1"] = fl(de1).sum(0)
-        dy2 = de1 @ w["fb_w1"].T
-        G["wo"] = fl(T["y"]).T @ fl(dy2); G["bo"] = fl(dy2).sum(0)
-        dy = (dy2 @ w["wo"].T).reshape(B, C, H, d)
         Gf = {}
-        Gf["M2g"] = fl(nbar).T @ fl(dy); Gf["c2g"] = fl(dy).sum(0)
-        dnbar = dy @ f["M2g"].T
+        Gf["W_A"] = fl(nbar.reshape(B, C, H * d)).T @ fl(de1); Gf["b_A"] = fl(de1).sum(0)
+        dnbar = (de1 @ f["W_A"].T).reshape(B, C, H, d)
         return dnbar, G, Gf
 
     # ---- stage P backward --------------------------------------------------------------------
@@ -475,8 +475,18 @@ class Folded:
 
     # ---- stage W backward --------------------------------------------------------------------
     def weights_unfold_bwd(self, Gf):
-        w = self.w
+        w, f = self.w, self.f
+        H, d = self.cfg.num_heads, self.cfg.num_hidden
         G = {}
+        # tail fold: W_A = P1 fb_w1, b_A = b1 fb_w1 + fb_b1, P1 = blockdiag(M2g) wo, b1 = tile(c2g) wo + bo
+        G["fb_w1"] = f["P1"].T @ Gf["W_A"] + torch.outer(f["b1"], Gf["b_A"])
+        G["fb_b1"] = Gf["b_A"]
+        dP1 = Gf["W_A"] @ w["fb_w1"].T
+        db1 = Gf["b_A"] @ w["fb_w1"].T
+        G["wo"] = torch.cat([f["M2g"].T @ dP1[h * d:(h + 1) * d] for h in range(H)], 0) + torch.outer(f["c2g"].repeat(H), db1)
+        G["bo"] = db1
+        Gf["M2g"] = sum(dP1[h * d:(h + 1) * d] @ w["wo"][h * d:(h + 1) * d].T for h in range(H))
+        Gf["c2g"] = (db1 @ w["wo"].T).reshape(H, d).sum(0)
         G["q_wf"] = Gf["A_q"] @ w["wq"].T
         G["wq"] = w["q_wf"].T @ Gf["A_q"] + torch.outer(w["q_bf"], Gf["c_q"])
         G["q_bf"] = Gf["c_q"] @ w["wq"].T

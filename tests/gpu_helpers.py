@@ -52,15 +52,15 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
     gw = _weights_struct(grads)
     dp = torch.empty_like(pg); da = torch.empty_like(ag); dsig = torch.empty_like(sg)
     # snapshot forward buffers before the backward recycles some of them
-    names_fwd = ["xi", "lam", "A_q", "c_q", "Wp", "bp", "W2g", "b2g", "M2g", "c2g", "a0", "acore", "ahat", "k", "v0", "U",
-                 "kappa", "Weff", "beff", "W3", "b3", "nbar", "lse", "y", "y2", "e1", "e3c", "e3", "fo", "o1p", "o2p"]
+    names_fwd = ["xi", "lam", "A_q", "c_q", "Wp", "bp", "W2g", "b2g", "M2g", "c2g", "W_A", "b_A", "a0", "acore", "ahat", "k", "v0", "U",
+                 "kappa", "Weff", "beff", "W3", "b3", "nbar", "lse", "e1", "e3c", "e3", "fo", "o1p", "o2p"]
     snap = {n: ws_view(lib, desc, ws, n).clone() for n in names_fwd}
     rc = lib.enf_xattn_bwd(ctypes.byref(desc), ctypes.byref(w), ptr(xg), xbs, ptr(pg), ptr(ag), sig_ptr, ptr(dg), ctypes.byref(gw),
                            ptr(dp), ptr(da), ptr(dsig), ptr(ws), nbytes, st)
     assert rc == 0, lib.enf_last_error()
     torch.cuda.synchronize()
     names_bwd = ["g_W3", "g_b3", "g_U", "g_kappa", "g_sigma", "gf_A_q", "gf_c_q", "gf_Wp", "gf_bp", "gf_W2g", "gf_b2g",
-                 "gf_M2g", "gf_c2g"]
+                 "gf_M2g", "gf_c2g", "gf_W_A", "gf_b_A"]
     snap.update({n: ws_view(lib, desc, ws, n).clone() for n in names_bwd})
 
     # float64 folded model
@@ -69,13 +69,13 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
     out_ref = m.forward(xe.double(), p.double(), a.double(), sigma.double())
     G, dp_ref, da_ref, ds_ref = m.backward(xe.double(), p.double(), a.double(), sigma.double(), d_out.double())
     ref = dict(xi=m.xi[:1] if shared_x else m.xi, lam=m.L["Lam"], A_q=m.f["A_q"], c_q=m.f["c_q"], Wp=m.f["Wp"], bp=m.f["bp"],
-               W2g=m.f["W2g"], b2g=m.f["b2g"], M2g=m.f["M2g"], c2g=m.f["c2g"], a0=m.L["a0"], acore=m.L["ahat_core"],
+               W2g=m.f["W2g"], b2g=m.f["b2g"], M2g=m.f["M2g"], c2g=m.f["c2g"], W_A=m.f["W_A"], b_A=m.f["b_A"], a0=m.L["a0"], acore=m.L["ahat_core"],
                ahat=m.L["ahat"], k=m.L["k"], v0=m.L["v0"], U=m.L["U"], kappa=m.L["kappa"], Weff=m.L["Weff"], beff=m.L["beff"],
-               W3=m.L["W3"], b3=m.L["b3"], nbar=m.S["nbar"], lse=m.S["lse"], y=m.T["y"], y2=m.T["y2"], e1=m.T["e1"],
+               W3=m.L["W3"], b3=m.L["b3"], nbar=m.S["nbar"], lse=m.S["lse"], e1=m.T["e1"],
                e3c=m.T["e3c"], e3=m.T["e3"], fo=m.T["fo"], o1p=m.T["o1p"], o2p=m.T["o2p"],
                g_W3=m.GL["W3"], g_b3=m.GL["b3"], g_U=m.GL["U"], g_kappa=m.GL["kappa"], g_sigma=m.GL["sigma"],
                gf_A_q=m.Gf["A_q"], gf_c_q=m.Gf["c_q"], gf_Wp=m.Gf["Wp"], gf_bp=m.Gf["bp"], gf_W2g=m.Gf["W2g"],
-               gf_b2g=m.Gf["b2g"], gf_M2g=m.Gf["M2g"], gf_c2g=m.Gf["c2g"])
+               gf_b2g=m.Gf["b2g"], gf_M2g=m.Gf["M2g"], gf_c2g=m.Gf["c2g"], gf_W_A=m.Gf["W_A"], gf_b_A=m.Gf["b_A"])
     errs = {}
     for n in names_fwd + names_bwd:
         r = ref[n].reshape(-1)
