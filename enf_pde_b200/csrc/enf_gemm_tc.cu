@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_f_kernel(const __grid_c
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ CUtensorMap tmBlo, FArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   const uint32_t b_bytes = (uint32_t)g.N * 128;
   const uint32_t stage_bytes = 2 * kABytesF + 2 * b_bytes;        // A | A_lo | B | B_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)g.stages * stage_bytes);
@@ -305,7 +305,7 @@ template <int MT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_w_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmG, WArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   constexpr uint32_t a_bytes = MT * 4 * 4096;
   const uint32_t g_bytes = (uint32_t)(g.N / 32) * 4096;
   const uint32_t stage_bytes = a_bytes + g_bytes;

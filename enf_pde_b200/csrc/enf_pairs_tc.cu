@@ -45,7 +45,7 @@ template <int D, int H>
 __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
   using C = TcCfg<D, H>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW = base + C::OFF_W;
   uint8_t* sS = base + C::OFF_S;
   uint8_t* sA0 = base + C::OFF_A0;

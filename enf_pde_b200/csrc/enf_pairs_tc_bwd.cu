@@ -97,7 +97,7 @@ template <int D, int H>
 __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW1v = base;
   uint8_t* sWp = base + C::WIMG;
   uint8_t* sW3 = base + 2 * C::WIMG;                 // [2]
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(Enf
   using C = BwdCfg<D, H>;
   constexpr int HD = C::HD;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW1q = base;
   uint8_t* sW1v = base + C::WIMG;
   uint8_t* sWp = base + 2 * C::WIMG;

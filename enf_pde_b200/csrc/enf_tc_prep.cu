@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(int mode, const float
                                                            const float* __restrict__ Y, const uint8_t* __restrict__ img,
                                                            float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   constexpr uint32_t BLK = 128 * 128;            // bytes of one [128 rows][64] block
   constexpr uint32_t TILE = (D / 64) * BLK;
   uint8_t* tA = base;
