@@ -27,18 +27,21 @@ template <int D, int H> struct TcCfg {
   static constexpr uint32_t WBLK = D * 128;            // bytes of one 64-feature block of a weight image
   static constexpr uint32_t ABLK = ROWS * 128;         // bytes of one 64-feature block of an activation tile
   static constexpr uint32_t ATILE = (D / 64) * ABLK;
-  static constexpr int TMEM_COLS = 2 * D;              // T0 | T1   (power of two: 128 or 256)
+  static constexpr int TMEM_COLS = 3 * D <= 256 ? 256 : 512;   // T0 | T1 | RFF phases (D columns)
   // byte offsets inside the 1024-aligned dynamic shared memory
   static constexpr uint32_t OFF_W = 0;                 // W1_q, W1_v, W' images
   static constexpr uint32_t OFF_S = 3 * WIMG;          // W3[z,0] stage
   static constexpr uint32_t OFF_A0 = OFF_S + WIMG;
   static constexpr uint32_t OFF_A1 = OFF_A0 + ATILE;
-  static constexpr uint32_t OFF_F = OFF_A1 + ATILE;    // float arrays start here
+  static constexpr uint32_t OFF_U = OFF_A1 + ATILE;    // projection operand: invariants of the 128 rows (2 atoms)
+  static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;   // projection operand: [Omega_q | Omega_v] (D / 64 atoms)
+  static constexpr uint32_t OFF_F = OFF_OM + (D / 64) * kProjAtom;    // float arrays start here
   // float arrays (counts)
-  static constexpr int F_XI = ROWS * 8, F_LAM = 64, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_BIAS = 3 * D,
-                       F_OM = 2 * 6 * (D / 2), F_SPART = NQ * ROWS * H, F_EXCH = 2 * NQ * ROWS * 2;
-  static constexpr int F_TOTAL = F_XI + F_LAM + F_UZ + F_KAP + F_B3 + F_BIAS + F_OM + F_SPART + F_EXCH;
+  static constexpr int F_LAM = 2 * 64, F_WIN = 2 * ROWS, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_BIAS = 3 * D,
+                       F_SPART = NQ * ROWS * H, F_EXCH = 2 * NQ * ROWS * 2;
+  static constexpr int F_TOTAL = F_LAM + F_WIN + F_UZ + F_KAP + F_B3 + F_BIAS + F_SPART + F_EXCH;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 template <int D, int H>
@@ -50,14 +53,15 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   uint8_t* sS = base + C::OFF_S;
   uint8_t* sA0 = base + C::OFF_A0;
   uint8_t* sA1 = base + C::OFF_A1;
+  uint8_t* sU = base + C::OFF_U;
+  uint8_t* sOm = base + C::OFF_OM;
   float* f = reinterpret_cast<float*>(base + C::OFF_F);
-  float* s_xi = f; f += C::F_XI;
-  float* s_lam = f; f += C::F_LAM;
+  float* s_lam = f; f += C::F_LAM;            // [2][64]: pose records of this and the next latent
+  float* s_win = f; f += C::F_WIN;            // [2][ROWS]: window values of this and the next latent
   float* s_uz = f; f += C::F_UZ;
   float* s_kap = f; f += C::F_KAP;
   float* s_b3 = f; f += C::F_B3;
   float* s_bias = f; f += C::F_BIAS;          // b1q | b1v | bp
-  float* s_om = f; f += C::F_OM;              // omega_q | omega_v, scaled by 2 pi
   float* s_spart = f; f += C::F_SPART;        // [NQ][ROWS][H]
   float* s_exch = f; f += C::F_EXCH;          // two alternating [NQ][ROWS][2] exchange buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   uint64_t* bar_g3 = bars + 3;
   uint64_t* bar_g4 = bars + 4;                // [2]
   uint64_t* bar_w3 = bars + 6;                // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_p = bars + 8;                 // RFF phases of the next latent are in TMEM
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = warp & 3, cq = warp >> 2;
@@ -78,27 +83,31 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   constexpr int HD = D / 2;
 
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) tc::mbar_init(bars + i, 1);
+    for (int i = 0; i < 9; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
   if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
   // per-CTA constants
-  for (int e = tid; e < ROWS * 8; e += C::NT) {
-    int r = e >> 3;
-    s_xi[e] = (c0 + r < P.C) ? P.xi[(int64_t)b * P.xi_bs + (int64_t)(c0 + r) * 8 + (e & 7)] : 0.f;
-  }
   for (int e = tid; e < D; e += C::NT) { s_bias[e] = P.q_b1[e]; s_bias[D + e] = P.v_b1[e]; s_bias[2 * D + e] = P.bp[e]; }
-  for (int e = tid; e < 6 * HD; e += C::NT) {
-    const float two_pi = 6.283185307179586f;
-    s_om[e] = e < P.I * HD ? two_pi * P.q_omega[e] : 0.f;
-    s_om[6 * HD + e] = e < P.I * HD ? two_pi * P.v_omega[e] : 0.f;
+  if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[(int64_t)b * P.Z * ENF_LAM_SIZE + tid];
+  proj_zero(sU, 2, tid, C::NT);
+  proj_zero(sOm, D / 64, tid, C::NT);
+  // the record thread of a row (cq == 0) keeps the row's query features in registers for the whole kernel
+  float xi_r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xi_r[k] = 0.f;
+  if (cq == 0 && row_valid) {
+    const float4* src = reinterpret_cast<const float4*>(P.xi + (int64_t)b * P.xi_bs + (int64_t)(c0 + row) * 8);
+    float4 a = __ldg(src), c = __ldg(src + 1);
+    xi_r[0] = a.x; xi_r[1] = a.y; xi_r[2] = a.z; xi_r[3] = a.w; xi_r[4] = c.x; xi_r[5] = c.y; xi_r[6] = c.z; xi_r[7] = c.w;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = *s_tmem;
-  const uint32_t t0 = tm, t1 = tm + D;
-  const uint32_t my_t = ((uint32_t)(lq * 32) << 16) + col0;      // lane-quadrant / column offset of this warp
+  const uint32_t t0 = tm, t1 = tm + D, tp = tm + 2 * D;
+  const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
+  const uint32_t my_t = lane_off + col0;      // lane-quadrant / column offset of this warp
 
   if (tid == 0) {
     tc::mbar_expect_tx(bar_w, 3 * C::WIMG);
@@ -107,6 +116,24 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::bulk_g2s(sW + 2 * C::WIMG, P.img_Wp, C::WIMG, bar_w);
     tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
     tc::bulk_g2s(sS, P.img_W3 + ((int64_t)b * P.Z * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+  }
+  const uint32_t aA0 = tc::smem_u32(sA0), aA1 = tc::smem_u32(sA1), aS = tc::smem_u32(sS), aW = tc::smem_u32(sW);
+  const uint32_t aU = tc::smem_u32(sU), aOm = tc::smem_u32(sOm);
+
+  // Omega image [Omega_q | Omega_v]; invariants of latent 0; phases of latent 0
+  proj_build_omega(sOm, 0, P.q_omega, P.I, HD, tid, C::NT);
+  proj_build_omega(sOm, HD, P.v_omega, P.I, HD, tid, C::NT);
+  if (cq == 0) {
+    const Rec rec = pair_record(P, s_lam, xi_r, P.sigma ? P.sigma[(int64_t)b * P.Z] : 1.f);
+    proj_write_u(sU, row, rec.u, P.I);
+    s_win[row] = rec.w;
+  }
+  tc::fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tc::tc_fence_after();
+    issue_proj(tp, aU, aOm, D);
+    tc::mma_commit(bar_p);
   }
 
   int xw = 0;                                  // which exchange buffer is next
@@ -119,21 +146,22 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     for (int j = 0; j < 32; ++j) acc[h][j] = 0.f;
   }
 
-  const uint32_t aA0 = tc::smem_u32(sA0), aA1 = tc::smem_u32(sA1), aS = tc::smem_u32(sS), aW = tc::smem_u32(sW);
-
   for (int z = 0; z < P.Z; ++z) {
     const uint32_t par = z & 1;
     const int64_t bz = (int64_t)b * P.Z + z;
-    // ---- (a) per-latent vectors, invariants, gamma_q ----------------------------------------------------
-    if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[bz * ENF_LAM_SIZE + tid];
+    const bool more = z + 1 < P.Z;
+    // ---- (a) per-latent vectors; gamma_q, gamma_v from the phases the tensor core left in TMEM -----------------------
     if (tid < H) s_kap[tid] = P.kappa[bz * H + tid];
+    if (more && tid < ENF_LAM_SIZE) s_lam[(par ^ 1) * 64 + tid] = P.lam[(bz + 1) * ENF_LAM_SIZE + tid];
     for (int e = tid; e < H * D; e += C::NT) {
       s_uz[e] = P.U[bz * H * D + e];
       s_b3[e] = P.b3[bz * H * D + e];
     }
-    __syncthreads();
-    const Rec rec = pair_record(P, s_lam, s_xi + row * 8, P.sigma ? P.sigma[bz] : 1.f);
-    rff_to_tile<D>(rec, P.I, s_om, sA0, C::ABLK, row, col0);
+    tc::mbar_wait(bar_p, par);
+    tc::tc_fence_after();
+    rff_from_proj<D, false>(tp + lane_off + 16 * cq, sA0, nullptr, C::ABLK, row, 16 * cq);
+    rff_from_proj<D, false>(tp + lane_off + HD + 16 * cq, sA1, nullptr, C::ABLK, row, 16 * cq);
+    tc::tc_fence_before();
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -141,15 +169,15 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       tc::tc_fence_after();
       issue_gemm<D>(t0, aA0, aW, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g1);
-    }
-    // ---- (b) gamma_v (overlaps GEMM1) -------------------------------------------------------------------
-    rff_to_tile<D>(rec, P.I, s_om + 6 * HD, sA1, C::ABLK, row, col0);
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc::tc_fence_after();
       issue_gemm<D>(t1, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g2);
+    }
+    // ---- (b) invariants of the NEXT latent -> projection operand (its MMA is issued with GEMM3 below) ------------------
+    const float win = s_win[par * ROWS + row];
+    if (more && cq == 0) {
+      const Rec rec = pair_record(P, s_lam + (par ^ 1) * 64, xi_r, P.sigma ? P.sigma[bz + 1] : 1.f);
+      proj_write_u(sU, row, rec.u, P.I);
+      s_win[(par ^ 1) * ROWS + row] = rec.w;
     }
     // ---- (c) E1: h1q = relu(T0 + b1q); logit partials (overlaps GEMM2) -------------------------------------
     float v[32];
@@ -189,6 +217,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       tc::tc_fence_after();
       issue_gemm<D>(t0, aA0, aW + 2 * C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g3);
+      if (more) {                      // phases of the next latent (every thread read this latent's before the barrier)
+        issue_proj(tp, aU, aOm, D);
+        tc::mma_commit(bar_p);
+      }
     }
     // softmax statistics for this latent (every thread of the row, redundantly; overlaps GEMM3)
     float pw[H], corr[H];
@@ -197,7 +229,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       float dot = 0.f;
 #pragma unroll
       for (int q = 0; q < C::NQ; ++q) dot += s_spart[(q * ROWS + row) * H + h];
-      float sv = scale * (dot + s_kap[h]) + rec.w;
+      float sv = scale * (dot + s_kap[h]) + win;
       if (cq == 0 && row_valid && P.slog) P.slog[(((int64_t)b * P.C + c0 + row) * P.Z + z) * H + h] = sv;
       float m_new = fmaxf(m_run[h], sv);
       corr[h] = __expf(m_run[h] - m_new);
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       l_run[h] = l_run[h] * corr[h] + pw[h];
       m_run[h] = m_new;
     }
-    // ---- (e) E3: g = gelu(T0 + b'), row statistics, g -> A1 (LayerNorm applied after GEMM4 as a correction) ----
+    // ---- (e) E3: g = gelu(T0 + b'), row statistics, LayerNorm -> A1 ----
     tc::mbar_wait(bar_g3, par);
     tc::tc_fence_after();
     if (H > 1 && tid == 0) {          // A0 is free again: stream W3[z,1] into it
@@ -252,7 +284,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     for (int h = 0; h < H; ++h) {
       tc::mbar_wait(&bar_g4[h], par);
       tc::tc_fence_after();
-      if (h == 0 && tid == 0 && z + 1 < P.Z) {       // stage buffer is free: prefetch next latent's W3[.,0]
+      if (h == 0 && tid == 0 && more) {       // stage buffer is free: prefetch next latent's W3[.,0]
         tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
         tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
       }

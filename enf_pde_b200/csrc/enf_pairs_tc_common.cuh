@@ -133,6 +133,71 @@ __device__ __forceinline__ void rff_to_tile_split(const Rec& r, int I, const flo
   }
 }
 
+// ---- RFF projection on the tensor core ---------------------------------------------------------------------------
+// proj[row][n] = 2 pi sum_i u[row][i] Omega[i][n] as ONE small MMA per 128-row tile (M = 128, N = #frequencies, K = 32)
+// instead of I FMAs + I shared loads per output element.  fp16 operands carry a two-term split of both factors so the
+// phase keeps fp32-level accuracy:   k 0..5: u_hi * Om_hi    k 6..11: u_lo * Om_hi    k 12..17: u_hi * Om_lo   (rest 0).
+// Both operands are MN-major, 128-byte-swizzled tiles of [32 k-rows][64 halves] per 64-wide atom:
+//   sU  [2 atoms][32][128 B]  (8 KB)   written per tile by one thread per query row,
+//   sOm [N/64 atoms][32][128 B]        built once per CTA.
+constexpr uint32_t kProjAtom = 32 * 128;
+__device__ __forceinline__ uint32_t proj_elem_off(int k, int m) {      // byte offset of element (k-row k, MN index m)
+  return (uint32_t)((m >> 6) * kProjAtom + k * 128 + ((((m & 63) >> 3) ^ (k & 7)) << 4) + (m & 7) * 2);
+}
+__device__ __forceinline__ void proj_store_pair(uint8_t* tile, int i, int m, float val, bool a_side) {
+  const __half hi = __float2half_rn(val);
+  const __half lo = __float2half_rn(val - __half2float(hi));
+  *reinterpret_cast<__half*>(tile + proj_elem_off(i, m)) = hi;
+  *reinterpret_cast<__half*>(tile + proj_elem_off(6 + i, m)) = a_side ? lo : hi;
+  *reinterpret_cast<__half*>(tile + proj_elem_off(12 + i, m)) = a_side ? hi : lo;
+}
+// zero a projection operand tile (all threads), before the first write
+__device__ __forceinline__ void proj_zero(uint8_t* tile, int natoms, int tid, int nt) {
+  uint4* p = reinterpret_cast<uint4*>(tile);
+  for (int e = tid; e < natoms * (int)kProjAtom / 16; e += nt) p[e] = make_uint4(0u, 0u, 0u, 0u);
+}
+// Omega image: column n of the tile = frequency j of embedding `omega` (I x HD, row-major), scaled by 2 pi
+__device__ __forceinline__ void proj_build_omega(uint8_t* tile, int n0, const float* __restrict__ omega, int I, int HD, int tid, int nt) {
+  for (int e = tid; e < I * HD; e += nt) {
+    const int i = e / HD, j = e % HD;
+    proj_store_pair(tile, i, n0 + j, 6.283185307179586f * omega[e], false);
+  }
+}
+__device__ __forceinline__ void proj_write_u(uint8_t* tile, int row, const float* u, int I) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) if (i < I) proj_store_pair(tile, i, row, u[i], true);
+}
+// D[128 x N] = sU^T sOm  (N = 64 or 128)
+__device__ __forceinline__ void issue_proj(uint32_t d_tmem, uint32_t u_addr, uint32_t om_addr, int N) {
+  const uint32_t idesc = tc::make_idesc(ROWS, N, tc::kOperandFmt, 1, 1);
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+    tc::mma_f16(d_tmem, tc::desc_mnmajor(u_addr + kk * 2048, kProjAtom), tc::desc_mnmajor(om_addr + kk * 2048, kProjAtom), idesc, kk > 0);
+}
+// my 16 phases (TMEM columns t_proj .. +15 of my lane) -> sin | cos -> 16-bit, swizzled A tile: columns j0.. and HD + j0..
+// SPLIT: also the low part of a two-term 16-bit split into tile_lo.
+template <int D, bool SPLIT>
+__device__ __forceinline__ void rff_from_proj(uint32_t t_proj, uint8_t* tile_hi, uint8_t* tile_lo, uint32_t ablk, int row, int j0) {
+  constexpr int HD = D / 2;
+  float ph[16];
+  tc::tmem_ld16(t_proj, ph);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int c8 = 0; c8 < 16; c8 += 8) {
+    float sn[8], cs[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { sn[t] = __sinf(ph[c8 + t]); cs[t] = __cosf(ph[c8 + t]); }
+    tc::st_row8_bf16(tile_hi, ablk, row, j0 + c8, sn);
+    tc::st_row8_bf16(tile_hi, ablk, row, HD + j0 + c8, cs);
+    if (SPLIT) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { sn[t] -= tc::round_operand(sn[t]); cs[t] -= tc::round_operand(cs[t]); }
+      tc::st_row8_bf16(tile_lo, ablk, row, j0 + c8, sn);
+      tc::st_row8_bf16(tile_lo, ablk, row, HD + j0 + c8, cs);
+    }
+  }
+}
+
 // D[128 x N=D] = A[128 x K=D] (K-major activation tile) * B (K-major weight image: rows = output feature)
 template <int D>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate = 0) {
