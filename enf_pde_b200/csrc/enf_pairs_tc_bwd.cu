@@ -103,16 +103,16 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   uint8_t* sW3 = base + 2 * C::WIMG;                 // [2]
   uint8_t* sB0 = base + 4 * C::WIMG;
   uint8_t* sB1 = sB0 + C::ATILE;
-  float* f = reinterpret_cast<float*>(sB1 + C::ATILE);
-  float* s_xi = f; f += ROWS * 8;
+  uint8_t* sU = sB1 + C::ATILE;                       // RFF projection operands (enf_pairs_tc_common.cuh)
+  uint8_t* sOm = sU + 2 * kProjAtom;                  // Omega_v image, one 64-wide atom
+  float* f = reinterpret_cast<float*>(sOm + kProjAtom);
   float* s_lam = f; f += 64;
   float* s_bias = f; f += 2 * D;                      // b1v | bp
   float* s_b3 = f; f += H * D;
-  float* s_om = f; f += 6 * C::HD;
   float* s_exch = f; f += 2 * C::NQ * ROWS * 2;
   float* s_db3 = f; f += H * D;
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
-  uint64_t *bar_w = bars, *bar_g2 = bars + 1, *bar_g3 = bars + 2, *bar_g4 = bars + 3 /*[2]*/, *bar_gb = bars + 5 /*[2]*/;
+  uint64_t *bar_w = bars, *bar_g2 = bars + 1, *bar_g3 = bars + 2, *bar_g4 = bars + 3 /*[2]*/, *bar_gb = bars + 5 /*[2]*/, *bar_p = bars + 7;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[bz * ENF_LAM_SIZE + tid];
   for (int e = tid; e < D; e += C::NT) { s_bias[e] = P.v_b1[e]; s_bias[D + e] = P.bp[e]; }
   for (int e = tid; e < H * D; e += C::NT) { s_b3[e] = P.b3[bz * H * D + e]; s_db3[e] = 0.f; }
-  for (int e = tid; e < 6 * C::HD; e += C::NT) s_om[e] = e < P.I * C::HD ? 6.283185307179586f * P.v_omega[e] : 0.f;
+  proj_zero(sU, 2, tid, C::NT);
+  proj_zero(sOm, 1, tid, C::NT);
   float gs, inv_gs;
   load_scale(P.gmax, gs, inv_gs);
   tc::tc_fence_before();
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   tc::tc_fence_after();
   const uint32_t tm = *s_tmem;
   const uint32_t t0 = tm, t1 = tm + D, tW3 = tm + 2 * D;
-  const uint32_t my_t = ((uint32_t)(lq * 32) << 16) + col0;
+  const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
+  const uint32_t my_t = lane_off + col0;
   if (tid == 0) {
     tc::mbar_expect_tx(bar_w, (2 + H) * C::WIMG);
     tc::bulk_g2s(sW1v, P.img_v_w1, C::WIMG, bar_w);
@@ -145,23 +147,43 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
     for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);
   }
   const uint32_t aB0 = tc::smem_u32(sB0), aB1 = tc::smem_u32(sB1), aW1v = tc::smem_u32(sW1v), aWp = tc::smem_u32(sWp),
-                 aW3 = tc::smem_u32(sW3);
+                 aW3 = tc::smem_u32(sW3), aU = tc::smem_u32(sU), aOm = tc::smem_u32(sOm);
   int xw = 0;
   const int ntiles = (P.C + ROWS - 1) / ROWS;
   const float sigma = P.sigma ? P.sigma[bz] : 1.f;
+  // invariants of one query row of tile `ct` -> projection operand (one thread per row)
+  auto write_invariants = [&](int ct) {
+    float xi_r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xi_r[k] = 0.f;
+    if (ct * ROWS + row < P.C) {
+      const float4* src = reinterpret_cast<const float4*>(P.xi + (int64_t)b * P.xi_bs + (int64_t)(ct * ROWS + row) * 8);
+      float4 a = __ldg(src), c = __ldg(src + 1);
+      xi_r[0] = a.x; xi_r[1] = a.y; xi_r[2] = a.z; xi_r[3] = a.w; xi_r[4] = c.x; xi_r[5] = c.y; xi_r[6] = c.z; xi_r[7] = c.w;
+    }
+    const Rec rec = pair_record(P, s_lam, xi_r, sigma);
+    proj_write_u(sU, row, rec.u, P.I);
+  };
+  proj_build_omega(sOm, 0, P.v_omega, P.I, C::HD, tid, C::NT);
+  if (cq == 0) write_invariants(0);
+  tc::fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tc::tc_fence_after();
+    issue_proj(t0, aU, aOm, C::HD);
+    tc::mma_commit(bar_p);
+  }
 
   for (int ct = 0; ct < ntiles; ++ct) {
     const uint32_t par = ct & 1;
     const int c0 = ct * ROWS;
     const bool valid = c0 + row < P.C;
     const int64_t bc = (int64_t)b * P.C + c0 + row;
-    for (int e = tid; e < ROWS * 8; e += C::NT) {
-      int r = e >> 3;
-      s_xi[e] = (c0 + r < P.C) ? P.xi[(int64_t)b * P.xi_bs + (int64_t)(c0 + r) * 8 + (e & 7)] : 0.f;
-    }
-    __syncthreads();
-    const Rec rec = pair_record(P, s_lam, s_xi + row * 8, sigma);
-    rff_to_tile<D>(rec, P.I, s_om, sB0, C::ABLK, row, col0);
+    // gamma_v from the phases the tensor core left in T0
+    tc::mbar_wait(bar_p, par);
+    tc::tc_fence_after();
+    rff_from_proj<D, false>(t0 + lane_off + 16 * cq, sB0, nullptr, C::ABLK, row, 16 * cq);
+    tc::tc_fence_before();
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -170,6 +192,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
       issue_gemm<D>(t0, aB0, aW1v, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g2);
     }
+    if (cq == 0 && ct + 1 < ntiles) write_invariants(ct + 1);       // next tile's projection operand (overlaps GEMM2)
     float v[32];
     // E2: h1v = relu(T0 + b1v) -> B1
     tc::mbar_wait(bar_g2, par);
@@ -297,6 +320,13 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
     tc::tmem_ld_wait();
     if (valid) st_half32(P.dthat + ((bz * P.C) + c0 + row) * D + col0, v);
     tc::tc_fence_before();
+    tc::fence_proxy_async();
+    __syncthreads();                          // T0 has been read by everyone; the next tile's invariants are in sU
+    if (tid == 0 && ct + 1 < ntiles) {
+      tc::tc_fence_after();
+      issue_proj(t0, aU, aOm, C::HD);
+      tc::mma_commit(bar_p);
+    }
   }
   // flush dW3[b,z,h] (lane = input feature, column = output feature) and db3
   __syncthreads();
@@ -707,7 +737,7 @@ int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
   int blocks = (int)((BC * H * 32 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   bwd_prep_kernel<<<blocks, 256, 0, st>>>(p.dnbar, p.nbar, BC * H, D, const_cast<float*>(p.Dg), const_cast<float*>(p.gmax));
-  size_t smem_a = 4 * C::WIMG + 2 * C::ATILE + (ROWS * 8 + 64 + 2 * D + H * D + 6 * C::HD + 2 * C::NQ * ROWS * 2 + H * D) * 4 + 128 + 1024;
+  size_t smem_a = 4 * C::WIMG + 2 * C::ATILE + 3 * kProjAtom + (64 + 2 * D + H * D + 2 * C::NQ * ROWS * 2 + H * D) * 4 + 128 + 1024;
   size_t smem_b = 3 * C::WIMG + 3 * C::ATILE +
                   (ROWS * 8 + 64 + H * D + 3 * D + 12 * C::HD + 2 * C::NQ * ROWS * 2 + ROWS * 8 * 2 + ROWS + H * D + 3 * D + 64 + 8) * 4 + 128 + 1024;
   if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
