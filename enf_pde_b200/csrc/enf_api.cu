@@ -94,6 +94,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     if (enf_pairs_bwd_tc_supported(D.d, D.H)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       Y.add("dthat", BC * (size_t)D.Z * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
+      Y.add("duv", BC * (size_t)D.Z * 8);
     }
   }
   Y.add("xi", BC * ENF_F_XI);
@@ -481,7 +482,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_q_w1_lo = (const uint8_t*)c.f("img_q_w1_lo"); tp.img_v_w1_lo = (const uint8_t*)c.f("img_v_w1_lo");
     tp.U = pp.U; tp.b3 = pp.b3; tp.slog = c.f("slog"); tp.lse = pp.lse; tp.nbar = pp.nbar;
     tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax");
-    tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc");
+    tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");
     tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
     tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");
     tp.g_Wp = c.f("gf_Wp"); tp.g_bp = c.f("gf_bp");

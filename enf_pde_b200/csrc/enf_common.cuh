@@ -184,10 +184,12 @@ struct EnfPairTcBwdParams {
   float* Dg;                                 // [B,C,H]   dnbar . nbar                (written by the prep kernel)
   float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernel)
   __half* dthat;                             // [B,Z,C,d] scaled cotangent of that    (A -> B)
-  float* ds;                                 // [B,Z,C,H] scaled cotangent of logits  (A -> B)
+  float* ds;                                 // [B,Z,C,H] scaled cotangent of logits  (A -> C)
+  float* duv;                                // [B,Z,C,8] scaled cotangent of the invariants through the value path (B -> C)
   float* g_W3; float* g_b3;                  // per-latent outputs of A
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // shared-weight grads (atomics)
   float* g_U; float* g_kappa; float* g_lam; float* g_sigma;                                // per-latent outputs of B
 };
 bool enf_pairs_bwd_tc_supported(int d, int H);
 int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);
+int enf_launch_pairs_bwd_tc_q(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);   // kernel C (query path), called by the above

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
 // =================================================================================================
 // kernel B
 // =================================================================================================
-template <int D, int H>
+template <int D, int H, bool QPATH>
 __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   constexpr int HD = C::HD;
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(Enf
     }
     tc::mbar_wait(&bar_m[2], par);
     tc::tc_fence_after();
-    if (tid == 0) {                                    // B2 (dtpre) is free again: fetch the W1_q low image into it
+    if (QPATH && tid == 0) {                           // B2 (dtpre) is free again: fetch the W1_q low image into it
       tc::mbar_expect_tx(&bar_lo[1], C::WIMG);
       tc::bulk_g2s(sB2, P.img_q_w1_lo, C::WIMG, &bar_lo[1]);
     }
@@ -570,6 +570,19 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(Enf
     }
     tc::tc_fence_before();
     __syncthreads();                                   // everyone is done reading gamma_v from B0
+    if (!QPATH) {                                      // kernel C (enf_pairs_tc_bwd_q.cu) takes it from here
+      if (cq == 0 && valid) {
+        float4* dst = reinterpret_cast<float4*>(P.duv + pr * 8);
+        dst[0] = make_float4(s_du[row * 8], s_du[row * 8 + 1], s_du[row * 8 + 2], s_du[row * 8 + 3]);
+        dst[1] = make_float4(s_du[row * 8 + 4], s_du[row * 8 + 5], s_du[row * 8 + 6], s_du[row * 8 + 7]);
+      }
+      if (tid == 0 && ct + 1 < ntiles) {               // B1 (dzv) is free: every MMA reading it has completed
+        tc::mbar_expect_tx(&bar_lo[0], C::WIMG);
+        tc::bulk_g2s(sB1, P.img_v_w1_lo, C::WIMG, &bar_lo[0]);
+      }
+      __syncthreads();
+      continue;
+    }
     // ---------------- query path -----------------------------------------------------------------------------
     rff_to_tile_split<D>(rec, P.I, s_om, sB0, sB1, C::ABLK, row, col0);      // B1 (dzv) is free: all its MMAs completed
     tc::fence_proxy_async();
@@ -707,7 +720,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(Enf
     float* dst[3] = {P.g_Wp, P.g_v_w1, P.g_q_w1};
     const uint32_t src[3] = {tWp, tW1v, tW1q};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < (QPATH ? 3 : 2); ++k) {
       float v[32];
       tc::tmem_ld32(src[k] + my_t, v);
       tc::tmem_ld_wait();
@@ -717,14 +730,16 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_b_kernel(Enf
     }
   }
   for (int e = tid; e < D; e += C::NT) {
-    atomicAdd(P.g_q_b1 + e, s_db[e] * inv_gs);
+    if (QPATH) atomicAdd(P.g_q_b1 + e, s_db[e] * inv_gs);
     atomicAdd(P.g_v_b1 + e, s_db[D + e] * inv_gs);
     atomicAdd(P.g_bp + e, s_db[2 * D + e] * inv_gs);
   }
-  for (int e = tid; e < H * D; e += C::NT) P.g_U[bz * H * D + e] = s_dU[e] * inv_gs;
-  if (tid < H) P.g_kappa[bz * H + tid] = s_misc[tid] * inv_gs;
-  if (tid < ENF_LAM_SIZE) P.g_lam[bz * ENF_LAM_SIZE + tid] = s_dlam[tid] * inv_gs;
-  if (tid == 64 && P.win_kind != ENF_WIN_NONE) P.g_sigma[bz] = s_misc[4] * inv_gs;
+  if (QPATH) {
+    for (int e = tid; e < H * D; e += C::NT) P.g_U[bz * H * D + e] = s_dU[e] * inv_gs;
+    if (tid < H) P.g_kappa[bz * H + tid] = s_misc[tid] * inv_gs;
+    if (tid < ENF_LAM_SIZE) P.g_lam[bz * ENF_LAM_SIZE + tid] = s_dlam[tid] * inv_gs;
+    if (tid == 64 && P.win_kind != ENF_WIN_NONE) P.g_sigma[bz] = s_misc[4] * inv_gs;
+  }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tm);
@@ -741,11 +756,12 @@ int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
   size_t smem_b = 3 * C::WIMG + 3 * C::ATILE +
                   (ROWS * 8 + 64 + H * D + 3 * D + 12 * C::HD + 2 * C::NQ * ROWS * 2 + ROWS * 8 * 2 + ROWS + H * D + 3 * D + 64 + 8) * 4 + 128 + 1024;
   if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(pairs_bwd_tc_b_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(pairs_bwd_tc_b_kernel<D, H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)(p.B * p.Z);
   pairs_bwd_tc_a_kernel<D, H><<<grid, C::NT, smem_a, st>>>(p);
-  pairs_bwd_tc_b_kernel<D, H><<<grid, C::NT, smem_b, st>>>(p);
-  return 3;
+  pairs_bwd_tc_b_kernel<D, H, false><<<grid, C::NT, smem_b, st>>>(p);
+  if (enf_launch_pairs_bwd_tc_q(st, D, H, p) < 0) return -1;
+  return 4;
 }
 
 }  // namespace
