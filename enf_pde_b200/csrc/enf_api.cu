@@ -95,6 +95,8 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       Y.add("dthat", BC * (size_t)D.Z * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
       Y.add("duv", BC * (size_t)D.Z * 8);
+      // fp16 operand images of `that` per (field, latent, 128-query tile), stashed by the forward for backward kernel A
+      Y.add("that_img", BZ * (size_t)((D.C + 127) / 128) * 128 * d / 2);
     }
   }
   Y.add("xi", BC * ENF_F_XI);
@@ -353,6 +355,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
     tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3"); tp.cw3 = c.f("cw3");
     tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = c.f("slog");
+    tp.that_img = enf_pairs_bwd_tc_supported(D.d, D.H) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
     prof_mark(0, 0, st);
     nl = enf_launch_pairs_fwd_tc(st, d, H, tp);
     prof_mark(0, 1, st);
@@ -482,6 +485,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_q_w1_lo = (const uint8_t*)c.f("img_q_w1_lo"); tp.img_v_w1_lo = (const uint8_t*)c.f("img_v_w1_lo");
     tp.U = pp.U; tp.b3 = pp.b3; tp.slog = c.f("slog"); tp.lse = pp.lse; tp.nbar = pp.nbar;
     tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax");
+    tp.that_img = reinterpret_cast<const uint8_t*>(c.f("that_img"));
     tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");
     tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
     tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");

@@ -164,6 +164,8 @@ struct EnfPairTcParams {
   const float* cw3;                          // [B,Z,H,d] column sums of the bf16-rounded W3
   const float* U; const float* kappa; const float* b3;
   float* nbar; float* lse; float* slog;      // slog [B,C,Z,H]: logits incl. window (saved for the backward), may be null
+  uint8_t* that_img;                         // [B,Z,ceil(C/128)] operand images (128 rows x d, fp16, swizzled) of that = LN(gelu(.)),
+                                             // stashed for backward kernel A; may be null (forward only / SIMT backward)
 };
 bool enf_pairs_fwd_tc_supported(int d, int H);
 int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p);
@@ -180,6 +182,7 @@ struct EnfPairTcBwdParams {
   const uint8_t* img_q_w1_lo; const uint8_t* img_v_w1_lo;   // images of W - round16(W) (two-term split of the relu layers)
   const float* U; const float* b3;
   const float* slog; const float* lse; const float* nbar;   // forward state
+  const uint8_t* that_img;                   // [B,Z,ceil(C/128)] that operand images stashed by the forward
   const float* dnbar;                        // [B,C,H,d] cotangent of nbar
   float* Dg;                                 // [B,C,H]   dnbar . nbar                (written by the prep kernel)
   float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernel)

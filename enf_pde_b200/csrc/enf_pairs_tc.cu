@@ -11,8 +11,8 @@
 // with tcgen05.mma (kind::f16, fp16 operands, fp32 accumulators in TMEM) issued by one thread, weights
 // resident in shared memory as pre-swizzled images, the per-latent W3 images streamed by the bulk-copy
 // (TMA) engine, tcgen05.ld feeding the elementwise epilogues, and D/32 threads per query row so that
-// the softmax accumulators (H x d fp32 per row) stay in registers.  Nothing per-pair touches HBM except
-// the logits saved for the backward.  MMA and epilogues overlap where the chain allows it
+// the softmax accumulators (H x d fp32 per row) stay in registers.  Per pair, HBM only sees what is saved for
+// the backward: the logits and (optionally) the fp16 operand tile of `that`, bulk-stored straight from shared memory.  MMA and epilogues overlap where the chain allows it
 // (GEMM1 | E0v, GEMM2 | E1, GEMM3 | softmax update, GEMM4_1 | E4_0).
 #include "enf_pairs_tc_common.cuh"
 
@@ -269,6 +269,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
+      if (P.that_img) {                // stash the that operand tile for backward kernel A (bulk store, no thread work)
+        tc::bulk_s2g(P.that_img + ((size_t)bz * gridDim.x + blockIdx.x) * C::ATILE, sA1, C::ATILE);
+        tc::bulk_commit();
+      }
       tc::mbar_wait(&bar_w3[0], par);
       tc::tc_fence_after();
       issue_gemm<D>(t0, aA1, aS, C::ABLK, C::WBLK);
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[h][j] = fmaf(v[j], pr, fmaf(acc[h][j], corr[h], tz));
     }
+    if (tid == 0 && P.that_img) tc::bulk_wait_read0();      // the stash has been read out of A1 before the next latent overwrites it
     tc::tc_fence_before();
     __syncthreads();
   }

@@ -21,17 +21,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float gelu_fast(float x) {
   const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
   float t = tanh_fast(x * fmaf(c1, x * x, c0));
-  float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+  return x * fmaf(0.5f, t, 0.5f);               // same expression as gelu_fast_both: the backward's recompute matches bit for bit
 }
 __device__ __forceinline__ void gelu_fast_both(float x, float& g, float& dg) {
   const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
   float x2 = x * x;
   float t = tanh_fast(x * fmaf(c1, x2, c0));
-  float hx = 0.5f * x;
-  g = fmaf(hx, t, hx);
-  // d/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2)
-  dg = fmaf(hx * fmaf(-t, t, 1.f), fmaf(3.f * c1, x2, c0), fmaf(0.5f, t, 0.5f));
+  float s = fmaf(0.5f, t, 0.5f);                 // 0.5 (1 + t)
+  g = x * s;
+  // d/dx = s + x * 0.5 (1 - t^2) (c0 + 3 c1 x^2),  0.5 (1 - t^2) = s (2 - 2 s)  =>  s + g (2 - 2 s) (c0 + 3 c1 x^2)
+  dg = fmaf(g * fmaf(-2.f, s, 2.f), fmaf(3.f * c1, x2, c0), s);
 }
 
 struct Rec { float u[6]; float w; float c; };   // invariants, window value, raw cosine (spherical windows)

@@ -47,6 +47,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- bulk async copy shared -> global (bulk async-group completion) ------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk store of this thread has finished READING its shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- small async copies global -> shared (LDGSTS; no registers), BYTES = 4, 8 or 16 ---------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- TMEM ------------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {     // one full warp; writes base address to smem
