@@ -195,4 +195,5 @@ struct EnfPairTcBwdParams {
 };
 bool enf_pairs_bwd_tc_supported(int d, int H);
 int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);
+int enf_launch_pairs_bwd_tc_v(cudaStream_t st, int d, const EnfPairTcBwdParams& p);          // kernel B (value path, bottom), called by the above
 int enf_launch_pairs_bwd_tc_q(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);   // kernel C (query path), called by the above
