@@ -86,7 +86,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
-    Y.add("cw3", BZ * Hd); Y.add("slog", BC * (size_t)D.Z * H);
+    Y.add("slog", BC * (size_t)D.Z * H);
     // tf32 stage GEMMs: activated copies of the decode-MLP pre-activations (their A operands arrive by TMA) and the
     // low parts W - trunc_tf32(W) of the weights those GEMMs multiply by (3-term split product)
     Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
@@ -341,11 +341,10 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
     c.launches += enf_launch_transpose(st, w->v_w1, c.f("v_w1T"), d, d, 1);
     c.launches += enf_launch_transpose(st, c.f("Wp"), c.f("WpT"), d, d, 1);
-    c.launches += enf_launch_transpose(st, c.f("W3"), c.f("W3T"), d, d, (int)(BZ * H));
     c.launches += enf_launch_weight_image(st, c.f("q_w1T"), c.f("img_q_w1"), nullptr, d, d, 1);
     c.launches += enf_launch_weight_image(st, c.f("v_w1T"), c.f("img_v_w1"), nullptr, d, d, 1);
     c.launches += enf_launch_weight_image(st, c.f("WpT"), c.f("img_Wp"), nullptr, d, d, 1);
-    c.launches += enf_launch_weight_image(st, c.f("W3T"), c.f("img_W3"), c.f("cw3"), d, d, (int)(BZ * H));
+    c.launches += enf_launch_weight_image_T(st, c.f("W3"), c.f("img_W3"), d, d, (int)(BZ * H));
     EnfPairTcParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.B = D.B; tp.C = D.C; tp.Z = D.Z; tp.I = rl.I;
@@ -353,7 +352,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.xi = pp.xi; tp.xi_bs = pp.xi_bs; tp.lam = pp.lam; tp.sigma = pp.sigma;
     tp.q_omega = w->q_omega; tp.v_omega = w->v_omega; tp.q_b1 = w->q_b1; tp.v_b1 = w->v_b1; tp.bp = c.f("bp");
     tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
-    tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3"); tp.cw3 = c.f("cw3");
+    tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
     tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = c.f("slog");
     tp.that_img = enf_pairs_bwd_tc_supported(D.d, D.H) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
     prof_mark(0, 0, st);
@@ -462,7 +461,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->fb_w2, 1, Hd), enf_mat(c.f("s1"), Hd),
          with_lo(EnfGemmOpts(), LO("lo_fb_w2")));                                                               // de3
   c.launches += enf_launch_ln_bwd(st, c.f("s1"), c.f("e3c"), c.f("erstd"), w->fb_g, c.f("e1"), BC, Hd, c.f("s1"),
-                                  G("fb_g"), G("fb_beta"), 1);                                                    // de1 (in place)
+                                  G("fb_g"), G("fb_beta"), 1, 0, tc_fwd ? 1 : 0);                                 // de1 (in place)
   c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("nbar"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(c.f("gf_W_A"), Hd), opt_acc_big());
   colsum(c.f("s1"), BC, Hd, c.f("gf_b_A"));
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(c.f("W_A"), 1, Hd), enf_mat(c.f("s0"), Hd),

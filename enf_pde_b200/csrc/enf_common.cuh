@@ -111,7 +111,8 @@ int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t
 int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
                       float* out_core, float* out_affine, float* rstd, int gelu_in, int round_affine = 0);
 int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,
-                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx = 0);
+                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx = 0,
+                      int fast_gelu = 0);
 int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi);
 int enf_launch_latent_record(cudaStream_t st, const EnfDesc& d, const float* p, float* lam);
 int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float* p, const float* dlam, float* dp);
@@ -126,6 +127,8 @@ int enf_launch_mul_rows(cudaStream_t st, float* out, const float* A, const float
 int enf_launch_transpose(cudaStream_t st, const float* in, float* out, int rows, int cols, int batch);
 
 int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual = 0);
+// image of W^T built from the untransposed W [batch][K][N] (no fp32 transpose pass)
+int enf_launch_weight_image_T(cudaStream_t st, const float* W, void* img, int N, int K, int batch);
 
 // ---- fused pair kernels (enf_pairs_simt.cu) ------------------------------------------------------
 struct EnfPairParams {
@@ -161,7 +164,6 @@ struct EnfPairTcParams {
   const float* q_b1; const float* v_b1; const float* bp;
   const uint8_t* img_q_w1; const uint8_t* img_v_w1; const uint8_t* img_Wp;   // bf16 operand images of W^T ([n][k])
   const uint8_t* img_W3;                     // [B*Z*H] images of W3^T
-  const float* cw3;                          // [B,Z,H,d] column sums of the bf16-rounded W3
   const float* U; const float* kappa; const float* b3;
   float* nbar; float* lse; float* slog;      // slog [B,C,Z,H]: logits incl. window (saved for the backward), may be null
   uint8_t* that_img;                         // [B,Z,ceil(C/128)] operand images (128 rows x d, fp16, swizzled) of that = LN(gelu(.)),

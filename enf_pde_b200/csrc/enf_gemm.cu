@@ -1,7 +1,8 @@
 // Generic strided / batched / split-K fp32 GEMM used by the per-latent (L), per-weight (W) and
 // per-query tail (Q) stages.  These stages are a few percent of the work of the fused pair kernels;
 // this kernel favours generality (arbitrary strides => transposes and head-sliced views for free)
-// over peak throughput.  64x64x16 tiles, 256 threads, 4x4 register tile per thread.
+// over peak throughput.  64x64x16 tiles, 256 threads, 4x4 register tile per thread, 4-stage cp.async pipeline
+// (most calls are tiny fold / unfold products whose time is global-load latency, not flops).
 #include <cstdlib>
 
 #include "enf_common.cuh"
@@ -23,9 +24,17 @@ struct GemmKArgs {
   float alpha;
 };
 
+constexpr int ST = 4;      // cp.async pipeline depth: the small fold / unfold products are latency bound, not flop bound
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ __align__(16) float As[ST][BK][BM + 4];
+  __shared__ __align__(16) float Bs[ST][BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -38,41 +47,58 @@ __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
   const bool a_kfast = (g.sak == 1);     // consecutive threads walk k (row-major A) else walk m
   const bool b_nfast = (g.sbn == 1);
 
+  // element e = tid + 256 i of a BK x BM (BK x BN) tile: the (k, m) / (k, n) slot this thread fills
+  int a_kk[4], a_mm[4], b_kk[4], b_nn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 256;
+    if (a_kfast) { a_kk[i] = e & (BK - 1); a_mm[i] = e >> 4; } else { a_mm[i] = e & (BM - 1); a_kk[i] = e >> 6; }
+    if (b_nfast) { b_nn[i] = e & (BN - 1); b_kk[i] = e >> 6; } else { b_kk[i] = e & (BK - 1); b_nn[i] = e >> 4; }
+  }
+  auto load_tile = [&](int stage, int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + a_mm[i], gk = k0 + a_kk[i];
+      float* dst = &As[stage][a_kk[i]][a_mm[i]];
+      if (gm < g.M && gk < kend) cp_async4(dst, A + (int64_t)gm * g.sam + (int64_t)gk * g.sak); else *dst = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gn = n0 + b_nn[i], gk = k0 + b_kk[i];
+      float* dst = &Bs[stage][b_kk[i]][b_nn[i]];
+      if (gn < g.N && gk < kend) cp_async4(dst, B + (int64_t)gk * g.sbk + (int64_t)gn * g.sbn); else *dst = 0.f;
+    }
+  };
+
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+  const int nk = (kend - kbeg + BK - 1) / BK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + i * 256;
-      int kk, mm;
-      if (a_kfast) { kk = e & (BK - 1); mm = e >> 4; } else { mm = e & (BM - 1); kk = e >> 6; }
-      int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < g.M && gk < kend) {
-        v = __ldg(A + (int64_t)gm * g.sam + (int64_t)gk * g.sak);
-        if (g.act_a) v = enf_gelu(v);
+  for (int s = 0; s < ST - 1; ++s) {
+    if (s < nk) load_tile(s, kbeg + s * BK);
+    cp_async_commit();
+  }
+  for (int t = 0; t < nk; ++t) {
+    const int stage = t % ST;
+    cp_async_wait<ST - 2>();                  // this thread's copies of tile t have landed
+    if (g.act_a) {                            // gelu on load, applied by the thread that fetched the element
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float* p = &As[stage][a_kk[i]][a_mm[i]];
+        *p = enf_gelu(*p);
       }
-      As[kk][mm] = v;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + i * 256;
-      int kk, nn;
-      if (b_nfast) { nn = e & (BN - 1); kk = e >> 6; } else { kk = e & (BK - 1); nn = e >> 4; }
-      int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < g.N && gk < kend) v = __ldg(B + (int64_t)gk * g.sbk + (int64_t)gn * g.sbn);
-      Bs[kk][nn] = v;
-    }
-    __syncthreads();
+    __syncthreads();                          // tile t visible to all; everyone is done computing on tile t - 1
+    if (t + ST - 1 < nk) load_tile((t + ST - 1) % ST, kbeg + (t + ST - 1) * BK);
+    cp_async_commit();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float4 a = *reinterpret_cast<const float4*>(&As[stage][kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[stage][kk][tx * 4]);
       float av[4] = {a.x, a.y, a.z, a.w};
       float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -80,7 +106,6 @@ __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
   }
 
   const float* bias = g.bias ? g.bias + (int64_t)bz * g.bias_bs : nullptr;

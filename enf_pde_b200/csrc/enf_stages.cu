@@ -247,6 +247,81 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ i
 }
 
 // dy = cotangent of (core*g + b).  dx = cotangent of the (pre-gelu) input.  dg/db accumulated atomically.
+// One warp per row, one pass: a lane keeps its (<= 16) elements of dy / core in registers between the row
+// reduction and the write-back (float4 accesses when N % 128 == 0).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float x2 = x * x, t;
+  float u = x * fmaf(c1, x2, c0);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  float s = fmaf(0.5f, t, 0.5f);
+  return fmaf(x * s * fmaf(-2.f, s, 2.f), fmaf(3.f * c1, x2, c0), s);
+}
+template <int NV4>     // N == 128 * NV4
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* dy, const float* __restrict__ core,
+                                                         const float* __restrict__ rstd, const float* __restrict__ g,
+                                                         const float* __restrict__ pre, int64_t M,
+                                                         float* dx, float* __restrict__ dg,
+                                                         float* __restrict__ db, int gelu_in, int rnd, int fast_gelu) {
+  constexpr int N = 128 * NV4;
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 gv[NV4], pg[NV4], pb[NV4];
+#pragma unroll
+  for (int t = 0; t < NV4; ++t) {
+    gv[t] = *reinterpret_cast<const float4*>(g + 128 * t + 4 * lane);
+    pg[t] = make_float4(0.f, 0.f, 0.f, 0.f); pb[t] = pg[t];
+  }
+  for (int64_t r = warp; r < M; r += nwarps) {
+    float4 d[NV4], c[NV4], p[NV4];
+#pragma unroll
+    for (int t = 0; t < NV4; ++t) {
+      d[t] = *reinterpret_cast<const float4*>(dy + r * N + 128 * t + 4 * lane);
+      c[t] = __ldg(reinterpret_cast<const float4*>(core + r * N + 128 * t + 4 * lane));
+      if (gelu_in) p[t] = __ldg(reinterpret_cast<const float4*>(pre + r * N + 128 * t + 4 * lane));
+    }
+    const float rs = rstd[r];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < NV4; ++t) {
+      float a0 = d[t].x * gv[t].x, a1 = d[t].y * gv[t].y, a2 = d[t].z * gv[t].z, a3 = d[t].w * gv[t].w;
+      m1 += (a0 + a1) + (a2 + a3);
+      m2 += (a0 * c[t].x + a1 * c[t].y) + (a2 * c[t].z + a3 * c[t].w);
+    }
+    m1 = warp_sum(m1) * (1.f / N); m2 = warp_sum(m2) * (1.f / N);
+#pragma unroll
+    for (int t = 0; t < NV4; ++t) {
+      float dv[4] = {d[t].x, d[t].y, d[t].z, d[t].w}, cv[4] = {c[t].x, c[t].y, c[t].z, c[t].w};
+      float gg[4] = {gv[t].x, gv[t].y, gv[t].z, gv[t].w}, pv[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+      if (gelu_in) { pv[0] = p[t].x; pv[1] = p[t].y; pv[2] = p[t].z; pv[3] = p[t].w; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = rs * (dv[q] * gg[q] - m1 - cv[q] * m2);
+        if (gelu_in) v *= fast_gelu ? gelu_grad_fast(pv[q]) : enf_gelu_grad(pv[q]);
+        o[q] = enf_maybe_round(v, rnd);
+      }
+      *reinterpret_cast<float4*>(dx + r * N + 128 * t + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
+      pg[t].x += dv[0] * cv[0]; pg[t].y += dv[1] * cv[1]; pg[t].z += dv[2] * cv[2]; pg[t].w += dv[3] * cv[3];
+      pb[t].x += dv[0]; pb[t].y += dv[1]; pb[t].z += dv[2]; pb[t].w += dv[3];
+    }
+  }
+  if (dg) {
+    // block-level reduction in shared memory first: 8 warps -> one atomic per column per block
+    __shared__ float sg[N], sb[N];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) { sg[j] = 0.f; sb[j] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NV4; ++t) {
+      const int j = 128 * t + 4 * lane;
+      atomicAdd(&sg[j], pg[t].x); atomicAdd(&sg[j + 1], pg[t].y); atomicAdd(&sg[j + 2], pg[t].z); atomicAdd(&sg[j + 3], pg[t].w);
+      atomicAdd(&sb[j], pb[t].x); atomicAdd(&sb[j + 1], pb[t].y); atomicAdd(&sb[j + 2], pb[t].z); atomicAdd(&sb[j + 3], pb[t].w);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) { atomicAdd(dg + j, sg[j]); atomicAdd(db + j, sb[j]); }
+  }
+}
+
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* dy, const float* __restrict__ core,
                                                      const float* __restrict__ rstd, const float* __restrict__ g,
                                                      const float* __restrict__ pre, int64_t M, int N,
@@ -446,9 +521,14 @@ int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const 
 }
 
 int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,
-                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx) {
-  int blocks = (int)((M + 7) / 8); if (blocks > 148 * 4) blocks = 148 * 4;
-  ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, N, dx, dg, db, gelu_in, round_dx);
+                      const float* pre, int64_t M, int N, float* dx, float* dg, float* db, int gelu_in, int round_dx, int fast_gelu) {
+  int blocks = (int)((M + 7) / 8); if (blocks > 148 * 8) blocks = 148 * 8;
+  // fast_gelu: tanh.approx in gelu' (tensor-core precision mode only: the result feeds tf32 operands anyway)
+  if (N == 128) ln_bwd_vec_kernel<1><<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, dx, dg, db, gelu_in, round_dx, fast_gelu);
+  else if (N == 256) ln_bwd_vec_kernel<2><<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, dx, dg, db, gelu_in, round_dx, fast_gelu);
+  else if (N == 384) ln_bwd_vec_kernel<3><<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, dx, dg, db, gelu_in, round_dx, fast_gelu);
+  else if (N == 512) ln_bwd_vec_kernel<4><<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, dx, dg, db, gelu_in, round_dx, fast_gelu);
+  else ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, core, rstd, g, pre, M, N, dx, dg, db, gelu_in, round_dx);
   return 1;
 }
 

@@ -37,6 +37,28 @@ __global__ void __launch_bounds__(256) weight_image_kernel(const float* __restri
   }
 }
 
+// Same image, built straight from the UNtransposed weight W [batch][K][N] (n contiguous, Flax layout): a thread owns
+// column n and 8 consecutive k, so a warp's loads are 8 coalesced 128-byte rows; the image is assembled in shared
+// memory and written out linearly.  Saves the fp32 transpose round trip of the per-latent W3 (268 MB each way at ns64).
+__global__ void __launch_bounds__(256) weight_image_T_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int N, int K) {
+  extern __shared__ uint4 s_img[];
+  const int64_t b = blockIdx.x;
+  const float* src = W + b * (int64_t)N * K;
+  const int cpr = K / 8;
+  for (int e = threadIdx.x; e < N * cpr; e += blockDim.x) {
+    const int n = e % N, k0 = (e / N) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (int64_t)(k0 + i) * N + n);
+    uint4 q;
+    q.x = tc::pack_bf16(v[0], v[1]); q.y = tc::pack_bf16(v[2], v[3]); q.z = tc::pack_bf16(v[4], v[5]); q.w = tc::pack_bf16(v[6], v[7]);
+    s_img[((size_t)(k0 >> 6) * N * 128 + tc::swz_chunk_off(n, (k0 & 63) >> 3)) >> 4] = q;
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(img + b * (int64_t)N * K * 2);
+  for (int e = threadIdx.x; e < N * K / 8; e += blockDim.x) dst[e] = s_img[e];
+}
+
 // ---- single-tile test GEMM: 128 rows, D features (D = 64 or 128) ---------------------------------------
 // mode 0: Dout[r][n] = sum_k X[r][k] * Wt[n][k]          (A K-major from registers, B K-major from the image)
 // mode 1: Dout[r][k] = sum_n X[r][n] * Wt[n][k]          (B read MN-major from the SAME image: dgrad)
@@ -119,6 +141,13 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(int mode, const float
 
 int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual) {
   weight_image_kernel<<<batch, 256, 0, st>>>(Wt, (uint8_t*)img, cw, N, K, residual);
+  return 1;
+}
+
+int enf_launch_weight_image_T(cudaStream_t st, const float* W, void* img, int N, int K, int batch) {
+  const size_t smem = (size_t)N * K * 2;
+  if (smem > 48 * 1024) return -1;
+  weight_image_T_kernel<<<batch, 256, smem, st>>>(W, (uint8_t*)img, N, K);
   return 1;
 }
 
