@@ -325,13 +325,23 @@ def main():
     bwd_avg = sum(bwd_ms) / len(bwd_ms) if bwd_ms else float("nan")
     fwd_avg = sum(fwd_ms) / len(fwd_ms) if fwd_ms else float("nan")
     achieved = 2.0 * f_alg * pairs / (bwd_avg * 1e-3) / 1e12 if bwd_ms else None
-    roofline = {"bound": "tensor", "kernel": "pairs_bwd_kernel (fused pair backward)", "achieved": achieved,
+    tcmode = args.precision == "bf16"
+    kname = ("fused pair backward = pairs_bwd_tc_a_kernel + pairs_bwd_tc_v_kernel + pairs_bwd_tc_q_kernel (tcgen05, 3 launches timed as one)"
+             if tcmode else "pairs_bwd_kernel (fused pair backward, fp32 FMA)")
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu --set full captures
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{args.config}:{args.precision}", {}).get("bwd_dram_bytes")
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved,
                 "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-                "traffic": None, "peak_source": peaks["source"] + ", dense bf16 sustained",
+                "traffic": traffic, "peak_source": peaks["source"] + ", dense bf16 sustained",
                 "algorithmic_flop_per_launch": 2.0 * f_alg * pairs, "kernel_ms_avg": bwd_avg, "kernel_share_of_step": bwd_avg * args.steps / ms if bwd_ms else None,
                 "fwd_kernel_ms_avg": fwd_avg, "fwd_achieved": (f_alg * pairs / (fwd_avg * 1e-3) / 1e12) if fwd_ms else None,
-                "note": "arithmetic on this path is fp32 FMA (precision mode fp32); FLOP count is SURVEY 8d's contract figure "
-                        "F_pair_alg per (query, latent) pair, x2 for the backward (dgrad + wgrad, recompute not counted)"}
+                "whole_step_achieved": 3.0 * (f_alg * pairs + flops_per_query_tail(cfg) * B * C) / (ms / args.steps * 1e-3) / 1e12,
+                "note": ("tcgen05 kind::f16 MMAs (fp16 operands, fp32 accumulate in TMEM)" if tcmode else "arithmetic on this path is fp32 FMA (precision mode fp32)")
+                        + "; FLOP count is SURVEY 8d's contract figure F_pair_alg per (query, latent) pair, x2 for the backward "
+                          "(dgrad + wgrad; recompute and the 3-term split products of the relu layers are not counted)"}
     total_flop_step = 3.0 * (f_alg * pairs + flops_per_query_tail(cfg) * B * C)
 
     cpu = None

@@ -8,6 +8,7 @@
 // and the reverse of each for enf_xattn_bwd.  The algebra is tests/folded_model.py (validated on CPU
 // against the unfused oracle); DESIGN.md lists every buffer.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -93,8 +94,11 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     Y.add("lo_W_A", Hd * Hd); Y.add("lo_fb_w2", Hd * Hd); Y.add("lo_m0_w", Hd * d); Y.add("lo_m1_w", d2); Y.add("lo_mx_w1", d2);
     if (enf_pairs_bwd_tc_supported(D.d, D.H)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
-      Y.add("dthat", BC * (size_t)D.Z * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
+      const size_t Cpad = (size_t)((D.C + 127) / 128) * 128;      // kernels A / B work on whole 128-query tiles
+      Y.add("dthat", BZ * Cpad * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
+      Y.add("dnb16", (size_t)D.B * Cpad * Hd / 2);
       Y.add("duv", BC * (size_t)D.Z * 8);
+      Y.add("dbg", 8192);
       // fp16 operand images of `that` per (field, latent, 128-query tile), stashed by the forward for backward kernel A
       Y.add("that_img", BZ * (size_t)((D.C + 127) / 128) * 128 * d / 2);
     }
@@ -483,8 +487,10 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.launches += enf_launch_weight_image(st, c.f("v_w1T"), c.f("img_v_w1_lo"), nullptr, d, d, 1, 1);
     tp.img_q_w1_lo = (const uint8_t*)c.f("img_q_w1_lo"); tp.img_v_w1_lo = (const uint8_t*)c.f("img_v_w1_lo");
     tp.U = pp.U; tp.b3 = pp.b3; tp.slog = c.f("slog"); tp.lse = pp.lse; tp.nbar = pp.nbar;
-    tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax");
+    tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax"); tp.dnb16 = reinterpret_cast<uint4*>(c.f("dnb16"));
     tp.that_img = reinterpret_cast<const uint8_t*>(c.f("that_img"));
+    static const bool trace = getenv("ENF_DEBUG_TRACE") != nullptr;
+    tp.dbg = trace ? reinterpret_cast<long long*>(c.f("dbg")) : nullptr;
     tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");
     tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
     tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");

@@ -147,7 +147,7 @@ struct EnfPairParams {
   // backward only
   const float* q_w1T; const float* v_w1T; const float* WpT; const float* W3T;   // transposed copies
   const float* dnbar;                        // [B,C,H,d]
-  const float* slog;                         // [B,C,Z,H] logits saved by the tensor-core forward (or null: recompute)
+  const float* slog;                         // [B,Z,C,H] logits saved by the tensor-core forward (or null: recompute)
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // accumulated (atomics)
   float* g_W3; float* g_b3; float* g_U; float* g_kappa; float* g_lam; float* g_sigma;      // per-latent, accumulated
 };
@@ -165,7 +165,7 @@ struct EnfPairTcParams {
   const uint8_t* img_q_w1; const uint8_t* img_v_w1; const uint8_t* img_Wp;   // bf16 operand images of W^T ([n][k])
   const uint8_t* img_W3;                     // [B*Z*H] images of W3^T
   const float* U; const float* kappa; const float* b3;
-  float* nbar; float* lse; float* slog;      // slog [B,C,Z,H]: logits incl. window (saved for the backward), may be null
+  float* nbar; float* lse; float* slog;      // slog [B,Z,C,H]: logits incl. window (saved for the backward), may be null
   uint8_t* that_img;                         // [B,Z,ceil(C/128)] operand images (128 rows x d, fp16, swizzled) of that = LN(gelu(.)),
                                              // stashed for backward kernel A; may be null (forward only / SIMT backward)
 };
@@ -186,14 +186,18 @@ struct EnfPairTcBwdParams {
   const float* slog; const float* lse; const float* nbar;   // forward state
   const uint8_t* that_img;                   // [B,Z,ceil(C/128)] that operand images stashed by the forward
   const float* dnbar;                        // [B,C,H,d] cotangent of nbar
-  float* Dg;                                 // [B,C,H]   dnbar . nbar                (written by the prep kernel)
-  float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernel)
-  __half* dthat;                             // [B,Z,C,d] scaled cotangent of that    (A -> B)
+  float* Dg;                                 // [B,C,H]   dnbar16 . nbar              (written by the prep kernels)
+  float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernels)
+  uint4* dnb16;                              // scaled fp16 copy of dnbar in kernel A's load order:
+                                             //   [B][C/128][H][4 column quarters][4 chunks][128 rows] x 8 halves (prep kernels)
+  __half* dthat;                             // scaled cotangent of that (A -> B), same chunked order:
+                                             //   [B,Z][C/128][4 column quarters][4 chunks][128 rows] x 8 halves
   float* ds;                                 // [B,Z,C,H] scaled cotangent of logits  (A -> C)
   float* duv;                                // [B,Z,C,8] scaled cotangent of the invariants through the value path (B -> C)
   float* g_W3; float* g_b3;                  // per-latent outputs of A
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // shared-weight grads (atomics)
   float* g_U; float* g_kappa; float* g_lam; float* g_sigma;                                // per-latent outputs of B
+  long long* dbg;                            // optional clock64() trace of one CTA (diagnostics; null in production)
 };
 bool enf_pairs_bwd_tc_supported(int d, int H);
 int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);

@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
         float rstd = ln_gelu_row<D>(mrow, nrow, lane);                 // n
         const bool valid = r < nv;
         float sv = S.s[h * TM + r];
-        if (P.slog && valid) sv = P.slog[(((int64_t)b * P.C + c0 + r) * P.Z + z) * H + h];   // the forward's own logits
+        if (P.slog && valid) sv = P.slog[(((int64_t)b * P.Z + z) * P.C + c0 + r) * H + h];   // the forward's own logits
         float att = valid ? __expf(sv - S.m[h * TM + r]) : 0.f;
         const float* dnb = P.dnbar + (((int64_t)b * P.C + c0 + (valid ? r : 0)) * H + h) * D;
         float dotn = 0.f, m1 = 0.f;

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
 #pragma unroll
       for (int q = 0; q < C::NQ; ++q) dot += s_spart[(q * ROWS + row) * H + h];
       float sv = scale * (dot + s_kap[h]) + win;
-      if (cq == 0 && row_valid && P.slog) P.slog[(((int64_t)b * P.C + c0 + row) * P.Z + z) * H + h] = sv;
+      if (cq == 0 && row_valid && P.slog) P.slog[((bz * P.C) + c0 + row) * H + h] = sv;
       float m_new = fmaxf(m_run[h], sv);
       corr[h] = __expf(m_run[h] - m_new);
       pw[h] = __expf(sv - m_new);

@@ -40,36 +40,61 @@ __device__ __forceinline__ void load_scale(const float* gmax, float& gs, float& 
   inv_gs = 1.f / gs;
 }
 
-__device__ __forceinline__ void st_half32(__half* dst, const float* v) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
-    d4[q] = u;
-  }
-}
-// Dg[b,c,h] = dnbar . nbar ; gmax = max |dnbar|
-__global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ dnbar, const float* __restrict__ nbar,
-                                                       int64_t rows, int D, float* __restrict__ Dg, float* gmax) {
-  const int lane = threadIdx.x & 31;
-  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+// Prep, pass 1: gmax = max |dnbar|
+__global__ void __launch_bounds__(256) bwd_prep_max_kernel(const float4* __restrict__ dnbar, int64_t n4, float* gmax) {
   float mx = 0.f;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    float s = 0.f;
-    for (int j = lane; j < D; j += 32) {
-      float a = dnbar[r * D + j];
-      s = fmaf(a, nbar[r * D + j], s);
-      mx = fmaxf(mx, fabsf(a));
-    }
-    s = warp_sum(s);
-    if (lane == 0) Dg[r] = s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(dnbar + i);
+    mx = fmaxf(fmaxf(fmaxf(mx, fabsf(a.x)), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
   }
   mx = warp_max(mx);
-  if (lane == 0) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));     // non-negative floats order as ints
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));     // non-negative floats order as ints
+}
+// Prep, pass 2: dnb16 = fp16(gs * dnbar) in the order kernel A loads it (a warp's 16-byte loads are contiguous), and
+// Dg[b,c,h] = dnb16 . nbar / gs -- from the ROUNDED cotangent, so that sum_z ds_z = 0 holds exactly as in the forward.
+// One thread per (b, c, h, column quarter); rows beyond C are written as zeros.
+template <int D>
+__global__ void __launch_bounds__(256) bwd_prep_pack_kernel(const float* __restrict__ dnbar, const float* __restrict__ nbar, int B,
+                                                            int C, int H, const float* __restrict__ gmax, uint4* __restrict__ dnb16,
+                                                            float* __restrict__ Dg) {
+  constexpr int NQ = D / 32;
+  const int ntiles = (C + 127) / 128;
+  float gs, inv_gs;
+  load_scale(gmax, gs, inv_gs);
+  const int64_t total = (int64_t)B * ntiles * H * NQ * 128;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t % 128);
+    int64_t r = t / 128;
+    const int cq = (int)(r % NQ); r /= NQ;
+    const int h = (int)(r % H); r /= H;
+    const int ct = (int)(r % ntiles);
+    const int b = (int)(r / ntiles);
+    const int c = ct * 128 + row;
+    uint4* dst = dnb16 + ((((int64_t)b * ntiles + ct) * H + h) * NQ + cq) * 4 * 128 + row;       // + q * 128
+    float part = 0.f;
+    if (c < C) {
+      const float4* s4 = reinterpret_cast<const float4*>(dnbar + (((int64_t)b * C + c) * H + h) * D + cq * 32);
+      const float4* n4 = reinterpret_cast<const float4*>(nbar + (((int64_t)b * C + c) * H + h) * D + cq * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a0 = __ldg(s4 + 2 * q), a1 = __ldg(s4 + 2 * q + 1), m0 = __ldg(n4 + 2 * q), m1 = __ldg(n4 + 2 * q + 1);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        uint4 u;
+        __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h2[k] = __floats2half2_rn(av[2 * k] * gs, av[2 * k + 1] * gs);
+          const float2 back = __half22float2(h2[k]);
+          part = fmaf(back.x, mv[2 * k], part); part = fmaf(back.y, mv[2 * k + 1], part);
+        }
+        dst[q * 128] = u;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q * 128] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (c < C) atomicAdd(Dg + ((int64_t)b * C + c) * H + h, part * inv_gs);
+  }
 }
 
 // =================================================================================================
@@ -89,15 +114,27 @@ template <int D, int H> struct ACfg {
   static constexpr uint32_t OFF_T = H * B::WIMG;                     // [2] that tiles
   static constexpr uint32_t OFF_DM = OFF_T + 2 * B::ATILE;           // [H] dm tiles
   static constexpr uint32_t OFF_F = OFF_DM + H * B::ATILE;
-  static constexpr int F_TOTAL = H * D /*b3*/ + 2 * B::NQ * ROWS * 2 /*exchange*/ + H * D /*db3*/ + 2 * 3 * ROWS * H /*row scalars*/;
+  static constexpr int F_TOTAL = H * D /*b3*/ + 2 * B::NQ * ROWS * 4 /*exchange*/ + H * D /*db3*/ + 2 * 3 * ROWS * H /*row scalars*/;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// Warp roles: warps 0..15 are the epilogue warps (thread layout of enf_pairs_tc_common.cuh); warp 16 only issues --
+// bulk copies, tcgen05.mma, commits.  Epilogue warps never block on each other: when their part of an operand tile is
+// written they ARRIVE on a named barrier the issue warp SYNCs on, and go on with whatever does not need that MMA.
+constexpr int kABarHead = 5;      // + h: dm_h tile written                      (named barriers 1..4 belong to row_exchange)
+constexpr int kABarDth = 7;       // dthat of the tile has been read out of TMEM
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// diagnostics: clock64() of selected events of CTA 7, tiles 4..7, for thread `who` (ENF_DEBUG_TRACE=1)
+#define A_STAMP(who, slot) do { if (P.dbg && blockIdx.x == 7 && tid == (who) && ct >= 4 && ct < 8) P.dbg[((who) == 512 ? 512 : 0) + (ct - 4) * 32 + (slot)] = clock64(); } while (0)
+
 template <int D, int H>
-__global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   using A = ACfg<D, H>;
+  constexpr int NTA = C::NT + 32;                     // epilogue threads + the issue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW3 = base + A::OFF_W3;
@@ -105,7 +142,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   uint8_t* sDm = base + A::OFF_DM;
   float* f = reinterpret_cast<float*>(base + A::OFF_F);
   float* s_b3 = f; f += H * D;
-  float* s_exch = f; f += 2 * C::NQ * ROWS * 2;
+  float* s_exch = f; f += 2 * C::NQ * ROWS * 4;
   float* s_db3 = f; f += H * D;
   float* s_rs = f; f += 2 * 3 * ROWS * H;             // [2 tiles][logit | lse | Dg][ROWS][H], filled one tile ahead by cp.async
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
@@ -113,6 +150,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool issuer = warp == 16;
   const int lq = warp & 3, cq = warp >> 2;
   const int row = lq * 32 + lane, col0 = cq * 32;
   const int64_t bz = blockIdx.x;
@@ -125,7 +163,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
     tc::mbar_fence_init();
   }
   if (warp == 0) tc::tmem_alloc<512>(s_tmem);
-  for (int e = tid; e < H * D; e += C::NT) { s_b3[e] = P.b3[bz * H * D + e]; s_db3[e] = 0.f; }
+  for (int e = tid; e < H * D; e += NTA) { s_b3[e] = P.b3[bz * H * D + e]; s_db3[e] = 0.f; }
   float gs, inv_gs;
   load_scale(P.gmax, gs, inv_gs);
   tc::tc_fence_before();
@@ -136,165 +174,219 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
   const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
   const uint32_t my_t = lane_off + col0;
   const uint32_t aW3 = tc::smem_u32(sW3), aT = tc::smem_u32(sT), aDm = tc::smem_u32(sDm);
-  if (tid == 0) {
-    tc::mbar_expect_tx(bar_w, H * C::WIMG);
-    for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);
-    tc::mbar_expect_tx(&bar_t[0], C::ATILE);
-    tc::bulk_g2s(sT, timg, C::ATILE, &bar_t[0]);
-  }
-  int xw = 0;
-  // per-row scalars of tile `ct` (logits, log-sum-exp, Dg of my row, all heads) -> shared, without passing through registers
-  auto prefetch_rows = [&](int ct) {
-    const int c = ct * ROWS + row;
-    if (cq == 0 && c < P.C) {
-      const int64_t q = (int64_t)b * P.C + c;
-      float* dst = s_rs + (ct & 1) * 3 * ROWS * H + row * H;
-      tc::cp_async<4 * H>(dst, P.slog + (q * P.Z + z) * H);
-      tc::cp_async<4 * H>(dst + ROWS * H, P.lse + q * H);
-      tc::cp_async<4 * H>(dst + 2 * ROWS * H, P.Dg + q * H);
-    }
-  };
-  prefetch_rows(0);
-  tc::cp_async_wait_all();
-  __syncthreads();
 
-  for (int ct = 0; ct < ntiles; ++ct) {
-    const uint32_t par = ct & 1;
-    const int e = ct & 1;                              // that buffer of this tile; region roles: first = tR[e], other = tR[e ^ 1]
-    const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
-    const uint32_t aTc = aT + e * C::ATILE;
-    const int c0 = ct * ROWS;
-    const bool valid = c0 + row < P.C;
-    const int64_t bc = (int64_t)b * P.C + c0 + row;
-    if (ct + 1 < ntiles) prefetch_rows(ct + 1);
-    if (ct > 0) {                                      // every MMA of the previous tile is done with that[e ^ 1] and the dm tiles
-      tc::mbar_wait(bar_gb, par ^ 1);
+  if (issuer) {
+    // ================================ issue warp =================================================================
+    const bool lead = lane == 0;
+    if (lead) {
+      tc::mbar_expect_tx(bar_w, H * C::WIMG);
+      for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);
+      tc::mbar_expect_tx(&bar_t[0], C::ATILE);
+      tc::bulk_g2s(sT, timg, C::ATILE, &bar_t[0]);
+      tc::mbar_wait(bar_w, 0);
+      tc::mbar_wait(&bar_t[0], 0);
       tc::tc_fence_after();
+      issue_gemm<D>(tm, aT, aW3, C::ABLK, C::WBLK);               // m_0 of tile 0 -> region 0
+      tc::mma_commit(&bar_g4[0]);
     }
-    if (tid == 0) {
-      if (ct + 1 < ntiles) {
-        tc::mbar_expect_tx(&bar_t[e ^ 1], C::ATILE);
-        tc::bulk_g2s(sT + (e ^ 1) * C::ATILE, timg + (size_t)(ct + 1) * C::ATILE, C::ATILE, &bar_t[e ^ 1]);
-      }
-      if (ct == 0) {
-        tc::mbar_wait(bar_w, 0);
-        tc::mbar_wait(&bar_t[0], 0);
+    for (int ct = 0; ct < ntiles; ++ct) {
+      const int e = ct & 1;
+      const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
+      const uint32_t aTc = aT + e * C::ATILE;
+      A_STAMP(512, 0);
+      if (ct > 0) named_sync(kABarDth, NTA);          // tS (= the previous tile's dgrad region) has been read by every epilogue thread
+      A_STAMP(512, 1);
+      if (lead) {
         tc::tc_fence_after();
-        issue_gemm<D>(tF, aTc, aW3, C::ABLK, C::WBLK);
-        tc::mma_commit(&bar_g4[0]);
-      }
-      if (H > 1) {
-        issue_gemm<D>(tS, aTc, aW3 + C::WIMG, C::ABLK, C::WBLK);
-        tc::mma_commit(&bar_g4[1]);
-      }
-    }
-    float v[32];
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float att = 0.f, Dh = 0.f;
-      if (valid) {
-        const float* rs = s_rs + e * 3 * ROWS * H + row * H + h;
-        att = __expf(rs[0] - rs[ROWS * H]);
-        Dh = rs[2 * ROWS * H];
-      }
-      const float atts = att * gs;                     // cotangents are carried scaled by gs
-      float dnb[32];
-      {
-        const float4* src = reinterpret_cast<const float4*>(P.dnbar + (bc * H + h) * D + col0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 a = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          dnb[4 * q] = a.x; dnb[4 * q + 1] = a.y; dnb[4 * q + 2] = a.z; dnb[4 * q + 3] = a.w;
+        if (H > 1) {
+          issue_gemm<D>(tS, aTc, aW3 + C::WIMG, C::ABLK, C::WBLK);
+          tc::mma_commit(&bar_g4[1]);
+        }
+        if (ct + 1 < ntiles) {                        // next that tile -> the other buffer, once the previous tile's wgrad has read it
+          if (ct > 0) tc::mbar_wait(bar_gb, (ct - 1) & 1);
+          tc::mbar_expect_tx(&bar_t[e ^ 1], C::ATILE);
+          tc::bulk_g2s(sT + (e ^ 1) * C::ATILE, timg + (size_t)(ct + 1) * C::ATILE, C::ATILE, &bar_t[e ^ 1]);
         }
       }
-      tc::mbar_wait(&bar_g4[h], par);
-      tc::tc_fence_after();
-      tc::tmem_ld32((h == 0 ? tF : tS) + my_t, v);
-      tc::tmem_ld_wait();
-      float dg[32];
-      float st[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float g;
-          gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
-          v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
-        }
-      }
-      row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
-      const float mu = st[0] * (1.f / D);
-      const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
-      const float nm = -mu * rstd;
-      float dd[2] = {0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaf(v[j], rstd, nm);               // n
-        dd[0] = fmaf(dnb[j], v[j], dd[0]);
-        dd[1] += dnb[j];
-      }
-      row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, dd);
-      const float dsh = atts * (dd[0] - Dh);
-      const float mean1 = atts * dd[1] * (1.f / D), mean2 = atts * dd[0] * (1.f / D);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dnb[j] = (fmaf(atts, dnb[j], -mean1) - v[j] * mean2) * (rstd * dg[j]);     // dm
-      uint8_t* sDh = sDm + h * C::ATILE;
-#pragma unroll
-      for (int c8 = 0; c8 < 32; c8 += 8) tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dnb + c8);
-      {
-        float cs = warp_colsum32(dnb, lane);
-        atomicAdd(&s_db3[h * D + col0 + lane], cs);
-      }
-      if (cq == 0 && valid) P.ds[((bz * P.C) + c0 + row) * H + h] = dsh;
-      tc::tc_fence_before();
-      tc::fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        const uint32_t aDh = aDm + h * C::ATILE, aWh = aW3 + h * C::WIMG;
-        if (h + 1 < H) {
-          issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
-          issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
-        } else {
-          issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
-          tc::mma_commit(bar_d);
-          issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
-          tc::mma_commit(bar_gb);
-          if (ct + 1 < ntiles) {                       // tS is consumed: the next tile's first G4 goes there now
-            tc::mbar_wait(&bar_t[e ^ 1], ((ct + 1) >> 1) & 1);
-            tc::tc_fence_after();
-            issue_gemm<D>(tS, aT + (e ^ 1) * C::ATILE, aW3, C::ABLK, C::WBLK);
-            tc::mma_commit(&bar_g4[0]);
+      for (int h = 0; h < H; ++h) {
+        A_STAMP(512, 2 + 4 * h);
+        named_sync(kABarHead + h, NTA);               // dm_h is in shared memory
+        A_STAMP(512, 3 + 4 * h);
+        if (lead) {
+          tc::tc_fence_after();
+          const uint32_t aDh = aDm + h * C::ATILE, aWh = aW3 + h * C::WIMG;
+          if (h + 1 < H) {
+            issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
+            issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
+          } else {
+            issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
+            tc::mma_commit(bar_d);
+            issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
+            tc::mma_commit(bar_gb);
+            if (ct + 1 < ntiles) {                    // tS is consumed: the next tile's first G4 goes there now
+              tc::mbar_wait(&bar_t[e ^ 1], ((ct + 1) >> 1) & 1);
+              tc::tc_fence_after();
+              issue_gemm<D>(tS, aT + (e ^ 1) * C::ATILE, aW3, C::ABLK, C::WBLK);
+              tc::mma_commit(&bar_g4[0]);
+            }
           }
         }
+        A_STAMP(512, 4 + 4 * h);
+        __syncwarp();
       }
     }
-    // dthat = sum_h dm_h W3_h^T -> global (fp16, scaled)
-    tc::mbar_wait(bar_d, par);
+  } else {
+    // ================================ epilogue warps ==============================================================
+    int xw = 0;
+    // per-row scalars of tile `ct` (logits, log-sum-exp, Dg of my row, all heads) -> shared, without passing through registers
+    auto prefetch_rows = [&](int ct) {
+      const int c = ct * ROWS + row;
+      if (cq == 0 && c < P.C) {
+        const int64_t q = (int64_t)b * P.C + c;
+        float* dst = s_rs + (ct & 1) * 3 * ROWS * H + row * H;
+        tc::cp_async<4 * H>(dst, P.slog + (bz * P.C + c) * H);
+        tc::cp_async<4 * H>(dst + ROWS * H, P.lse + q * H);
+        tc::cp_async<4 * H>(dst + 2 * ROWS * H, P.Dg + q * H);
+      }
+    };
+    prefetch_rows(0);
+    uint4 dnq[4];                                      // my 32 columns of the scaled fp16 cotangent of nbar, (tile, head) about to be processed
+    auto load_dnb = [&](int ct, int h) {
+      const uint4* src = P.dnb16 + ((((int64_t)b * ntiles + ct) * H + h) * C::NQ + cq) * 4 * ROWS + row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dnq[q] = __ldg(src + q * ROWS);       // a warp reads 512 contiguous bytes per instruction
+    };
+    load_dnb(0, 0);
+
+    for (int ct = 0; ct < ntiles; ++ct) {
+      const uint32_t par = ct & 1;
+      const int e = ct & 1;                            // region roles of this tile: first = region e, other = region e ^ 1
+      const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
+      const int c0 = ct * ROWS;
+      const bool valid = c0 + row < P.C;
+      A_STAMP(32, 0);
+      tc::cp_async_wait_all();                         // this tile's row scalars (issued a tile ago by the cq == 0 thread of the row);
+                                                       // the row's other threads read them after the row_exchange barrier below
+      if (ct + 1 < ntiles) prefetch_rows(ct + 1);
+      if (ct > 0) {                                    // every MMA of the previous tile is done with the dm tiles
+        tc::mbar_wait(bar_gb, par ^ 1);
+        tc::tc_fence_after();
+      }
+      float v[32];
+      A_STAMP(32, 1);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        tc::mbar_wait(&bar_g4[h], par);
+        tc::tc_fence_after();
+        A_STAMP(32, 2 + 8 * h);
+        tc::tmem_ld32((h == 0 ? tF : tS) + my_t, v);
+        tc::tmem_ld_wait();
+        A_STAMP(32, 3 + 8 * h);
+        // one pass, one exchange: with g = gelu(m), n = (g - mu) rstd the row sums the LayerNorm backward needs are
+        //   sum_j dnb_j n_j = rstd (sum dnb g - mu sum dnb)   and   sum_j dnb_j
+        float dg[32];
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+          const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[j4 >> 3]) + ((j4 & 4) >> 1);     // dnb[j4 .. j4 + 3], packed
+          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
+          const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float g;
+            gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
+            v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+            st[2] = fmaf(dv[t], g, st[2]); st[3] += dv[t];
+          }
+        }
+        A_STAMP(32, 4 + 8 * h);
+        row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
+        A_STAMP(32, 5 + 8 * h);
+        float att = 0.f, Dh = 0.f;
+        if (valid) {
+          const float* rs = s_rs + e * 3 * ROWS * H + row * H + h;
+          att = __expf(rs[0] - rs[ROWS * H]);
+          Dh = rs[2 * ROWS * H];
+        }
+        const float atts = att;                        // dnb16 already carries the scale gs
+        const float mu = st[0] * (1.f / D);
+        const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
+        const float dd0 = rstd * (st[2] - mu * st[3]), dd1 = st[3];
+        const float dsh = atts * (dd0 - Dh * gs);
+        const float mean1 = atts * dd1 * (1.f / D), mean2 = atts * dd0 * (1.f / D);
+        // dm = rstd (att dnb - mean1 - n mean2) g'   with n = (g - mu) rstd, constants folded
+        const float ka = atts * rstd, kc = rstd * (mu * rstd * mean2 - mean1), kb = rstd * rstd * mean2;
+        uint8_t* sDh = sDm + h * C::ATILE;
+        float dm[32];
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[c8 >> 3]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 dv = __half22float2(h2[t]);
+            dm[c8 + 2 * t] = fmaf(-v[c8 + 2 * t], kb, fmaf(ka, dv.x, kc)) * dg[c8 + 2 * t];
+            dm[c8 + 2 * t + 1] = fmaf(-v[c8 + 2 * t + 1], kb, fmaf(ka, dv.y, kc)) * dg[c8 + 2 * t + 1];
+          }
+          tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dm + c8);
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        named_arrive(kABarHead + h, NTA);              // the issue warp takes it from here
+        A_STAMP(32, 6 + 8 * h);
+        {
+          float cs = warp_colsum32(dm, lane);
+          atomicAdd(&s_db3[h * D + col0 + lane], cs);
+        }
+        // fetch the cotangent rows of the next (tile, head) now, a whole MMA round trip ahead of their use
+        if (h + 1 < H) load_dnb(ct, h + 1);
+        else if (ct + 1 < ntiles) load_dnb(ct + 1, 0);
+        if (cq == 0 && valid) P.ds[((bz * P.C) + c0 + row) * H + h] = dsh;
+        A_STAMP(32, 7 + 8 * h);
+      }
+      // dthat = sum_h dm_h W3_h^T -> global (fp16, scaled)
+      tc::mbar_wait(bar_d, par);
+      tc::tc_fence_after();
+      A_STAMP(32, 18);
+      tc::tmem_ld32(tF + my_t, v);
+      tc::tmem_ld_wait();
+      A_STAMP(32, 19);
+      tc::tc_fence_before();
+      if (ct + 1 < ntiles) named_arrive(kABarDth, NTA);     // tF may be overwritten by the next tile's second G4
+      {                                                // chunked order: a warp stores 512 contiguous bytes per instruction
+        uint4* dst = reinterpret_cast<uint4*>(P.dthat) + ((bz * ntiles + ct) * C::NQ + cq) * 4 * ROWS + row;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+          dst[q * ROWS] = u;
+        }
+      }
+      A_STAMP(32, 20);
+    }
+    tc::mbar_wait(bar_gb, (ntiles - 1) & 1);
     tc::tc_fence_after();
-    tc::tmem_ld32(tF + my_t, v);
-    tc::tmem_ld_wait();
-    if (valid) st_half32(P.dthat + ((bz * P.C) + c0 + row) * D + col0, v);
-    tc::cp_async_wait_all();                  // next tile's row scalars have landed (visible to all after the barrier)
-    tc::tc_fence_before();
-    __syncthreads();                          // tF has been read by everyone: the next tile's second G4 may overwrite it
   }
   // flush dW3[b,z,h] (lane = input feature, column = output feature) and db3
-  tc::mbar_wait(bar_gb, (ntiles - 1) & 1);
+  __syncthreads();
   tc::tc_fence_after();
+  if (!issuer) {
 #pragma unroll
-  for (int h = 0; h < H; ++h) {
-    float w[32];
-    tc::tmem_ld32(tW3 + h * D + my_t, w);
-    tc::tmem_ld_wait();
-    float* o = P.g_W3 + ((bz * H + h) * D + row) * D + col0;
+    for (int h = 0; h < H; ++h) {
+      float w[32];
+      tc::tmem_ld32(tW3 + h * D + my_t, w);
+      tc::tmem_ld_wait();
+      float* o = P.g_W3 + ((bz * H + h) * D + row) * D + col0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(o + j) = make_float4(w[j] * inv_gs, w[j + 1] * inv_gs, w[j + 2] * inv_gs, w[j + 3] * inv_gs);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(w[j] * inv_gs, w[j + 1] * inv_gs, w[j + 2] * inv_gs, w[j + 3] * inv_gs);
+    }
   }
-  for (int e = tid; e < H * D; e += C::NT) P.g_b3[bz * H * D + e] = s_db3[e] * inv_gs;
+  for (int e = tid; e < H * D; e += NTA) P.g_b3[bz * H * D + e] = s_db3[e] * inv_gs;
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tm);
@@ -303,17 +395,19 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT, 1) pairs_bwd_tc_a_kernel(Enf
 template <int D, int H>
 int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = BwdCfg<D, H>;
-  const int64_t BC = (int64_t)p.B * p.C;
-  int blocks = (int)((BC * H * 32 + 255) / 256);
+  const int64_t n4 = (int64_t)p.B * p.C * H * D / 4;
+  int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bwd_prep_kernel<<<blocks, 256, 0, st>>>(p.dnbar, p.nbar, BC * H, D, const_cast<float*>(p.Dg), const_cast<float*>(p.gmax));
+  bwd_prep_max_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(p.dnbar), n4, const_cast<float*>(p.gmax));
+  if (cudaMemsetAsync(p.Dg, 0, (size_t)p.B * p.C * H * sizeof(float), st) != cudaSuccess) return -1;
+  bwd_prep_pack_kernel<D><<<148 * 8, 256, 0, st>>>(p.dnbar, p.nbar, p.B, p.C, H, p.gmax, p.dnb16, p.Dg);
   size_t smem_a = ACfg<D, H>::SMEM_BYTES;
   if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)(p.B * p.Z);
-  pairs_bwd_tc_a_kernel<D, H><<<grid, C::NT, smem_a, st>>>(p);
+  pairs_bwd_tc_a_kernel<D, H><<<grid, C::NT + 32, smem_a, st>>>(p);
   if (enf_launch_pairs_bwd_tc_v(st, D, p) < 0) return -1;
   if (enf_launch_pairs_bwd_tc_q(st, D, H, p) < 0) return -1;
-  return 4;
+  return 5;
 }
 
 }  // namespace

@@ -41,7 +41,7 @@ template <int D> struct VCfg {
   static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;    // Omega_v projection image, 1 atom
   static constexpr uint32_t OFF_OMT = OFF_OM + kProjAtom;      // Omega_v^T image for du, [16][64]
   static constexpr uint32_t OFF_F = OFF_OMT + 2048;
-  static constexpr int F_TOTAL = 64 /*lam*/ + 2 * D /*b1v | bp*/ + 2 * NQ * ROWS * 2 /*row exchange*/;
+  static constexpr int F_TOTAL = 64 /*lam*/ + 2 * D /*b1v | bp*/ + NQ * ROWS * 4 /*row exchange*/;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
   float* f = reinterpret_cast<float*>(base + C::OFF_F);
   float* s_lam = f; f += 64;
   float* s_bias = f; f += 2 * D;                      // b1v | bp
-  float* s_exch = f; f += 2 * C::NQ * ROWS * 2;
+  float* s_exch = f; f += C::NQ * ROWS * 4;          // one buffer: a single exchange per tile, block barriers in between
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
   uint64_t *bar_w = bars, *bar_p = bars + 1, *bar_g1 = bars + 2, *bar_g2 = bars + 3, *bar_g3 = bars + 4, *bar_g3b = bars + 5,
            *bar_g4 = bars + 6, *bar_u = bars + 7;
@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       // cotangent of that (kernel A), my 32 columns, fp16: in flight until E3
       uint4 dthq[4];
       {
-        const uint4* src = reinterpret_cast<const uint4*>(P.dthat + pr * D + col0);
+        const uint4* src = reinterpret_cast<const uint4*>(P.dthat) + ((bz * ntiles + ct) * C::NQ + cq) * 4 * ROWS + row;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dthq[q] = valid ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 4; ++q) dthq[q] = valid ? __ldg(src + q * ROWS) : make_uint4(0u, 0u, 0u, 0u);
       }
       if (it > 0 && cq != 0) {                             // every MMA of the previous tile is done with the operand tiles
         tc::mbar_wait(bar_u, (it - 1) & 1);               // (the row threads wait inside store_du below)
@@ -270,43 +270,45 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
       {
+        // one pass, one exchange: with g = gelu(tpre), that = (g - mu) rstd the LayerNorm backward needs
+        //   sum_j dth_j   and   sum_j dth_j that_j = rstd (sum dth g - mu sum dth)
         float dg[32];
-        float st[2] = {0.f, 0.f};
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(s_bias + D + col0 + j4);
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
+          const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[j4 >> 3]) + ((j4 & 4) >> 1);     // dthat[j4 .. j4 + 3], still packed
+          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
+          const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
           for (int t = 0; t < 4; ++t) {
             float g;
             gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
             v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+            st[2] = fmaf(dv[t], g, st[2]); st[3] += dv[t];
           }
         }
-        row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
+        xw = 0;
+        row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
         const float mu = st[0] * (1.f / D);
         const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
-        const float nm = -mu * rstd;
-        float dth[32];
+        const float m1 = st[3] * (1.f / D), m2 = rstd * (st[2] - mu * st[3]) * (1.f / D);
+        // dtpre = rstd (dth - m1 - that m2) g'   with that = (g - mu) rstd, constants folded
+        const float kc = rstd * (mu * rstd * m2 - m1), kb = rstd * rstd * m2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[q]);
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[c8 >> 3]);
+          float o[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) { float2 ff = __half22float2(h2[t]); dth[q * 8 + 2 * t] = ff.x; dth[q * 8 + 2 * t + 1] = ff.y; }
+          for (int t = 0; t < 4; ++t) {
+            const float2 dv = __half22float2(h2[t]);
+            o[2 * t] = fmaf(-v[c8 + 2 * t], kb, fmaf(rstd, dv.x, kc)) * dg[c8 + 2 * t];
+            o[2 * t + 1] = fmaf(-v[c8 + 2 * t + 1], kb, fmaf(rstd, dv.y, kc)) * dg[c8 + 2 * t + 1];
+          }
+          tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, o);
         }
-        float dd[2] = {0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf(v[j], rstd, nm);               // that
-          dd[0] += dth[j];
-          dd[1] = fmaf(dth[j], v[j], dd[1]);
-        }
-        row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, dd);
-        const float m1 = dd[0] * (1.f / D), m2 = dd[1] * (1.f / D);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dth[j] = (dth[j] - m1 - v[j] * m2) * (rstd * dg[j]);      // dtpre
-#pragma unroll
-        for (int c8 = 0; c8 < 32; c8 += 8) tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, dth + c8);
       }
       tc::tc_fence_before();
       tc::fence_proxy_async();

@@ -101,6 +101,7 @@ class _XAttnFunction(torch.autograd.Function):
         ctx.save_for_backward(x, p, a, *([sigma] if sigma is not None else []), *leaves)
         ctx.launches_fwd = lib.enf_last_launch_count()
         _XAttnFunction.last_launches = [ctx.launches_fwd, 0]
+        _XAttnFunction.last_ws = (desc_kw, ws)      # diagnostics (enf_debug_ws_offset views); the buffer lives until the next forward
         return out
 
     @staticmethod
