@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
 
   if (issuer) {
     // ================================ issue warp =================================================================
-    const bool lead = lane == 0;
+    const bool lead = tc::elect_one();
     if (lead) {
       tc::mbar_expect_tx(bar_w, H * C::WIMG);
       for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);

@@ -169,9 +169,9 @@ __device__ __forceinline__ void proj_write_u(uint8_t* tile, int row, const float
 // D[128 x N] = sU^T sOm  (N = 64 or 128)
 __device__ __forceinline__ void issue_proj(uint32_t d_tmem, uint32_t u_addr, uint32_t om_addr, int N) {
   const uint32_t idesc = tc::make_idesc(ROWS, N, tc::kOperandFmt, 1, 1);
+  const uint32_t a = tc::desc_lo_mn(u_addr, kProjAtom), b = tc::desc_lo_mn(om_addr, kProjAtom);
 #pragma unroll
-  for (int kk = 0; kk < 2; ++kk)
-    tc::mma_f16(d_tmem, tc::desc_mnmajor(u_addr + kk * 2048, kProjAtom), tc::desc_mnmajor(om_addr + kk * 2048, kProjAtom), idesc, kk > 0);
+  for (int kk = 0; kk < 2; ++kk) tc::mma_f16_lo(d_tmem, a + kk * (2048 >> 4), b + kk * (2048 >> 4), idesc, kk > 0);
 }
 // my 16 phases (TMEM columns t_proj .. +15 of my lane) -> sin | cos -> 16-bit, swizzled A tile: columns j0.. and HD + j0..
 // SPLIT: also the low part of a two-term 16-bit split into tile_lo.
@@ -201,27 +201,28 @@ __device__ __forceinline__ void rff_from_proj(uint32_t t_proj, uint8_t* tile_hi,
 template <int D>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate = 0) {
   constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 0);
+  const uint32_t a = tc::desc_lo_k(a_addr), b = tc::desc_lo_k(b_addr);
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk)
-    tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + (kk >> 2) * ablk + (kk & 3) * 32),
-                tc::desc_kmajor(b_addr + (kk >> 2) * wblk + (kk & 3) * 32), idesc, (kk > 0) | accumulate);
+    tc::mma_f16_lo(d_tmem, a + (((kk >> 2) * ablk + (kk & 3) * 32) >> 4), b + (((kk >> 2) * wblk + (kk & 3) * 32) >> 4), idesc,
+                   (kk > 0) | accumulate);
 }
 // dgrad: D[128 x D] (+)= G[128 x D] * W^T, with the SAME weight image read MN-major (rows = reduction index)
 template <int D>
 __device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, uint32_t g_addr, uint32_t w_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate) {
   constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 1);
+  const uint32_t a = tc::desc_lo_k(g_addr), b = tc::desc_lo_mn(w_addr, wblk);
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk)
-    tc::mma_f16(d_tmem, tc::desc_kmajor(g_addr + (kk >> 2) * ablk + (kk & 3) * 32), tc::desc_mnmajor(w_addr + kk * 2048, wblk), idesc,
-                (kk > 0) | accumulate);
+    tc::mma_f16_lo(d_tmem, a + (((kk >> 2) * ablk + (kk & 3) * 32) >> 4), b + kk * (2048 >> 4), idesc, (kk > 0) | accumulate);
 }
 // wgrad: dW[D x D] (+)= Act[128 x D]^T * G[128 x D]; both activation tiles read MN-major (rows = reduction index)
 template <int D>
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t act_addr, uint32_t g_addr, uint32_t ablk, uint32_t accumulate) {
   constexpr uint32_t idesc = tc::make_idesc(D, D, tc::kOperandFmt, 1, 1);
+  const uint32_t a = tc::desc_lo_mn(act_addr, ablk), b = tc::desc_lo_mn(g_addr, ablk);
 #pragma unroll
-  for (int kk = 0; kk < ROWS / 16; ++kk)
-    tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_mnmajor(g_addr + kk * 2048, ablk), idesc, (kk > 0) | accumulate);
+  for (int kk = 0; kk < ROWS / 16; ++kk) tc::mma_f16_lo(d_tmem, a + kk * (2048 >> 4), b + kk * (2048 >> 4), idesc, (kk > 0) | accumulate);
 }
 
 // Sum NV per-thread partials over the NQ threads that share a query row.  `buf` = two alternating

@@ -103,6 +103,27 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same, from the LOW 32-bit words of the two descriptors (the high word is the constant kDescHi for every tile in this
+// library).  The start-address field sits in the low 14 bits in units of 16 bytes, so stepping an operand by `off` bytes
+// is `lo + (off >> 4)` -- one add with an immediate per operand per MMA instead of rebuilding the descriptor.
+constexpr uint32_t kDescHi = uint32_t(kDescBase >> 32) | uint32_t(1024 >> 4);
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t block_bytes) { return ((saddr >> 4) & 0x3FFF) | (((block_bytes >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ void mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+// one lane of a converged warp (the issue warp's leader)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // arrive on `bar` when every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
