@@ -269,10 +269,6 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
       tc::cp_async_wait_all();                         // this tile's row scalars (issued a tile ago by the cq == 0 thread of the row);
                                                        // the row's other threads read them after the row_exchange barrier below
       if (ct + 1 < ntiles) prefetch_rows(ct + 1);
-      if (ct > 0) {                                    // every MMA of the previous tile is done with the dm tiles
-        tc::mbar_wait(bar_gb, par ^ 1);
-        tc::tc_fence_after();
-      }
       float v[32];
       A_STAMP(32, 1);
 #pragma unroll
@@ -286,21 +282,30 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
         // one pass, one exchange: with g = gelu(m), n = (g - mu) rstd the row sums the LayerNorm backward needs are
         //   sum_j dnb_j n_j = rstd (sum dnb g - mu sum dnb)   and   sum_j dnb_j
         float dg[32];
+        uint32_t gh[16];                               // g, packed to fp16 once the row sums have seen it in fp32 (it only re-enters
+                                                       // through the small LayerNorm projection term of dm): 16 registers instead of 32
         float st[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-          const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[j4 >> 3]) + ((j4 & 4) >> 1);     // dnb[j4 .. j4 + 3], packed
-          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
-          const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             float g;
             gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
             v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
-            st[2] = fmaf(dv[t], g, st[2]); st[3] += dv[t];
           }
+        }
+        // the cotangent rows were requested one phase ago; touching them only now keeps their L2 latency off the gelu pass
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[j4 >> 3]) + ((j4 & 4) >> 1);     // dnb[j4 .. j4 + 3], packed
+          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
+          st[2] = fmaf(d01.x, v[j4], st[2]); st[2] = fmaf(d01.y, v[j4 + 1], st[2]);
+          st[2] = fmaf(d23.x, v[j4 + 2], st[2]); st[2] = fmaf(d23.y, v[j4 + 3], st[2]);
+          st[3] += (d01.x + d01.y) + (d23.x + d23.y);
+          gh[j4 >> 1] = tc::pack_bf16(v[j4], v[j4 + 1]);
+          gh[(j4 >> 1) + 1] = tc::pack_bf16(v[j4 + 2], v[j4 + 3]);
         }
         A_STAMP(32, 4 + 8 * h);
         row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
@@ -320,29 +325,33 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
         // dm = rstd (att dnb - mean1 - n mean2) g'   with n = (g - mu) rstd, constants folded
         const float ka = atts * rstd, kc = rstd * (mu * rstd * mean2 - mean1), kb = rstd * rstd * mean2;
         uint8_t* sDh = sDm + h * C::ATILE;
-        float dm[32];
+        if (h == 0 && ct > 0) tc::mbar_wait(bar_gb, par ^ 1);      // every MMA of the previous tile is done with the dm tiles
 #pragma unroll
-        for (int c8 = 0; c8 < 32; c8 += 8) {
+        for (int c8 = 0; c8 < 32; c8 += 8) {           // dm overwrites g' in place
           const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[c8 >> 3]);
+          const __half2* g2 = reinterpret_cast<const __half2*>(&gh[c8 >> 1]);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 dv = __half22float2(h2[t]);
-            dm[c8 + 2 * t] = fmaf(-v[c8 + 2 * t], kb, fmaf(ka, dv.x, kc)) * dg[c8 + 2 * t];
-            dm[c8 + 2 * t + 1] = fmaf(-v[c8 + 2 * t + 1], kb, fmaf(ka, dv.y, kc)) * dg[c8 + 2 * t + 1];
+            const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
+            dg[c8 + 2 * t] = fmaf(-gv.x, kb, fmaf(ka, dv.x, kc)) * dg[c8 + 2 * t];
+            dg[c8 + 2 * t + 1] = fmaf(-gv.y, kb, fmaf(ka, dv.y, kc)) * dg[c8 + 2 * t + 1];
           }
-          tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dm + c8);
+          tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dg + c8);
         }
+        A_STAMP(32, 21 + 3 * h);
         tc::fence_proxy_async();
+        A_STAMP(32, 22 + 3 * h);
         tc::tc_fence_before();
         named_arrive(kABarHead + h, NTA);              // the issue warp takes it from here
         A_STAMP(32, 6 + 8 * h);
-        {
-          float cs = warp_colsum32(dm, lane);
-          atomicAdd(&s_db3[h * D + col0 + lane], cs);
-        }
-        // fetch the cotangent rows of the next (tile, head) now, a whole MMA round trip ahead of their use
+        // fetch the cotangent rows of the next (tile, head) now, a whole phase ahead of their use
         if (h + 1 < H) load_dnb(ct, h + 1);
         else if (ct + 1 < ntiles) load_dnb(ct + 1, 0);
+        {
+          float cs = warp_colsum32(dg, lane);
+          A_STAMP(32, 23 + 3 * h);
+          atomicAdd(&s_db3[h * D + col0 + lane], cs);
+        }
         if (cq == 0 && valid) P.ds[((bz * P.C) + c0 + row) * H + h] = dsh;
         A_STAMP(32, 7 + 8 * h);
       }
