@@ -87,7 +87,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
-    Y.add("slog", BC * (size_t)D.Z * H);
+    Y.add("slog", BC * (size_t)D.Z * H); Y.add("dbg_fwd", 8192);
     // tf32 stage GEMMs: activated copies of the decode-MLP pre-activations (their A operands arrive by TMA) and the
     // low parts W - trunc_tf32(W) of the weights those GEMMs multiply by (3-term split product)
     Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
@@ -359,6 +359,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
     tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = c.f("slog");
     tp.that_img = enf_pairs_bwd_tc_supported(D.d, D.H) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
+    static const bool trace_fwd = getenv("ENF_DEBUG_TRACE") != nullptr;
+    tp.dbg = trace_fwd ? reinterpret_cast<long long*>(c.f("dbg_fwd")) : nullptr;
     prof_mark(0, 0, st);
     nl = enf_launch_pairs_fwd_tc(st, d, H, tp);
     prof_mark(0, 1, st);

@@ -168,6 +168,7 @@ struct EnfPairTcParams {
   float* nbar; float* lse; float* slog;      // slog [B,Z,C,H]: logits incl. window (saved for the backward), may be null
   uint8_t* that_img;                         // [B,Z,ceil(C/128)] operand images (128 rows x d, fp16, swizzled) of that = LN(gelu(.)),
                                              // stashed for backward kernel A; may be null (forward only / SIMT backward)
+  long long* dbg;                            // optional clock64() trace of one CTA (diagnostics; null in production)
 };
 bool enf_pairs_fwd_tc_supported(int d, int H);
 int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p);

@@ -37,12 +37,22 @@ template <int D, int H> struct TcCfg {
   static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;   // projection operand: [Omega_q | Omega_v] (D / 64 atoms)
   static constexpr uint32_t OFF_F = OFF_OM + (D / 64) * kProjAtom;    // float arrays start here
   // float arrays (counts)
-  static constexpr int F_LAM = 2 * 64, F_WIN = 2 * ROWS, F_UZ = H * D, F_KAP = 8, F_B3 = H * D, F_BIAS = 3 * D,
-                       F_SPART = NQ * ROWS * H, F_EXCH = 2 * NQ * ROWS * 2;
-  static constexpr int F_TOTAL = F_LAM + F_WIN + F_UZ + F_KAP + F_B3 + F_BIAS + F_SPART + F_EXCH;
+  // per-latent vectors are double buffered (cp.async prefetch of the next latent): [2] x { Lam 64 | U H*D | b3 H*D | kappa, sigma 8 }
+  static constexpr int F_LAT = 64 + 2 * H * D + 8;
+  static constexpr int F_WIN = 2 * ROWS, F_BIAS = 3 * D, F_EXCH = 2 * NQ * ROWS * 2;
+  static_assert(H <= 2, "the logit partials [NQ][ROWS][H] share exchange buffer 1");
+  static constexpr int F_TOTAL = 2 * F_LAT + F_WIN + F_BIAS + F_EXCH;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
+
+// diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA (7, 0),
+// latents 8..11, thread 32
+#ifdef ENF_TRACE
+#define F_STAMP(slot) do { if (P.dbg && blockIdx.x == 7 && blockIdx.y == 0 && tid == 32 && z >= 8 && z < 12) P.dbg[(z - 8) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define F_STAMP(slot) do { } while (0)
+#endif
 
 template <int D, int H>
 __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
@@ -56,14 +66,11 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   uint8_t* sU = base + C::OFF_U;
   uint8_t* sOm = base + C::OFF_OM;
   float* f = reinterpret_cast<float*>(base + C::OFF_F);
-  float* s_lam = f; f += C::F_LAM;            // [2][64]: pose records of this and the next latent
+  float* s_lat = f; f += 2 * C::F_LAT;        // [2] per-latent vectors of this and the next latent
   float* s_win = f; f += C::F_WIN;            // [2][ROWS]: window values of this and the next latent
-  float* s_uz = f; f += C::F_UZ;
-  float* s_kap = f; f += C::F_KAP;
-  float* s_b3 = f; f += C::F_B3;
   float* s_bias = f; f += C::F_BIAS;          // b1q | b1v | bp
-  float* s_spart = f; f += C::F_SPART;        // [NQ][ROWS][H]
-  float* s_exch = f; f += C::F_EXCH;          // two alternating [NQ][ROWS][2] exchange buffers
+  float* s_exch = f; f += C::F_EXCH;          // two [NQ][ROWS][2] exchange buffers: 0 = E3 and E4_1, 1 = E4_0
+  float* s_spart = s_exch + C::NQ * ROWS * 2; // [NQ][ROWS][H] logit partials live in buffer 1 between E1 and the softmax statistics
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
   uint64_t* bar_w = bars + 0;
   uint64_t* bar_g1 = bars + 1;
@@ -89,18 +96,47 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
   // per-CTA constants
   for (int e = tid; e < D; e += C::NT) { s_bias[e] = P.q_b1[e]; s_bias[D + e] = P.v_b1[e]; s_bias[2 * D + e] = P.bp[e]; }
-  if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[(int64_t)b * P.Z * ENF_LAM_SIZE + tid];
+  // per-latent vectors of latent z -> buffer z & 1, without passing through registers (16-byte cp.async each)
+  auto prefetch_latent = [&](int z) {
+    const int64_t q = (int64_t)b * P.Z + z;
+    float* dst = s_lat + (z & 1) * C::F_LAT;
+    constexpr int NU = H * D / 4;
+    if (tid < NU) tc::cp_async<16>(dst + 64 + 4 * tid, P.U + q * H * D + 4 * tid);
+    else if (tid < 2 * NU) tc::cp_async<16>(dst + 64 + H * D + 4 * (tid - NU), P.b3 + q * H * D + 4 * (tid - NU));
+    else if (tid < 2 * NU + ENF_LAM_SIZE / 4) tc::cp_async<16>(dst + 4 * (tid - 2 * NU), P.lam + q * ENF_LAM_SIZE + 4 * (tid - 2 * NU));
+    else if (tid == 2 * NU + ENF_LAM_SIZE / 4) tc::cp_async<4 * H>(dst + 64 + 2 * H * D, P.kappa + q * H);
+    else if (tid == 2 * NU + ENF_LAM_SIZE / 4 + 1 && P.sigma) tc::cp_async<4>(dst + 64 + 2 * H * D + 4, P.sigma + q);
+  };
+  prefetch_latent(0);
+  tc::cp_async_wait_all();
   proj_zero(sU, 2, tid, C::NT);
   proj_zero(sOm, D / 64, tid, C::NT);
-  // the record thread of a row (cq == 0) keeps the row's query features in registers for the whole kernel
+  // every thread keeps its row's query features in registers for the whole kernel (the NQ threads of a row share the
+  // invariant rows of the next latent between them)
   float xi_r[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) xi_r[k] = 0.f;
-  if (cq == 0 && row_valid) {
+  if (row_valid) {
     const float4* src = reinterpret_cast<const float4*>(P.xi + (int64_t)b * P.xi_bs + (int64_t)(c0 + row) * 8);
     float4 a = __ldg(src), c = __ldg(src + 1);
     xi_r[0] = a.x; xi_r[1] = a.y; xi_r[2] = a.z; xi_r[3] = a.w; xi_r[4] = c.x; xi_r[5] = c.y; xi_r[6] = c.z; xi_r[7] = c.w;
   }
+  // invariants of latent `buf`'s record -> projection operand: thread cq of a row computes rows cq and cq + NQ, the last
+  // thread of the row also the window value
+  auto write_invariants = [&](const float* lat, int wbuf) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = cq + k * C::NQ;
+      if (i < P.I && i < 6) proj_store_pair(sU, i, row, inv_row(P, lat, xi_r, i), true);
+    }
+    if (cq == C::NQ - 1) {
+      float u0 = 0.f, u1 = 0.f, w, c;
+      if (P.win_kind == ENF_WIN_PER) { u0 = inv_row(P, lat, xi_r, 0); u1 = inv_row(P, lat, xi_r, 1); }
+      else if (P.win_kind == ENF_WIN_SPH && P.win_row < 0) u0 = inv_row(P, lat, xi_r, 0);
+      window_value(P, lat, xi_r, P.sigma ? lat[64 + 2 * H * D + 4] : 1.f, u0, u1, w, c);
+      s_win[wbuf * ROWS + row] = w;
+    }
+  };
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -123,11 +159,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   // Omega image [Omega_q | Omega_v]; invariants of latent 0; phases of latent 0
   proj_build_omega(sOm, 0, P.q_omega, P.I, HD, tid, C::NT);
   proj_build_omega(sOm, HD, P.v_omega, P.I, HD, tid, C::NT);
-  if (cq == 0) {
-    const Rec rec = pair_record(P, s_lam, xi_r, P.sigma ? P.sigma[(int64_t)b * P.Z] : 1.f);
-    proj_write_u(sU, row, rec.u, P.I);
-    s_win[row] = rec.w;
-  }
+  __syncthreads();                             // latent 0's vectors are visible
+  write_invariants(s_lat, 0);
   tc::fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -150,20 +183,24 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     const uint32_t par = z & 1;
     const int64_t bz = (int64_t)b * P.Z + z;
     const bool more = z + 1 < P.Z;
-    // ---- (a) per-latent vectors; gamma_q, gamma_v from the phases the tensor core left in TMEM -----------------------
-    if (tid < H) s_kap[tid] = P.kappa[bz * H + tid];
-    if (more && tid < ENF_LAM_SIZE) s_lam[(par ^ 1) * 64 + tid] = P.lam[(bz + 1) * ENF_LAM_SIZE + tid];
-    for (int e = tid; e < H * D; e += C::NT) {
-      s_uz[e] = P.U[bz * H * D + e];
-      s_b3[e] = P.b3[bz * H * D + e];
-    }
+    F_STAMP(0);
+    // ---- (a) RFF phases of this latent (its invariants were written during the previous latent's E4); prefetch of the
+    //          next latent's vectors; gamma_q, gamma_v from the phases
+    if (more) prefetch_latent(z + 1);
+    const float* s_lam_next = s_lat + (par ^ 1) * C::F_LAT;
+    const float* s_uz = s_lat + par * C::F_LAT + 64;
+    const float* s_b3 = s_uz + H * D;
+    const float* s_kap = s_b3 + H * D;
     tc::mbar_wait(bar_p, par);
     tc::tc_fence_after();
+    F_STAMP(1);
     rff_from_proj<D, false>(tp + lane_off + 16 * cq, sA0, nullptr, C::ABLK, row, 16 * cq);
     rff_from_proj<D, false>(tp + lane_off + HD + 16 * cq, sA1, nullptr, C::ABLK, row, 16 * cq);
+    F_STAMP(2);
     tc::tc_fence_before();
     tc::fence_proxy_async();
     __syncthreads();
+    F_STAMP(3);
     if (tid == 0) {
       if (z == 0) tc::mbar_wait(bar_w, 0);
       tc::tc_fence_after();
@@ -172,17 +209,13 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       issue_gemm<D>(t1, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g2);
     }
-    // ---- (b) invariants of the NEXT latent -> projection operand (its MMA is issued with GEMM3 below) ------------------
     const float win = s_win[par * ROWS + row];
-    if (more && cq == 0) {
-      const Rec rec = pair_record(P, s_lam + (par ^ 1) * 64, xi_r, P.sigma ? P.sigma[bz + 1] : 1.f);
-      proj_write_u(sU, row, rec.u, P.I);
-      s_win[(par ^ 1) * ROWS + row] = rec.w;
-    }
     // ---- (c) E1: h1q = relu(T0 + b1q); logit partials (overlaps GEMM2) -------------------------------------
     float v[32];
+    F_STAMP(4);
     tc::mbar_wait(bar_g1, par);
     tc::tc_fence_after();
+    F_STAMP(5);
     tc::tmem_ld32(t0 + my_t, v);
     tc::tmem_ld_wait();
     {
@@ -199,8 +232,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       for (int h = 0; h < H; ++h) s_spart[(cq * ROWS + row) * H + h] = part[h];
     }
     // ---- (d) E2: h1v = relu(T1 + b1v) -> A0 ----------------------------------------------------------------
+    F_STAMP(6);
     tc::mbar_wait(bar_g2, par);
     tc::tc_fence_after();
+    F_STAMP(7);
     tc::tmem_ld32(t1 + my_t, v);
     tc::tmem_ld_wait();
 #pragma unroll
@@ -210,17 +245,15 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       for (int t = 0; t < 8; ++t) o[t] = fmaxf(v[c8 + t] + s_bias[D + col0 + c8 + t], 0.f);
       tc::st_row8_bf16(sA0, C::ABLK, row, col0 + c8, o);
     }
+    F_STAMP(8);
     tc::tc_fence_before();
     tc::fence_proxy_async();
     __syncthreads();
+    F_STAMP(9);
     if (tid == 0) {
       tc::tc_fence_after();
       issue_gemm<D>(t0, aA0, aW + 2 * C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g3);
-      if (more) {                      // phases of the next latent (every thread read this latent's before the barrier)
-        issue_proj(tp, aU, aOm, D);
-        tc::mma_commit(bar_p);
-      }
     }
     // softmax statistics for this latent (every thread of the row, redundantly; overlaps GEMM3)
     float pw[H], corr[H];
@@ -238,8 +271,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       m_run[h] = m_new;
     }
     // ---- (e) E3: g = gelu(T0 + b'), row statistics, LayerNorm -> A1 ----
+    F_STAMP(10);
     tc::mbar_wait(bar_g3, par);
     tc::tc_fence_after();
+    F_STAMP(11);
     if (H > 1 && tid == 0) {          // A0 is free again: stream W3[z,1] into it
       tc::mbar_expect_tx(&bar_w3[1], C::WIMG);
       tc::bulk_g2s(sA0, P.img_W3 + (bz * H + 1) * C::WIMG, C::WIMG, &bar_w3[1]);
@@ -253,7 +288,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         float g = gelu_fast(v[j] + s_bias[2 * D + col0 + j]);
         v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
       }
+      F_STAMP(12);
+      xw = 0;
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
+      F_STAMP(13);
       const float mu = st[0] * (1.f / D);
       const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
       const float nm = -mu * rstd;
@@ -265,9 +303,12 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         tc::st_row8_bf16(sA1, C::ABLK, row, col0 + c8, o);
       }
     }
+    F_STAMP(14);
+    tc::cp_async_wait_all();                  // the next latent's vectors (requested at the top) are visible after this barrier
     tc::tc_fence_before();
     tc::fence_proxy_async();
     __syncthreads();
+    F_STAMP(15);
     if (tid == 0) {
       if (P.that_img) {                // stash the that operand tile for backward kernel A (bulk store, no thread work)
         tc::bulk_s2g(P.that_img + ((size_t)bz * gridDim.x + blockIdx.x) * C::ATILE, sA1, C::ATILE);
@@ -283,11 +324,29 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         tc::mma_commit(&bar_g4[1]);
       }
     }
+    // ---- invariants of the NEXT latent -> projection operand, in the shadow of GEMM4_0; warp 0 collects the arrivals and
+    //      issues the tiny phase MMA behind GEMM4 (named barrier 6: arrive / sync, nobody else blocks)
+    if (more) {
+      write_invariants(s_lam_next, par ^ 1);
+      tc::fence_proxy_async();
+      if (warp == 0) {
+        tc::named_sync(6, C::NT);
+        if (tid == 0) {
+          tc::tc_fence_after();
+          issue_proj(tp, aU, aOm, D);
+          tc::mma_commit(bar_p);
+        }
+        __syncwarp();
+      } else {
+        tc::named_arrive(6, C::NT);
+      }
+    }
     // ---- (f) E4: per head  m = T + b3 ; n = LN(gelu(m)) ; acc += p n --------------------------------------------
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       tc::mbar_wait(&bar_g4[h], par);
       tc::tc_fence_after();
+      F_STAMP(16 + 2 * h);
       if (h == 0 && tid == 0 && more) {       // stage buffer is free: prefetch next latent's W3[.,0]
         tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
         tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
@@ -300,6 +359,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         float g = gelu_fast(v[j] + s_b3[h * D + col0 + j]);
         v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
       }
+      xw = (h + 1) & 1;                       // E4_0 -> buffer 1 (the logit partials are dead), E4_1 -> buffer 0
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
       float mu = st[0] * (1.f / D);
       float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
@@ -307,10 +367,12 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       float tz = -pr * mu;
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[h][j] = fmaf(v[j], pr, fmaf(acc[h][j], corr[h], tz));
+      F_STAMP(17 + 2 * h);
     }
     if (tid == 0 && P.that_img) tc::bulk_wait_read0();      // the stash has been read out of A1 before the next latent overwrites it
     tc::tc_fence_before();
     __syncthreads();
+    F_STAMP(20);
   }
 
   if (row_valid) {

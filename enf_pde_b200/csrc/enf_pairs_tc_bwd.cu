@@ -124,11 +124,16 @@ template <int D, int H> struct ACfg {
 // written they ARRIVE on a named barrier the issue warp SYNCs on, and go on with whatever does not need that MMA.
 constexpr int kABarHead = 5;      // + h: dm_h tile written                      (named barriers 1..4 belong to row_exchange)
 constexpr int kABarDth = 7;       // dthat of the tile has been read out of TMEM
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+using tc::named_arrive;
+using tc::named_sync;
 
-// diagnostics: clock64() of selected events of CTA 7, tiles 4..7, for thread `who` (ENF_DEBUG_TRACE=1)
+// diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA 7, tiles 4..7,
+// for thread `who`
+#ifdef ENF_TRACE
 #define A_STAMP(who, slot) do { if (P.dbg && blockIdx.x == 7 && tid == (who) && ct >= 4 && ct < 8) P.dbg[((who) == 512 ? 512 : 0) + (ct - 4) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define A_STAMP(who, slot) do { } while (0)
+#endif
 
 template <int D, int H>
 __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
