@@ -223,10 +223,18 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
 #pragma unroll
       for (int h = 0; h < H; ++h) part[h] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float hq = fmaxf(v[j] + s_bias[col0 + j], 0.f);
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(s_bias + col0 + j4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float hq[4];
 #pragma unroll
-        for (int h = 0; h < H; ++h) part[h] = fmaf(hq, s_uz[h * D + col0 + j], part[h]);
+        for (int t = 0; t < 4; ++t) hq[t] = fmaxf(v[j4 + t] + bv[t], 0.f);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float4 uu = *reinterpret_cast<const float4*>(s_uz + h * D + col0 + j4);
+          part[h] = fmaf(hq[0], uu.x, part[h]); part[h] = fmaf(hq[1], uu.y, part[h]);
+          part[h] = fmaf(hq[2], uu.z, part[h]); part[h] = fmaf(hq[3], uu.w, part[h]);
+        }
       }
 #pragma unroll
       for (int h = 0; h < H; ++h) s_spart[(cq * ROWS + row) * H + h] = part[h];
@@ -241,8 +249,11 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
 #pragma unroll
     for (int c8 = 0; c8 < 32; c8 += 8) {
       float o[8];
+      const float4 b0 = *reinterpret_cast<const float4*>(s_bias + D + col0 + c8);
+      const float4 b1 = *reinterpret_cast<const float4*>(s_bias + D + col0 + c8 + 4);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o[t] = fmaxf(v[c8 + t] + s_bias[D + col0 + c8 + t], 0.f);
+      for (int t = 0; t < 8; ++t) o[t] = fmaxf(v[c8 + t] + bv[t], 0.f);
       tc::st_row8_bf16(sA0, C::ABLK, row, col0 + c8, o);
     }
     F_STAMP(8);
@@ -284,9 +295,14 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     {
       float st[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float g = gelu_fast(v[j] + s_bias[2 * D + col0 + j]);
-        v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(s_bias + 2 * D + col0 + j4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float g = gelu_fast(v[j4 + t] + bv[t]);
+          v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+        }
       }
       F_STAMP(12);
       xw = 0;
@@ -355,9 +371,14 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       tc::tmem_ld_wait();
       float st[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float g = gelu_fast(v[j] + s_b3[h * D + col0 + j]);
-        v[j] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float g = gelu_fast(v[j4 + t] + bv[t]);
+          v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+        }
       }
       xw = (h + 1) & 1;                       // E4_0 -> buffer 1 (the logit partials are dead), E4_1 -> buffer 0
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
