@@ -72,7 +72,7 @@ def read_peaks():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, 100 ms period)."""
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, 10 ms period)."""
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
@@ -96,7 +96,7 @@ class ClockSampler:
                 for n, bit in names.items():
                     if mask & bit:
                         self.reasons.add(n)
-                self._stop.wait(0.1)
+                self._stop.wait(0.01)
         except Exception as e:          # noqa: BLE001
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
