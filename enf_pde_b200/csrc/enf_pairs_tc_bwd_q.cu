@@ -37,7 +37,8 @@ template <int D, int H> struct QCfg {
   static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;    // Omega_q projection image, 1 atom
   static constexpr uint32_t OFF_OMT = OFF_OM + kProjAtom;      // Omega_q^T image for du, [16][64]
   static constexpr uint32_t OFF_F = OFF_OMT + 2048;
-  static constexpr int F_TOTAL = 64 /*lam*/ + D /*b1q*/ + H * D /*scale U*/ + 64 /*dlam*/ + 8 /*dkappa*/;
+  static constexpr int RX = 20;                                // per-row record: xi[8] | u[6], w, c | dw | pad
+  static constexpr int F_TOTAL = 64 /*lam*/ + D /*b1q*/ + H * D /*scale U*/ + 64 /*dlam*/ + 8 /*dkappa*/ + 3 * ROWS * RX /*row records of 3 tiles*/;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -67,6 +68,14 @@ __device__ __forceinline__ void issue_du(uint32_t d_tmem, uint32_t a_addr, uint3
   for (int kk = 0; kk < 4; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
 }
 
+// diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA 7, its first
+// item, tiles 4..7, for thread `who`
+#ifdef ENF_TRACE
+#define Q_STAMP(who, slot) do { if (P.dbg && blockIdx.x == 7 && item == 7 && tid == (who) && ct >= 4 && ct < 8) P.dbg[1024 + ((who) == 32 ? 0 : 128) + (ct - 4) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define Q_STAMP(who, slot) do { } while (0)
+#endif
+
 template <int D, int H>
 __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
   using C = QCfg<D, H>;
@@ -88,6 +97,8 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
   float* s_us = f; f += H * D;                        // scale * U[b,z,h,:]
   float* s_dlam = f; f += 64;                         // [0,56): dLam, [56]: dsigma
   float* s_dkap = f; f += 8;
+  float* s_rx = f; f += 3 * ROWS * C::RX;             // [3 tiles][ROWS][RX]: query features, invariants, window and dw of a row, written
+                                                      // by the row's cq == 0 thread, read one tile later by its cq == 1, 2 threads
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
   uint64_t *bar_w = bars, *bar_p = bars + 1, *bar_g1 = bars + 2, *bar_d = bars + 3, *bar_u = bars + 4;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
@@ -160,20 +171,24 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         xi_r[0] = a.x; xi_r[1] = a.y; xi_r[2] = a.z; xi_r[3] = a.w; xi_r[4] = c.x; xi_r[5] = c.y; xi_r[6] = c.z; xi_r[7] = c.w;
       }
     };
+    const uint32_t it0 = it;                           // row-record slot of tile ct of this item: (it0 + ct) % 3
     auto write_invariants = [&](int ct) {
       float xi_r[8];
       load_xi(ct, xi_r);
       const Rec rec = pair_record(P, s_lam, xi_r, sigma);
       proj_write_u(sU, row, rec.u, P.I);
+      float4* rx = reinterpret_cast<float4*>(s_rx + (((it0 + ct) % 3) * ROWS + row) * C::RX);
+      rx[0] = make_float4(xi_r[0], xi_r[1], xi_r[2], xi_r[3]);
+      rx[1] = make_float4(xi_r[4], xi_r[5], xi_r[6], xi_r[7]);
+      rx[2] = make_float4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]);
+      rx[3] = make_float4(rec.u[4], rec.u[5], rec.w, rec.c);
     };
-    float lam_acc0 = 0.f, lam_acc1 = 0.f, kap_acc[H];
+    float lam_acc = 0.f, kap_acc[H];                   // lam_acc: cq == 1 threads hold dLam[0..31], cq == 2 threads dLam[32..55] | dsigma
 #pragma unroll
     for (int h = 0; h < H; ++h) kap_acc[h] = 0.f;
-    float dw_prev = 0.f;
-    // one thread per row: du (tile ct) + du_v -> window backward -> dq -> dLam, dsigma partial sums (lane l keeps column l)
-    auto row_backward = [&](int ct, uint32_t par_u, float dw) {
-      float xi_r[8];
-      load_xi(ct, xi_r);
+    // du (tile ct) + du_v -> window backward -> dq -> my half of dLam / dsigma partial sums (lane l keeps column l).
+    // The row's record comes from shared memory (written a tile earlier by the cq == 0 thread); part = 0: cq == 1, 1: cq == 2.
+    auto row_backward = [&](int ct, uint32_t par_u, int part) {
       const bool valid = ct * ROWS + row < P.C;
       float duv[8];
 #pragma unroll
@@ -183,7 +198,12 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         float4 a = __ldg(src), c = __ldg(src + 1);
         duv[0] = a.x; duv[1] = a.y; duv[2] = a.z; duv[3] = a.w; duv[4] = c.x; duv[5] = c.y; duv[6] = c.z; duv[7] = c.w;
       }
-      const Rec rec = pair_record(P, s_lam, xi_r, sigma);
+      const float4* rx = reinterpret_cast<const float4*>(s_rx + (((it0 + ct) % 3) * ROWS + row) * C::RX);
+      const float4 x0 = rx[0], x1 = rx[1], r0 = rx[2], r1 = rx[3];
+      const float xi_r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      Rec rec;
+      rec.u[0] = r0.x; rec.u[1] = r0.y; rec.u[2] = r0.z; rec.u[3] = r0.w; rec.u[4] = r1.x; rec.u[5] = r1.y; rec.w = r1.z; rec.c = r1.w;
+      const float dw = reinterpret_cast<const float*>(rx)[16];
       tc::mbar_wait(bar_u, par_u);
       tc::tc_fence_after();
       float d16[16];
@@ -220,15 +240,18 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           else dq[r] = du[r];
         }
       }
-      float v0[32], v1[32];
+      float vv[32];
+      if (part == 0) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        v0[e] = dq[e >> 3] * xi_r[e & 7];
-        const int e1 = 32 + e;
-        v1[e] = e1 < ENF_LAM_SIZE ? dq[e1 >> 3] * xi_r[e1 & 7] : (e1 == ENF_LAM_SIZE ? dsg : 0.f);
+        for (int e = 0; e < 32; ++e) vv[e] = dq[e >> 3] * xi_r[e & 7];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int e1 = 32 + e;
+          vv[e] = e1 < ENF_LAM_SIZE ? dq[e1 >> 3] * xi_r[e1 & 7] : (e1 == ENF_LAM_SIZE ? dsg : 0.f);
+        }
       }
-      lam_acc0 += warp_colsum32(v0, lane);
-      lam_acc1 += warp_colsum32(v1, lane);
+      lam_acc += warp_colsum32(vv, lane);
     };
 
     if (cq == 0) write_invariants(0);
@@ -248,14 +271,19 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       float dsv[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) dsv[h] = valid ? __ldg(P.ds + pr * H + h) : 0.f;
+      Q_STAMP(32, 0); Q_STAMP(160, 0);
       if (it > 0) tc::mbar_wait(bar_u, (it - 1) & 1);     // every MMA of the previous tile is done with the operand tiles
+      Q_STAMP(32, 1); Q_STAMP(160, 1);
       // ---- S1: gamma_q hi / lo ---------------------------------------------------------------------------------
       tc::mbar_wait(bar_p, par);
       tc::tc_fence_after();
+      Q_STAMP(32, 2); Q_STAMP(160, 2);
       rff_from_proj<D, true>(tP + lane_off + 16 * cq, sGhi, sGlo, C::ABLK, row, 16 * cq);
+      Q_STAMP(32, 3); Q_STAMP(160, 3);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      Q_STAMP(32, 4); Q_STAMP(160, 4);
       if (tid == MMA_TID) {
         if (it == 0) tc::mbar_wait(bar_w, 0);
         tc::tc_fence_after();
@@ -264,7 +292,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
         tc::mma_commit(bar_g1);
       }
-      // ---- per-row side work, overlapped with the 3-term GEMM ---------------------------------------------------
+      // ---- per-row side work, overlapped with the 3-term GEMM: shared by three of the row's four threads ----------------
       if (cq == 0) {
         {                                                  // side operand row: [1 | ds_hi | ds_lo | 0 ...]
           __half hv[8];
@@ -278,17 +306,20 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           }
           *reinterpret_cast<uint4*>(sS + tc::swz_chunk_off(row, 0)) = *reinterpret_cast<const uint4*>(hv);
         }
-        if (ct + 1 < ntiles) write_invariants(ct + 1);
-        if (ct > 0) row_backward(ct - 1, (it - 1) & 1, dw_prev);
         float dw = 0.f;
 #pragma unroll
         for (int h = 0; h < H; ++h) { kap_acc[h] += dsv[h]; dw += dsv[h]; }
-        dw_prev = dw;
+        s_rx[(((it0 + ct) % 3) * ROWS + row) * C::RX + 16] = dw;
+        if (ct + 1 < ntiles) write_invariants(ct + 1);
+      } else if (cq <= 2 && ct > 0) {
+        row_backward(ct - 1, (it - 1) & 1, cq - 1);
       }
       // ---- E: h1q, dzq ---------------------------------------------------------------------------------------------
       float v[32];
+      Q_STAMP(32, 5); Q_STAMP(160, 5);
       tc::mbar_wait(bar_g1, par);
       tc::tc_fence_after();
+      Q_STAMP(32, 6); Q_STAMP(160, 6);
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
 #pragma unroll
@@ -317,9 +348,11 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         tc::st_row8_bf16(sGlo, C::ABLK, row, col0 + c8, oh);
         tc::st_row8_bf16(sDz, C::ABLK, row, col0 + c8, oz);
       }
+      Q_STAMP(32, 7); Q_STAMP(160, 7);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      Q_STAMP(32, 8); Q_STAMP(160, 8);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_rowsum<D>(tS2, aGlo, aS, C::ABLK, ct > 0);           // dU (per item)
@@ -335,6 +368,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       // ---- S3: d gamma_q -> dproj (my 16 frequencies: sin columns j, cos columns HD + j) ---------------------------
       tc::mbar_wait(bar_d, par);
       tc::tc_fence_after();
+      Q_STAMP(32, 9); Q_STAMP(160, 9);
       {
         float dsn[16], dcs[16];
         tc::tmem_ld16(tT + lane_off + 16 * cq, dsn);
@@ -358,9 +392,11 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           tc::st_row8_bf16(sGlo, C::ABLK, row, col, o);             // h1q's MMA was issued before the dgrad: it is complete
         }
       }
+      Q_STAMP(32, 10); Q_STAMP(160, 10);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      Q_STAMP(32, 11); Q_STAMP(160, 11);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_du(tDu, aGlo, aOmT);
@@ -368,18 +404,19 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       }
     }
     // ---- item flush --------------------------------------------------------------------------------------------------
-    if (cq == 0) {
-      row_backward(ntiles - 1, (it - 1) & 1, dw_prev);
-      atomicAdd(&s_dlam[lane], lam_acc0);
-      atomicAdd(&s_dlam[32 + lane], lam_acc1);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float sk = warp_sum(kap_acc[h]);
-        if (lane == 0) atomicAdd(&s_dkap[h], sk);
-      }
+    if (cq == 1 || cq == 2) {
+      row_backward(ntiles - 1, (it - 1) & 1, cq - 1);
+      atomicAdd(&s_dlam[(cq - 1) * 32 + lane], lam_acc);
     } else {
       tc::mbar_wait(bar_u, (it - 1) & 1);
       tc::tc_fence_after();
+      if (cq == 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float sk = warp_sum(kap_acc[h]);
+          if (lane == 0) atomicAdd(&s_dkap[h], sk);
+        }
+      }
     }
     if (cq == 0) {                                         // dU[h][j], j = my TMEM lane
       float d16[16];
