@@ -172,9 +172,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       }
     };
     const uint32_t it0 = it;                           // row-record slot of tile ct of this item: (it0 + ct) % 3
-    auto write_invariants = [&](int ct) {
-      float xi_r[8];
-      load_xi(ct, xi_r);
+    auto write_invariants = [&](int ct, const float* xi_r) {
       const Rec rec = pair_record(P, s_lam, xi_r, sigma);
       proj_write_u(sU, row, rec.u, P.I);
       float4* rx = reinterpret_cast<float4*>(s_rx + (((it0 + ct) % 3) * ROWS + row) * C::RX);
@@ -188,16 +186,16 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
     for (int h = 0; h < H; ++h) kap_acc[h] = 0.f;
     // du (tile ct) + du_v -> window backward -> dq -> my half of dLam / dsigma partial sums (lane l keeps column l).
     // The row's record comes from shared memory (written a tile earlier by the cq == 0 thread); part = 0: cq == 1, 1: cq == 2.
-    auto row_backward = [&](int ct, uint32_t par_u, int part) {
-      const bool valid = ct * ROWS + row < P.C;
-      float duv[8];
+    auto load_duv = [&](int ct, float* duv) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) duv[k] = 0.f;
-      if (valid) {
+      if (ct * ROWS + row < P.C) {
         const float4* src = reinterpret_cast<const float4*>(P.duv + (bz * P.C + ct * ROWS + row) * 8);
         float4 a = __ldg(src), c = __ldg(src + 1);
         duv[0] = a.x; duv[1] = a.y; duv[2] = a.z; duv[3] = a.w; duv[4] = c.x; duv[5] = c.y; duv[6] = c.z; duv[7] = c.w;
       }
+    };
+    auto row_backward = [&](int ct, uint32_t par_u, int part, const float* duv) {
       const float4* rx = reinterpret_cast<const float4*>(s_rx + (((it0 + ct) % 3) * ROWS + row) * C::RX);
       const float4 x0 = rx[0], x1 = rx[1], r0 = rx[2], r1 = rx[3];
       const float xi_r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -254,7 +252,14 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       lam_acc += warp_colsum32(vv, lane);
     };
 
-    if (cq == 0) write_invariants(0);
+    if (cq == 0) {
+      float xi0[8];
+      load_xi(0, xi0);
+      write_invariants(0, xi0);
+    }
+    float dsv_next[H];                                  // logit cotangents of the tile about to start (fetched a tile ahead)
+#pragma unroll
+    for (int h = 0; h < H; ++h) dsv_next[h] = row < P.C ? __ldg(P.ds + (bz * P.C + row) * H + h) : 0.f;
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == MMA_TID) {
@@ -270,7 +275,11 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       const int64_t pr = bz * P.C + c0 + row;
       float dsv[H];
 #pragma unroll
-      for (int h = 0; h < H; ++h) dsv[h] = valid ? __ldg(P.ds + pr * H + h) : 0.f;
+      for (int h = 0; h < H; ++h) dsv[h] = dsv_next[h];
+      // global operands of this tile's side work, requested before the RFF pass: one row record per thread role
+      float pre8[8];                                       // cq == 0: xi of tile ct + 1 ; cq == 1, 2: du_v of tile ct - 1
+      if (cq == 0) { if (ct + 1 < ntiles) load_xi(ct + 1, pre8); }
+      else if (cq <= 2) { if (ct > 0) load_duv(ct - 1, pre8); }
       Q_STAMP(32, 0); Q_STAMP(160, 0);
       if (it > 0) tc::mbar_wait(bar_u, (it - 1) & 1);     // every MMA of the previous tile is done with the operand tiles
       Q_STAMP(32, 1); Q_STAMP(160, 1);
@@ -310,9 +319,9 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
 #pragma unroll
         for (int h = 0; h < H; ++h) { kap_acc[h] += dsv[h]; dw += dsv[h]; }
         s_rx[(((it0 + ct) % 3) * ROWS + row) * C::RX + 16] = dw;
-        if (ct + 1 < ntiles) write_invariants(ct + 1);
+        if (ct + 1 < ntiles) write_invariants(ct + 1, pre8);
       } else if (cq <= 2 && ct > 0) {
-        row_backward(ct - 1, (it - 1) & 1, cq - 1);
+        row_backward(ct - 1, (it - 1) & 1, cq - 1, pre8);
       }
       // ---- E: h1q, dzq ---------------------------------------------------------------------------------------------
       float v[32];
@@ -349,6 +358,10 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         tc::st_row8_bf16(sDz, C::ABLK, row, col0 + c8, oz);
       }
       Q_STAMP(32, 7); Q_STAMP(160, 7);
+      if (ct + 1 < ntiles) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) dsv_next[h] = (c0 + ROWS + row < P.C) ? __ldg(P.ds + (pr + ROWS) * H + h) : 0.f;
+      }
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
@@ -405,7 +418,9 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
     }
     // ---- item flush --------------------------------------------------------------------------------------------------
     if (cq == 1 || cq == 2) {
-      row_backward(ntiles - 1, (it - 1) & 1, cq - 1);
+      float duv[8];
+      load_duv(ntiles - 1, duv);
+      row_backward(ntiles - 1, (it - 1) & 1, cq - 1, duv);
       atomicAdd(&s_dlam[(cq - 1) * 32 + lane], lam_acc);
     } else {
       tc::mbar_wait(bar_u, (it - 1) & 1);
