@@ -71,6 +71,14 @@ __device__ __forceinline__ void issue_du_v(uint32_t d_tmem, uint32_t a_addr, uin
   for (int kk = 0; kk < 4; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
 }
 
+// diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA 7, its first
+// item, tiles 4..7, for thread `who`
+#ifdef ENF_TRACE
+#define V_STAMP(slot) do { if (P.dbg && blockIdx.x == 7 && item == 7 && (tid == 32 || tid == 160) && ct >= 4 && ct < 8) P.dbg[2048 + (tid == 32 ? 0 : 128) + (ct - 4) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define V_STAMP(slot) do { } while (0)
+#endif
+
 template <int D>
 __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairTcBwdParams P) {
   using C = VCfg<D>;
@@ -157,8 +165,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
     const float sigma = P.sigma ? P.sigma[bz] : 1.f;
     __syncthreads();
 
-    auto write_invariants = [&](int ct) {
-      float xi_r[8];
+    auto load_xi = [&](int ct, float* xi_r) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) xi_r[k] = 0.f;
       if (ct * ROWS + row < P.C) {
@@ -166,6 +173,8 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         float4 a = __ldg(src), c = __ldg(src + 1);
         xi_r[0] = a.x; xi_r[1] = a.y; xi_r[2] = a.z; xi_r[3] = a.w; xi_r[4] = c.x; xi_r[5] = c.y; xi_r[6] = c.z; xi_r[7] = c.w;
       }
+    };
+    auto write_invariants = [&](const float* xi_r) {
       const Rec rec = pair_record(P, s_lam, xi_r, sigma);
       proj_write_u(sU, row, rec.u, P.I);
     };
@@ -186,7 +195,11 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       }
     };
 
-    if (cq == 0) write_invariants(0);
+    if (cq == 0) {
+      float xi0[8];
+      load_xi(0, xi0);
+      write_invariants(xi0);
+    }
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == MMA_TID) {
@@ -207,21 +220,23 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
 #pragma unroll
         for (int q = 0; q < 4; ++q) dthq[q] = valid ? __ldg(src + q * ROWS) : make_uint4(0u, 0u, 0u, 0u);
       }
-      if (it > 0 && cq != 0) {                             // every MMA of the previous tile is done with the operand tiles
-        tc::mbar_wait(bar_u, (it - 1) & 1);               // (the row threads wait inside store_du below)
+      V_STAMP(0);
+      if (it > 0) {                                        // every MMA of the previous tile is done with the operand tiles
+        tc::mbar_wait(bar_u, (it - 1) & 1);
         tc::tc_fence_after();
       }
-      if (cq == 0 && it > 0) {
-        if (ct > 0) store_du(ct - 1, (it - 1) & 1);
-        else { tc::mbar_wait(bar_u, (it - 1) & 1); tc::tc_fence_after(); }      // previous item's last tile was stored at its flush
-      }
+      if (cq == 1 && ct > 0) store_du(ct - 1, (it - 1) & 1);      // previous tile's du -> duv (the item's last tile: at its flush)
       // ---- S1: gamma_v hi / lo ---------------------------------------------------------------------------------
+      V_STAMP(1);
       tc::mbar_wait(bar_p, par);
       tc::tc_fence_after();
+      V_STAMP(2);
       rff_from_proj<D, true>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
+      V_STAMP(3);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      V_STAMP(4);
       if (tid == MMA_TID) {
         if (it == 0) tc::mbar_wait(bar_w, 0);
         tc::tc_fence_after();
@@ -231,11 +246,17 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         tc::mma_commit(bar_g1);
       }
       // next tile's invariants -> projection operand (overlaps the 3-term GEMM; tP was read by everyone before the barrier)
-      if (cq == 0 && ct + 1 < ntiles) write_invariants(ct + 1);
+      if (cq == 0 && ct + 1 < ntiles) {                    // (loading xi here, not a phase earlier: it would only be spilled across S1)
+        float xi_next[8];
+        load_xi(ct + 1, xi_next);
+        write_invariants(xi_next);
+      }
       // ---- E2: h1v, mask ---------------------------------------------------------------------------------------------
       float v[32];
+      V_STAMP(5);
       tc::mbar_wait(bar_g1, par);
       tc::tc_fence_after();
+      V_STAMP(6);
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
       uint32_t mask = 0;
@@ -247,14 +268,17 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          o[t] = fmaxf(v[c8 + t] + bv[t], 0.f);
-          mask |= (o[t] > 0.f ? 1u : 0u) << (c8 + t);
+          const float pre = v[c8 + t] + bv[t];
+          o[t] = fmaxf(pre, 0.f);
+          mask |= (pre > 0.f ? 1u : 0u) << (c8 + t);
         }
         tc::st_row8_bf16(sX, C::ABLK, row, col0 + c8, o);
       }
+      V_STAMP(7);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      V_STAMP(8);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_gemm<D>(tT, aX, aWp, C::ABLK, C::WBLK);
@@ -267,6 +291,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       // ---- E3: tpre -> g, g', that ; dtpre ------------------------------------------------------------------------
       tc::mbar_wait(bar_g2, par);
       tc::tc_fence_after();
+      V_STAMP(9);
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
       {
@@ -310,9 +335,11 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
           tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, o);
         }
       }
+      V_STAMP(10);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      V_STAMP(11);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_dgrad<D>(tT, aDt, aWp, C::ABLK, C::WBLK, 0);          // d h1v
@@ -324,16 +351,21 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       // ---- E4: dzv = d h1v [h1v > 0] ----------------------------------------------------------------------------------
       tc::mbar_wait(bar_g3, par);
       tc::tc_fence_after();
+      V_STAMP(12);
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+      V_STAMP(13);
       tc::mbar_wait(bar_g3b, par);                         // the wgrad has finished reading dtpre: its tile takes dzv
+      V_STAMP(14);
 #pragma unroll
       for (int c8 = 0; c8 < 32; c8 += 8) tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, v + c8);
+      V_STAMP(15);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      V_STAMP(16);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_dgrad<D>(tT, aDt, aW, C::ABLK, C::WBLK, 0);           // d gamma_v
@@ -344,6 +376,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       // ---- S3: d gamma_v -> dproj (my 16 frequencies: sin columns j, cos columns HD + j) ---------------------------
       tc::mbar_wait(bar_g4, par);
       tc::tc_fence_after();
+      V_STAMP(17);
       {
         float dsn[16], dcs[16];
         tc::tmem_ld16(tT + lane_off + 16 * cq, dsn);
@@ -367,9 +400,11 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
           tc::st_row8_bf16(sX, C::ABLK, row, col, o);               // h1v's wgrad completed before E4 stored (bar_g3b)
         }
       }
+      V_STAMP(18);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
+      V_STAMP(19);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_du_v(tDu, aX, aOmT);
@@ -377,7 +412,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       }
     }
     // ---- item flush: the last tile's du ----------------------------------------------------------------------------
-    if (cq == 0) store_du(ntiles - 1, (it - 1) & 1);
+    if (cq == 1) store_du(ntiles - 1, (it - 1) & 1);
   }
   // ---- CTA flush: shared-weight gradients ------------------------------------------------------------------------------
   if (it > 0) {

@@ -191,6 +191,37 @@ def test_tensor_core_path_against_oracle(case):
     assert all(v < TOL_BF16 for v in errs.values()), errs
 
 
+TC_EXTRA = [
+    # several 128-query tiles with a ragged last one, and more (field, latent) items than SMs: the persistent backward
+    # kernels walk > 1 item per CTA, kernel A swaps its TMEM regions over an odd number of tiles
+    ("tc_multi_tile", dict(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                           embedding_freq_multiplier=(0.05, 0.1)), 5, 300, 36, None),
+    # single head (H = 1 instantiations of every tcgen05 kernel), non-periodic window, two orientation-bearing poses
+    ("tc_one_head", dict(num_in=2, num_hidden=128, num_heads=1, num_out=2, latent_dim=8, invariant_type="ponita",
+                         embedding_freq_multiplier=(0.05, 0.05)), 2, 200, 9, None),
+    # spherical window (acos / exp path of the window backward in kernel C), 3 outputs
+    ("tc_sphere_window", dict(num_in=2, num_hidden=128, num_heads=2, num_out=3, latent_dim=32, invariant_type="latitude_periodic",
+                              embedding_freq_multiplier=(0.05, 0.2)), 2, 260, 18, (6, 3)),
+]
+
+
+@pytest.mark.parametrize("case", TC_EXTRA, ids=lambda c: c[0])
+def test_tensor_core_multi_tile_against_oracle(case):
+    """precision='bf16' beyond one query tile / one item per CTA; tolerance 2e-3 (BASELINE.json's bf16/tf32 bucket)."""
+    _, kw, B, C, Z, grid = case
+    cfg = R.EnfConfig(**kw)
+    params, x, p, a, sigma, d_out = make_case(cfg, B, C, Z, seed=5, polar_grid=grid)
+    out_ref, dth_ref, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="bf16")
+    errs = dict(out=rel_err(out, out_ref), dp=rel_err(dp, dp_ref), da=rel_err(da, da_ref),
+                ds=rel_err(ds, ds_ref) if cfg.use_gaussian_window else 0.0)
+    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
+    scale = max(float(v.abs().max()) for v in fr.values())
+    errs["dtheta"] = max(float((fg[k].double().cpu() - fr[k]).abs().max()) / scale for k in fr)
+    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < TOL_BF16 for v in errs.values()), errs
+
+
 def test_tensor_core_full_size_ns_subset():
     """BASELINE config 2 at full size through the tensor-core forward: random rows against the oracle."""
     cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
