@@ -63,6 +63,7 @@ INVARIANT_KINDS = {
     "polar_periodic": 5, "latitude_periodic": 6, "ball": 7, "ball_lat": 8,
 }
 PREC_FP32, PREC_BF16 = 0, 1
+FLAG_FORWARD_ONLY = 1
 
 EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_fwd",
            "enf_xattn_bwd", "enf_last_launch_count", "enf_last_error", "enf_debug_ws_offset", "enf_profile_enable",
@@ -71,7 +72,7 @@ EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_wo
 
 class EnfDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("B", "C", "Z", "d", "H", "L", "O", "Dx", "invariant_kind", "use_window", "precision", "reserved")]
+                ("B", "C", "Z", "d", "H", "L", "O", "Dx", "invariant_kind", "use_window", "precision", "flags")]
 
 
 class EnfWeights(ctypes.Structure):

@@ -71,12 +71,14 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
+  if (D->flags & ~ENF_FLAG_FORWARD_ONLY) return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
   if (rl) *rl = r;
   return ENF_OK;
 }
 
 Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Layout Y;
+  const bool train = !(D.flags & ENF_FLAG_FORWARD_ONLY);      // forward only: no backward state, no gradient buffers
   const size_t d = D.d, H = D.H, Hd = H * d, d2 = d * d;
   const size_t BZ = (size_t)D.B * D.Z, BC = (size_t)D.B * D.C;
   Y.add("A_q", d * Hd); Y.add("c_q", Hd); Y.add("Wp", d2); Y.add("bp", d); Y.add("W2g", d * 2 * Hd); Y.add("b2g", 2 * Hd);
@@ -84,15 +86,21 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("dP1", Hd * Hd); Y.add("db1", Hd); Y.add("q_w1T", d2); Y.add("v_w1T", d2); Y.add("WpT", d2);
   Y.add("lam", BZ * ENF_LAM_SIZE); Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
   Y.add("k", BZ * Hd); Y.add("v0", BZ * Hd); Y.add("U", BZ * Hd); Y.add("kappa", BZ * H);
-  Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd); Y.add("W3T", BZ * H * d2);
+  Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd);
+  {
+    // transposed W3 copies: only the fp32-FMA backward reads them
+    const bool tc_both = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H);
+    if (train && !tc_both) Y.add("W3T", BZ * H * d2);
+  }
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
-    Y.add("slog", BC * (size_t)D.Z * H); Y.add("dbg_fwd", 8192);
+    if (train) Y.add("slog", BC * (size_t)D.Z * H);
+    Y.add("dbg_fwd", 8192);
     // tf32 stage GEMMs: activated copies of the decode-MLP pre-activations (their A operands arrive by TMA) and the
     // low parts W - trunc_tf32(W) of the weights those GEMMs multiply by (3-term split product)
     Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
     Y.add("lo_W_A", Hd * Hd); Y.add("lo_fb_w2", Hd * Hd); Y.add("lo_m0_w", Hd * d); Y.add("lo_m1_w", d2); Y.add("lo_mx_w1", d2);
-    if (enf_pairs_bwd_tc_supported(D.d, D.H)) {
+    if (train && enf_pairs_bwd_tc_supported(D.d, D.H)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       const size_t Cpad = (size_t)((D.C + 127) / 128) * 128;      // kernels A / B work on whole 128-query tiles
       Y.add("dthat", BZ * Cpad * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
@@ -107,6 +115,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("nbar", BC * Hd); Y.add("lse", BC * H);
   Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
   Y.add("fo", BC * Hd); Y.add("o1p", BC * d); Y.add("o2p", BC * d);
+  if (!train) return Y;
   Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("s2", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
   Y.add("dbeff", BZ * Hd); Y.add("dk", BZ * Hd); Y.add("dv0", BZ * Hd); Y.add("dahat", BZ * d); Y.add("da0", BZ * d);
   // ---- accumulators, zeroed at the start of each bwd ----
@@ -277,6 +286,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
   if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
   const bool use_tc = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);   // other shapes: fp32 kernels
+  const bool train = !(D.flags & ENF_FLAG_FORWARD_ONLY);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
   Layout Y = make_layout(D, rl);
@@ -357,8 +367,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.q_omega = w->q_omega; tp.v_omega = w->v_omega; tp.q_b1 = w->q_b1; tp.v_b1 = w->v_b1; tp.bp = c.f("bp");
     tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
     tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
-    tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = c.f("slog");
-    tp.that_img = enf_pairs_bwd_tc_supported(D.d, D.H) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
+    tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = train ? c.f("slog") : nullptr;
+    tp.that_img = (train && enf_pairs_bwd_tc_supported(D.d, D.H)) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
     static const bool trace_fwd = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace_fwd ? reinterpret_cast<long long*>(c.f("dbg_fwd")) : nullptr;
     prof_mark(0, 0, st);
@@ -399,7 +409,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing fwd: ") + cudaGetErrorString(e));
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_fwd_state[workspace] = D;
+    if (train) g_fwd_state[workspace] = D; else g_fwd_state.erase(workspace);
   }
   g_launches = c.launches;
   return ENF_OK;
@@ -416,6 +426,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (!w || !x || !p || !a || !d_out || !dp || !da || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
   if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
   if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set");
+  if (D.flags & ENF_FLAG_FORWARD_ONLY) return fail(ENF_ERR_STATE, "a forward-only description (ENF_FLAG_FORWARD_ONLY) has no backward");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_fwd_state.find(workspace);

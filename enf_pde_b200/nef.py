@@ -101,6 +101,7 @@ class _XAttnFunction(torch.autograd.Function):
         ctx.save_for_backward(x, p, a, *([sigma] if sigma is not None else []), *leaves)
         ctx.launches_fwd = lib.enf_last_launch_count()
         _XAttnFunction.last_launches = [ctx.launches_fwd, 0]
+        ctx.forward_only = bool(desc_kw.get("flags", 0) & _lib.FLAG_FORWARD_ONLY)
         _XAttnFunction.last_ws = (desc_kw, ws)      # diagnostics (enf_debug_ws_offset views); the buffer lives until the next forward
         return out
 
@@ -233,8 +234,11 @@ class EquivariantCrossAttentionNeF:
             raise ValueError(f"gaussian_window_size must have shape {(B, Z, 1)}")
         desc = dict(B=B, C=C, Z=Z, d=self.num_hidden, H=self.num_heads, L=self.latent_dim, O=self.num_out, Dx=Dx,
                     invariant_kind=_lib.INVARIANT_KINDS[inv.invariant_type], use_window=int(self.use_gaussian_window),
-                    precision=self.precision, reserved=0)
+                    precision=self.precision, flags=0)
         leaves = params_to_leaves(variables)
+        # forward only (validation roll-outs, pde_trainer.py:389-405): nothing is kept for a backward
+        if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p, a, sigma, *leaves))):
+            desc["flags"] = _lib.FLAG_FORWARD_ONLY
         return _XAttnFunction.apply((desc, x_shared), x_arg, p, a, sigma, *leaves)
 
     __call__ = apply

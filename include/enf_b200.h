@@ -53,6 +53,14 @@ enum EnfPrecision {
   ENF_PREC_BF16 = 1    /* tcgen05 tensor cores, 16-bit operands, fp32 accumulate: <= 2e-3 bucket */
 };
 
+/* EnfDesc.flags */
+enum EnfFlags {
+  /* forward only: validation / visualisation roll-outs (apply_nef_jitted, pde_trainer.py:389-405;
+   * _base_pde_trainer.py:446-457,588-598).  Nothing is saved for a backward (no logits, no operand
+   * stash), the workspace is ~10x smaller, enf_xattn_bwd on such a workspace returns ENF_ERR_STATE. */
+  ENF_FLAG_FORWARD_ONLY = 1
+};
+
 enum EnfError {
   ENF_OK = 0,
   ENF_ERR_BAD_DESC = -1,        /* inconsistent / unsupported sizes                     */
@@ -78,7 +86,7 @@ typedef struct EnfDesc {
   int32_t invariant_kind;  /* EnfInvariantKind                                            */
   int32_t use_window;      /* use_gaussian_window                                         */
   int32_t precision;       /* EnfPrecision                                                */
-  int32_t reserved;
+  int32_t flags;           /* EnfFlags (0 = training: the workspace keeps the state enf_xattn_bwd needs) */
 } EnfDesc;
 
 /* The parameter leaves of nef.init(...)['params'] (Flax tree), as device pointers.

@@ -15,7 +15,7 @@ from helpers import rel_err
 def desc_for(cfg, B, C, Z, precision=0):
     return _lib.EnfDesc(B=B, C=C, Z=Z, d=cfg.num_hidden, H=cfg.num_heads, L=cfg.latent_dim, O=cfg.num_out, Dx=cfg.num_in,
                         invariant_kind=_lib.INVARIANT_KINDS[cfg.invariant_type], use_window=int(cfg.use_gaussian_window),
-                        precision=precision, reserved=0)
+                        precision=precision, flags=0)
 
 
 def ws_view(lib, desc, ws, name):

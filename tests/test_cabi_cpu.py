@@ -45,12 +45,22 @@ def test_invariant_dims_match_reference_classes():
 
 def test_bad_descriptions_are_rejected_without_a_gpu():
     lib = E.load_library()
-    ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, reserved=0)
+    ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, flags=0)
     assert lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**ok))) > 0
-    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7)):
+    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=2)):
         d = _lib.EnfDesc(**{**ok, **bad})
         assert lib.enf_xattn_workspace_bytes(ctypes.byref(d)) == 0, bad
         assert lib.enf_last_error() != b""
+
+
+def test_forward_only_workspace_is_smaller():
+    """ENF_FLAG_FORWARD_ONLY (validation roll-outs): no backward state in the workspace."""
+    lib = E.load_library()
+    for prec in (0, 1):
+        kw = dict(B=32, C=4096, Z=64, d=128, H=2, L=16, O=1, Dx=2, invariant_kind=3, use_window=1, precision=prec)
+        train = lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**kw, flags=0)))
+        infer = lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**kw, flags=_lib.FLAG_FORWARD_ONLY)))
+        assert 0 < infer < 0.6 * train, (prec, train, infer)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
@@ -65,7 +75,7 @@ def test_compute_fails_loudly_without_a_device():
     with pytest.raises(RuntimeError):
         nef.apply(params, x, p, a, s)
     lib = E.load_library()
-    d = _lib.EnfDesc(B=1, C=5, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, reserved=0)
+    d = _lib.EnfDesc(B=1, C=5, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, flags=0)
     w = _lib.EnfWeights(**{n: 16 for n in _lib.LEAVES})
     rc = lib.enf_xattn_fwd(ctypes.byref(d), ctypes.byref(w), 16, 10, 16, 16, 16, 16, 256, 1 << 40, None)
     assert rc == -6 and b"no CUDA device" in lib.enf_last_error()

@@ -222,6 +222,35 @@ def test_tensor_core_multi_tile_against_oracle(case):
     assert all(v < TOL_BF16 for v in errs.values()), errs
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_only_matches_training_forward(precision):
+    """torch.no_grad() -> ENF_FLAG_FORWARD_ONLY: same kernels, no backward state (SURVEY 8f-2: validation roll-outs);
+    bit-identical decoded field; the C ABI refuses a backward on such a description."""
+    import ctypes
+    from enf_pde_b200 import _lib
+    from enf_pde_b200.nef import _XAttnFunction
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1))
+    params, x, p, a, sigma, _ = make_case(cfg, 3, 200, 16, seed=9)
+    nef = _nef_for(cfg, precision)
+    P = _to_cuda(params)
+    f = lambda t: t.to("cuda", torch.float32)
+    pg = f(p).requires_grad_(True)
+    out_train = nef.apply(P, f(x), pg, f(a), f(sigma))
+    ws_train = _XAttnFunction.last_ws[1].numel()
+    assert _XAttnFunction.last_ws[0]["flags"] == 0
+    with torch.no_grad():
+        out_inf = nef.apply(P, f(x), f(p), f(a), f(sigma))
+    assert _XAttnFunction.last_ws[0]["flags"] == _lib.FLAG_FORWARD_ONLY
+    assert _XAttnFunction.last_ws[1].numel() < ws_train
+    assert torch.equal(out_inf, out_train.detach())
+    lib = _lib.load()
+    desc = _lib.EnfDesc(**_XAttnFunction.last_ws[0])
+    w = _lib.EnfWeights(**{n: 16 for n in _lib.LEAVES})
+    rc = lib.enf_xattn_bwd(ctypes.byref(desc), ctypes.byref(w), 16, 0, 16, 16, 16, 16, None, 16, 16, 16, 256, 1 << 40, None)
+    assert rc == -7, lib.enf_last_error()
+
+
 def test_tensor_core_full_size_ns_subset():
     """BASELINE config 2 at full size through the tensor-core forward: random rows against the oracle."""
     cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
