@@ -396,13 +396,15 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm((int)BC, d, Hd, enf_mat(c.f("fo_act"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
     o.bias = w->m1_b; o.gelu_out = c.f("o2_act"); o.b_lo = c.f("lo_m1_w");
     c.gemm((int)BC, d, d, enf_mat(c.f("o1_act"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
-    c.gemm((int)BC, O, d, enf_mat(c.f("o2_act"), d), enf_mat(w->m2_w, O), enf_mat(out, O), opt_bias(w->m2_b));
+    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2_act"), w->m2_w, w->m2_b, out, BC, d, O, 0);
+    else c.gemm((int)BC, O, d, enf_mat(c.f("o2_act"), d), enf_mat(w->m2_w, O), enf_mat(out, O), opt_bias(w->m2_b));
   } else {
     c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), opt_bias(w->fb_b2));
     EnfGemmOpts o; o.act_a = 1;
     o.bias = w->m0_b; c.gemm((int)BC, d, Hd, enf_mat(c.f("fo"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
     o.bias = w->m1_b; c.gemm((int)BC, d, d, enf_mat(c.f("o1p"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
-    o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o);
+    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2p"), w->m2_w, w->m2_b, out, BC, d, O, 1);
+    else { o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o); }
   }
   if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
   cudaError_t e = cudaGetLastError();
@@ -460,10 +462,15 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     const float* a_fo = tc_fwd ? c.f("fo_act") : c.f("fo");
     EnfGemmOpts o;
     o.tc = 1;
-    c.gemm(d, O, (int)BC, enf_mat(a_o2, 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
-    colsum(d_out, BC, O, G("m2_b"));
-    o.mul_gelu_grad = c.f("o2p");
-    c.gemm((int)BC, d, O, enf_mat(d_out, O), enf_mat(w->m2_w, 1, O), enf_mat(c.f("d_o2p"), d), o);
+    if (enf_thin_supported(d, O)) {
+      c.launches += enf_launch_thin_wgrad(st, a_o2, d_out, G("m2_w"), G("m2_b"), BC, d, O, wa.act_a);
+      c.launches += enf_launch_thin_dgrad(st, d_out, w->m2_w, c.f("o2p"), c.f("d_o2p"), BC, d, O);
+    } else {
+      c.gemm(d, O, (int)BC, enf_mat(a_o2, 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
+      colsum(d_out, BC, O, G("m2_b"));
+      o.mul_gelu_grad = c.f("o2p");
+      c.gemm((int)BC, d, O, enf_mat(d_out, O), enf_mat(w->m2_w, 1, O), enf_mat(c.f("d_o2p"), d), o);
+    }
     c.gemm(d, d, (int)BC, enf_mat(a_o1, 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
     colsum(c.f("d_o2p"), BC, d, G("m1_b"));
     o.mul_gelu_grad = c.f("o1p"); o.b_lo = LO("lo_m1_w");

@@ -108,6 +108,11 @@ int enf_launch_split_lo(cudaStream_t st, const EnfSplitList& l);
 // ---- small stage kernels (enf_stages.cu) -------------------------------------------------------
 int enf_launch_rowscale(cudaStream_t st, const float* W, const float* g, float* out, int rows, int cols);
 int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t ld, float* out, const float* mul, int64_t ld_mul);
+// decode MLP's last layer (d -> O, O <= 4): out = act(A) W + b ; dX = (dO W^T) gelu'(pre) ; dW += act(A)^T dO, db += colsum(dO)
+bool enf_thin_supported(int d, int O);
+int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a);
+int enf_launch_thin_dgrad(cudaStream_t st, const float* dO, const float* W, const float* pre, float* dX, int64_t M, int d, int O);
+int enf_launch_thin_wgrad(cudaStream_t st, const float* A, const float* dO, float* dW, float* db, int64_t M, int d, int O, int act_a);
 int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
                       float* out_core, float* out_affine, float* rstd, int gelu_in, int round_affine = 0);
 int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const float* rstd, const float* g,

@@ -1,7 +1,7 @@
 // Generic strided / batched / split-K fp32 GEMM used by the per-latent (L), per-weight (W) and
 // per-query tail (Q) stages.  These stages are a few percent of the work of the fused pair kernels;
 // this kernel favours generality (arbitrary strides => transposes and head-sliced views for free)
-// over peak throughput.  64x64x16 tiles, 256 threads, 4x4 register tile per thread, 4-stage cp.async pipeline
+// over peak throughput.  64x64x16 tiles, 256 threads, 4x4 register tile per thread, 8-stage cp.async pipeline
 // (most calls are tiny fold / unfold products whose time is global-load latency, not flops).
 #include <cstdlib>
 
@@ -24,7 +24,8 @@ struct GemmKArgs {
   float alpha;
 };
 
-constexpr int ST = 4;      // cp.async pipeline depth: the small fold / unfold products are latency bound, not flop bound
+constexpr int ST = 8;      // cp.async pipeline depth (K = 128 is entirely in flight at once): the small fold / unfold products are
+                           // latency bound, not flop bound.  8 stages of A and B tiles = 68 KB of dynamic shared memory
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -33,8 +34,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
-  __shared__ __align__(16) float As[ST][BK][BM + 4];
-  __shared__ __align__(16) float Bs[ST][BK][BN + 4];
+  extern __shared__ __align__(16) float gemm_smem[];
+  float (*As)[BK][BM + 4] = reinterpret_cast<float (*)[BK][BM + 4]>(gemm_smem);
+  float (*Bs)[BK][BN + 4] = reinterpret_cast<float (*)[BK][BN + 4]>(gemm_smem + ST * BK * (BM + 4));
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -159,6 +161,10 @@ int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C,
   if (splitk < 1) splitk = 1;
   g.splitk = splitk; g.kchunk = kchunk;
   dim3 grid(tiles_m, tiles_n, o.batch * splitk);
-  enf_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  constexpr size_t smem = (size_t)ST * BK * ((BM + 4) + (BN + 4)) * sizeof(float);
+  static const bool configured =
+      cudaFuncSetAttribute(enf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  if (!configured) return -1;
+  enf_gemm_kernel<<<grid, 256, smem, st>>>(g);
   return 1;
 }

@@ -503,6 +503,126 @@ int enf_launch_rowscale(cudaStream_t st, const float* W, const float* g, float* 
   return 1;
 }
 
+// ---- the decode MLP's last layer (d -> O, O <= 4): three memory-bound "thin" products -------------------------------------
+namespace {
+// out[m,o] = sum_k act(A[m,k]) W[k,o] + b[o]; one warp per row, float4 lanes over k
+template <int O>
+__global__ void __launch_bounds__(256) thin_out_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ b,
+                                                       float* __restrict__ out, int64_t M, int d, int act_a) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float acc[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[o] = 0.f;
+    for (int k = 4 * lane; k < d; k += 128) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(A + m * d + k));
+      float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (act_a) a[t] = enf_gelu(a[t]);
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[o] = fmaf(a[t], __ldg(W + (k + t) * O + o), acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) out[m * O + o] = acc[o] + b[o];
+    }
+  }
+}
+// dX[m,k] = (sum_o dO[m,o] W[k,o]) gelu'(pre[m,k]); one thread per 4 consecutive k
+template <int O>
+__global__ void __launch_bounds__(256) thin_dgrad_kernel(const float* __restrict__ dO, const float* __restrict__ W,
+                                                         const float* __restrict__ pre, float* __restrict__ dX, int64_t M, int d) {
+  const int64_t total = M * (d / 4);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / (d / 4);
+    const int k = (int)(t % (d / 4)) * 4;
+    float g[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) g[o] = __ldg(dO + m * O + o);
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pre + m * d + k));
+    const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < O; ++o) s = fmaf(g[o], __ldg(W + (k + q) * O + o), s);
+      r[q] = s * enf_gelu_grad(p[q]);
+    }
+    *reinterpret_cast<float4*>(dX + m * d + k) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+// dW[k,o] += sum_m act(A[m,k]) dO[m,o] ; db[o] += sum_m dO[m,o]; thread = column k, rows_per_block rows per block
+template <int O>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dO, float* __restrict__ dW,
+                                                         float* __restrict__ db, int64_t M, int d, int act_a, int64_t rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float acc[O], bs[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) { acc[o] = 0.f; bs[o] = 0.f; }
+#pragma unroll 4
+    for (int64_t m = r0; m < r1; ++m) {
+      float a = __ldg(A + m * d + k);
+      if (act_a) a = enf_gelu(a);
+#pragma unroll
+      for (int o = 0; o < O; ++o) { const float g = __ldg(dO + m * O + o); acc[o] = fmaf(a, g, acc[o]); bs[o] += g; }
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      atomicAdd(dW + (int64_t)k * O + o, acc[o]);
+      if (k == 0 && db) atomicAdd(db + o, bs[o]);
+    }
+  }
+}
+}  // namespace
+
+bool enf_thin_supported(int d, int O) { return O >= 1 && O <= 4 && d % 4 == 0; }
+int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a) {
+  int blocks = (int)((M + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (O) {
+    case 1: thin_out_kernel<1><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
+    case 2: thin_out_kernel<2><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
+    case 3: thin_out_kernel<3><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
+    case 4: thin_out_kernel<4><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
+    default: return -1;
+  }
+  return 1;
+}
+int enf_launch_thin_dgrad(cudaStream_t st, const float* dO, const float* W, const float* pre, float* dX, int64_t M, int d, int O) {
+  int64_t total = M * (d / 4);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (O) {
+    case 1: thin_dgrad_kernel<1><<<blocks, 256, 0, st>>>(dO, W, pre, dX, M, d); break;
+    case 2: thin_dgrad_kernel<2><<<blocks, 256, 0, st>>>(dO, W, pre, dX, M, d); break;
+    case 3: thin_dgrad_kernel<3><<<blocks, 256, 0, st>>>(dO, W, pre, dX, M, d); break;
+    case 4: thin_dgrad_kernel<4><<<blocks, 256, 0, st>>>(dO, W, pre, dX, M, d); break;
+    default: return -1;
+  }
+  return 1;
+}
+int enf_launch_thin_wgrad(cudaStream_t st, const float* A, const float* dO, float* dW, float* db, int64_t M, int d, int O, int act_a) {
+  int64_t rpb = (M + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 16) rpb = 16;
+  int blocks = (int)((M + rpb - 1) / rpb);
+  int threads = d < 256 ? ((d + 31) / 32) * 32 : 256;
+  switch (O) {
+    case 1: thin_wgrad_kernel<1><<<blocks, threads, 0, st>>>(A, dO, dW, db, M, d, act_a, rpb); break;
+    case 2: thin_wgrad_kernel<2><<<blocks, threads, 0, st>>>(A, dO, dW, db, M, d, act_a, rpb); break;
+    case 3: thin_wgrad_kernel<3><<<blocks, threads, 0, st>>>(A, dO, dW, db, M, d, act_a, rpb); break;
+    case 4: thin_wgrad_kernel<4><<<blocks, threads, 0, st>>>(A, dO, dW, db, M, d, act_a, rpb); break;
+    default: return -1;
+  }
+  return 1;
+}
+
 int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t ld, float* out, const float* mul,
                       int64_t ld_mul) {
   if (M <= 0) return 0;
