@@ -135,11 +135,13 @@ using tc::named_sync;
 #define A_STAMP(who, slot) do { } while (0)
 #endif
 
-template <int D, int H>
-__global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
+// SEP = true: a 17th warp issues (96 registers per thread: the register file is granted in units of 4 warps);
+// SEP = false: warp 0 issues between its own epilogue phases (it SYNCs on the named barriers, the others ARRIVE), 128 registers.
+template <int D, int H, bool SEP>
+__global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   using A = ACfg<D, H>;
-  constexpr int NTA = C::NT + 32;                     // epilogue threads + the issue warp
+  constexpr int NTA = C::NT + (SEP ? 32 : 0);         // epilogue threads (+ the issue warp)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW3 = base + A::OFF_W3;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool issuer = warp == 16;
+  const bool issuer = SEP && warp == 16;
   const int lq = warp & 3, cq = warp >> 2;
   const int row = lq * 32 + lane, col0 = cq * 32;
   const int64_t bz = blockIdx.x;
@@ -180,64 +182,65 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
   const uint32_t my_t = lane_off + col0;
   const uint32_t aW3 = tc::smem_u32(sW3), aT = tc::smem_u32(sT), aDm = tc::smem_u32(sDm);
 
+  // ---- what the issuing lane does at the three issue points of a tile ------------------------------------------------------
+  auto issue_prologue = [&]() {
+    tc::mbar_expect_tx(bar_w, H * C::WIMG);
+    for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);
+    tc::mbar_expect_tx(&bar_t[0], C::ATILE);
+    tc::bulk_g2s(sT, timg, C::ATILE, &bar_t[0]);
+    tc::mbar_wait(bar_w, 0);
+    tc::mbar_wait(&bar_t[0], 0);
+    tc::tc_fence_after();
+    issue_gemm<D>(tm, aT, aW3, C::ABLK, C::WBLK);               // m_0 of tile 0 -> region 0
+    tc::mma_commit(&bar_g4[0]);
+  };
+  auto issue_top = [&](int ct) {                      // tS (= the previous tile's dgrad region) has been read by every epilogue thread
+    const int e = ct & 1;
+    tc::tc_fence_after();
+    if (H > 1) {
+      issue_gemm<D>(tm + (e ^ 1) * D, aT + e * C::ATILE, aW3 + C::WIMG, C::ABLK, C::WBLK);
+      tc::mma_commit(&bar_g4[1]);
+    }
+    if (ct + 1 < ntiles) {                            // next that tile -> the other buffer, once the previous tile's wgrad has read it
+      if (ct > 0) tc::mbar_wait(bar_gb, (ct - 1) & 1);
+      tc::mbar_expect_tx(&bar_t[e ^ 1], C::ATILE);
+      tc::bulk_g2s(sT + (e ^ 1) * C::ATILE, timg + (size_t)(ct + 1) * C::ATILE, C::ATILE, &bar_t[e ^ 1]);
+    }
+  };
+  auto issue_head = [&](int ct, int h) {              // dm_h is in shared memory
+    const int e = ct & 1;
+    const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
+    const uint32_t aTc = aT + e * C::ATILE;
+    tc::tc_fence_after();
+    const uint32_t aDh = aDm + h * C::ATILE, aWh = aW3 + h * C::WIMG;
+    if (h + 1 < H) {
+      issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
+      issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
+    } else {
+      issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
+      tc::mma_commit(bar_d);
+      issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
+      tc::mma_commit(bar_gb);
+      if (ct + 1 < ntiles) {                          // tS is consumed: the next tile's first G4 goes there now
+        tc::mbar_wait(&bar_t[e ^ 1], ((ct + 1) >> 1) & 1);
+        tc::tc_fence_after();
+        issue_gemm<D>(tS, aT + (e ^ 1) * C::ATILE, aW3, C::ABLK, C::WBLK);
+        tc::mma_commit(&bar_g4[0]);
+      }
+    }
+  };
+
   if (issuer) {
     // ================================ issue warp =================================================================
     const bool lead = tc::elect_one();
-    if (lead) {
-      tc::mbar_expect_tx(bar_w, H * C::WIMG);
-      for (int h = 0; h < H; ++h) tc::bulk_g2s(sW3 + h * C::WIMG, P.img_W3 + (bz * H + h) * C::WIMG, C::WIMG, bar_w);
-      tc::mbar_expect_tx(&bar_t[0], C::ATILE);
-      tc::bulk_g2s(sT, timg, C::ATILE, &bar_t[0]);
-      tc::mbar_wait(bar_w, 0);
-      tc::mbar_wait(&bar_t[0], 0);
-      tc::tc_fence_after();
-      issue_gemm<D>(tm, aT, aW3, C::ABLK, C::WBLK);               // m_0 of tile 0 -> region 0
-      tc::mma_commit(&bar_g4[0]);
-    }
+    if (lead) issue_prologue();
     for (int ct = 0; ct < ntiles; ++ct) {
-      const int e = ct & 1;
-      const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
-      const uint32_t aTc = aT + e * C::ATILE;
-      A_STAMP(512, 0);
-      if (ct > 0) named_sync(kABarDth, NTA);          // tS (= the previous tile's dgrad region) has been read by every epilogue thread
-      A_STAMP(512, 1);
-      if (lead) {
-        tc::tc_fence_after();
-        if (H > 1) {
-          issue_gemm<D>(tS, aTc, aW3 + C::WIMG, C::ABLK, C::WBLK);
-          tc::mma_commit(&bar_g4[1]);
-        }
-        if (ct + 1 < ntiles) {                        // next that tile -> the other buffer, once the previous tile's wgrad has read it
-          if (ct > 0) tc::mbar_wait(bar_gb, (ct - 1) & 1);
-          tc::mbar_expect_tx(&bar_t[e ^ 1], C::ATILE);
-          tc::bulk_g2s(sT + (e ^ 1) * C::ATILE, timg + (size_t)(ct + 1) * C::ATILE, C::ATILE, &bar_t[e ^ 1]);
-        }
-      }
+      if (ct > 0) named_sync(kABarDth, NTA);
+      if (lead) issue_top(ct);
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        A_STAMP(512, 2 + 4 * h);
-        named_sync(kABarHead + h, NTA);               // dm_h is in shared memory
-        A_STAMP(512, 3 + 4 * h);
-        if (lead) {
-          tc::tc_fence_after();
-          const uint32_t aDh = aDm + h * C::ATILE, aWh = aW3 + h * C::WIMG;
-          if (h + 1 < H) {
-            issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
-            issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
-          } else {
-            issue_dgrad<D>(tF, aDh, aWh, C::ABLK, C::WBLK, h > 0);
-            tc::mma_commit(bar_d);
-            issue_wgrad<D>(tW3 + h * D, aTc, aDh, C::ABLK, ct > 0);
-            tc::mma_commit(bar_gb);
-            if (ct + 1 < ntiles) {                    // tS is consumed: the next tile's first G4 goes there now
-              tc::mbar_wait(&bar_t[e ^ 1], ((ct + 1) >> 1) & 1);
-              tc::tc_fence_after();
-              issue_gemm<D>(tS, aT + (e ^ 1) * C::ATILE, aW3, C::ABLK, C::WBLK);
-              tc::mma_commit(&bar_g4[0]);
-            }
-          }
-        }
-        A_STAMP(512, 4 + 4 * h);
+        named_sync(kABarHead + h, NTA);
+        if (lead) issue_head(ct, h);
         __syncwarp();
       }
     }
@@ -255,6 +258,10 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
         tc::cp_async<4 * H>(dst + 2 * ROWS * H, P.Dg + q * H);
       }
     };
+    if (!SEP && warp == 0) {
+      if (tc::elect_one()) issue_prologue();
+      __syncwarp();
+    }
     prefetch_rows(0);
     uint4 dnq[4];                                      // my 32 columns of the scaled fp16 cotangent of nbar, (tile, head) about to be processed
     auto load_dnb = [&](int ct, int h) {
@@ -270,6 +277,11 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
       const uint32_t tF = tm + e * D, tS = tm + (e ^ 1) * D;
       const int c0 = ct * ROWS;
       const bool valid = c0 + row < P.C;
+      if (!SEP && warp == 0) {                         // warp 0 doubles as the issuer
+        if (ct > 0) named_sync(kABarDth, NTA);
+        if (tc::elect_one()) issue_top(ct);
+        __syncwarp();
+      }
       A_STAMP(32, 0);
       tc::cp_async_wait_all();                         // this tile's row scalars (issued a tile ago by the cq == 0 thread of the row);
                                                        // the row's other threads read them after the row_exchange barrier below
@@ -347,7 +359,13 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
         tc::fence_proxy_async();
         A_STAMP(32, 22 + 3 * h);
         tc::tc_fence_before();
-        named_arrive(kABarHead + h, NTA);              // the issue warp takes it from here
+        if (!SEP && warp == 0) {
+          named_sync(kABarHead + h, NTA);
+          if (tc::elect_one()) issue_head(ct, h);
+          __syncwarp();
+        } else {
+          named_arrive(kABarHead + h, NTA);            // the issuer takes it from here
+        }
         A_STAMP(32, 6 + 8 * h);
         // fetch the cotangent rows of the next (tile, head) now, a whole phase ahead of their use
         if (h + 1 < H) load_dnb(ct, h + 1);
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + 32, 1) pairs_bwd_tc_a_kerne
       tc::tmem_ld_wait();
       A_STAMP(32, 19);
       tc::tc_fence_before();
-      if (ct + 1 < ntiles) named_arrive(kABarDth, NTA);     // tF may be overwritten by the next tile's second G4
+      if (ct + 1 < ntiles && (SEP || warp != 0)) named_arrive(kABarDth, NTA);     // tF may be overwritten by the next tile's second G4
       {                                                // chunked order: a warp stores 512 contiguous bytes per instruction
         uint4* dst = reinterpret_cast<uint4*>(P.dthat) + ((bz * ntiles + ct) * C::NQ + cq) * 4 * ROWS + row;
 #pragma unroll
@@ -416,9 +434,10 @@ int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
   if (cudaMemsetAsync(p.Dg, 0, (size_t)p.B * p.C * H * sizeof(float), st) != cudaSuccess) return -1;
   bwd_prep_pack_kernel<D><<<148 * 8, 256, 0, st>>>(p.dnbar, p.nbar, p.B, p.C, H, p.gmax, p.dnb16, p.Dg);
   size_t smem_a = ACfg<D, H>::SMEM_BYTES;
-  if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
+  constexpr bool kSepIssueWarp = false;
+  if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H, kSepIssueWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)(p.B * p.Z);
-  pairs_bwd_tc_a_kernel<D, H><<<grid, C::NT + 32, smem_a, st>>>(p);
+  pairs_bwd_tc_a_kernel<D, H, kSepIssueWarp><<<grid, C::NT + (kSepIssueWarp ? 32 : 0), smem_a, st>>>(p);
   if (enf_launch_pairs_bwd_tc_v(st, D, p) < 0) return -1;
   if (enf_launch_pairs_bwd_tc_q(st, D, H, p) < 0) return -1;
   return 5;
