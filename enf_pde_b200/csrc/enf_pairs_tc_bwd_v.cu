@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       V_STAMP(6);
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
-      uint32_t mask = 0;
+      uint32_t neg = 0;                                    // bit j: pre-activation j is negative (sign bits, two integer ops per element)
 #pragma unroll
       for (int c8 = 0; c8 < 32; c8 += 8) {
         float o[8];
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         for (int t = 0; t < 8; ++t) {
           const float pre = v[c8 + t] + bv[t];
           o[t] = fmaxf(pre, 0.f);
-          mask |= (pre > 0.f ? 1u : 0u) << (c8 + t);
+          neg |= (__float_as_uint(pre) & 0x80000000u) >> (31 - (c8 + t));
         }
         tc::st_row8_bf16(sX, C::ABLK, row, col0 + c8, o);
       }
@@ -298,22 +298,24 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         // one pass, one exchange: with g = gelu(tpre), that = (g - mu) rstd the LayerNorm backward needs
         //   sum_j dth_j   and   sum_j dth_j that_j = rstd (sum dth g - mu sum dth)
         float dg[32];
+        uint32_t gh[16];                                   // g packed to fp16 once the row sums have seen it in fp32 (16 registers, not 32)
         float st[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(s_bias + D + col0 + j4);
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
           const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[j4 >> 3]) + ((j4 & 4) >> 1);     // dthat[j4 .. j4 + 3], still packed
           const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
           const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+          float g[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            float g;
-            gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
-            v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
-            st[2] = fmaf(dv[t], g, st[2]); st[3] += dv[t];
+            gelu_fast_both(v[j4 + t] + bv[t], g[t], dg[j4 + t]);
+            st[0] += g[t]; st[1] = fmaf(g[t], g[t], st[1]);
+            st[2] = fmaf(dv[t], g[t], st[2]); st[3] += dv[t];
           }
+          gh[j4 >> 1] = tc::pack_bf16(g[0], g[1]);
+          gh[(j4 >> 1) + 1] = tc::pack_bf16(g[2], g[3]);
         }
         xw = 0;
         row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
@@ -325,12 +327,13 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
 #pragma unroll
         for (int c8 = 0; c8 < 32; c8 += 8) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[c8 >> 3]);
+          const __half2* g2 = reinterpret_cast<const __half2*>(&gh[c8 >> 1]);
           float o[8];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 dv = __half22float2(h2[t]);
-            o[2 * t] = fmaf(-v[c8 + 2 * t], kb, fmaf(rstd, dv.x, kc)) * dg[c8 + 2 * t];
-            o[2 * t + 1] = fmaf(-v[c8 + 2 * t + 1], kb, fmaf(rstd, dv.y, kc)) * dg[c8 + 2 * t + 1];
+            const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
+            o[2 * t] = fmaf(-gv.x, kb, fmaf(rstd, dv.x, kc)) * dg[c8 + 2 * t];
+            o[2 * t + 1] = fmaf(-gv.y, kb, fmaf(rstd, dv.y, kc)) * dg[c8 + 2 * t + 1];
           }
           tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, o);
         }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       tc::tmem_ld32(tT + my_t, v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+      for (int j = 0; j < 32; ++j) v[j] = ((neg >> j) & 1u) ? 0.f : v[j];
       V_STAMP(13);
       tc::mbar_wait(bar_g3b, par);                         // the wgrad has finished reading dtpre: its tile takes dzv
       V_STAMP(14);
