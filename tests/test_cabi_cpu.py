@@ -53,6 +53,18 @@ def test_bad_descriptions_are_rejected_without_a_gpu():
         assert lib.enf_last_error() != b""
 
 
+def test_jax_binding_module_is_importable_and_refuses_without_jax():
+    """the jax.ffi glue is shipped as source; without JAX it must import and fail with a clear message, not crash."""
+    import enf_pde_b200.jax_binding as J
+    if J.HAVE_JAX:
+        pytest.skip("JAX present: the binding needs the shim library, built separately")
+    with pytest.raises(ImportError, match="jax"):
+        J.make_enf_apply(128, 2, 1, 16, "rel_pos_periodic", 2)
+    src = open(os.path.join(os.path.dirname(J.__file__), "csrc", "enf_xla_ffi.cc")).read()
+    for sym in ("EnfXattnFwd", "EnfXattnBwd", "enf_xattn_fwd(", "enf_xattn_bwd(", "XLA_FFI_DEFINE_HANDLER_SYMBOL"):
+        assert sym in src
+
+
 def test_forward_only_workspace_is_smaller():
     """ENF_FLAG_FORWARD_ONLY (validation roll-outs): no backward state in the workspace."""
     lib = E.load_library()
