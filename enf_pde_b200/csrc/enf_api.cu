@@ -452,6 +452,9 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     return fail(ENF_ERR_CUDA, "memset of accumulators failed");
 
   // ---- Q backward: decode MLP, block FFN, folded (mixer Dense_1 . out_proj . FFN Dense_0) ---------------------
+  // dW == NULL (latents-only backward: Meta-SGD inner loop, ODE phase): the weight-gradient products of the per-query tail
+  // and of the latent stage are skipped, only the chain towards dp / da / dsigma is evaluated
+  const bool wg = dW != nullptr;
   auto LO = [&](const char* name) { return tc_fwd ? c.f(name) : (const float*)nullptr; };
   {
     // wgrad A operands: gelu of the stored pre-activation (fp32 mode: applied on load; tensor-core mode: the
@@ -463,31 +466,41 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     EnfGemmOpts o;
     o.tc = 1;
     if (enf_thin_supported(d, O)) {
-      c.launches += enf_launch_thin_wgrad(st, a_o2, d_out, G("m2_w"), G("m2_b"), BC, d, O, wa.act_a);
+      if (wg) c.launches += enf_launch_thin_wgrad(st, a_o2, d_out, G("m2_w"), G("m2_b"), BC, d, O, wa.act_a);
       c.launches += enf_launch_thin_dgrad(st, d_out, w->m2_w, c.f("o2p"), c.f("d_o2p"), BC, d, O);
     } else {
-      c.gemm(d, O, (int)BC, enf_mat(a_o2, 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
-      colsum(d_out, BC, O, G("m2_b"));
+      if (wg) {
+        c.gemm(d, O, (int)BC, enf_mat(a_o2, 1, d), enf_mat(d_out, O), enf_mat(G("m2_w"), O), wa);
+        colsum(d_out, BC, O, G("m2_b"));
+      }
       o.mul_gelu_grad = c.f("o2p");
       c.gemm((int)BC, d, O, enf_mat(d_out, O), enf_mat(w->m2_w, 1, O), enf_mat(c.f("d_o2p"), d), o);
     }
-    c.gemm(d, d, (int)BC, enf_mat(a_o1, 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
-    colsum(c.f("d_o2p"), BC, d, G("m1_b"));
+    if (wg) {
+      c.gemm(d, d, (int)BC, enf_mat(a_o1, 1, d), enf_mat(c.f("d_o2p"), d), enf_mat(G("m1_w"), d), wa);
+      colsum(c.f("d_o2p"), BC, d, G("m1_b"));
+    }
     o.mul_gelu_grad = c.f("o1p"); o.b_lo = LO("lo_m1_w");
     c.gemm((int)BC, d, d, enf_mat(c.f("d_o2p"), d), enf_mat(w->m1_w, 1, d), enf_mat(c.f("d_o1p"), d), o);
-    c.gemm(Hd, d, (int)BC, enf_mat(a_fo, 1, Hd), enf_mat(c.f("d_o1p"), d), enf_mat(G("m0_w"), d), wa);
-    colsum(c.f("d_o1p"), BC, d, G("m0_b"));
+    if (wg) {
+      c.gemm(Hd, d, (int)BC, enf_mat(a_fo, 1, Hd), enf_mat(c.f("d_o1p"), d), enf_mat(G("m0_w"), d), wa);
+      colsum(c.f("d_o1p"), BC, d, G("m0_b"));
+    }
     o.mul_gelu_grad = c.f("fo"); o.b_lo = LO("lo_m0_w");
     c.gemm((int)BC, Hd, d, enf_mat(c.f("d_o1p"), d), enf_mat(w->m0_w, 1, d), enf_mat(c.f("s0"), Hd), o);      // dfo
   }
-  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("e3"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("fb_w2"), Hd), opt_acc_big());
-  colsum(c.f("s0"), BC, Hd, G("fb_b2"));
+  if (wg) {
+    c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("e3"), 1, Hd), enf_mat(c.f("s0"), Hd), enf_mat(G("fb_w2"), Hd), opt_acc_big());
+    colsum(c.f("s0"), BC, Hd, G("fb_b2"));
+  }
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s0"), Hd), enf_mat(w->fb_w2, 1, Hd), enf_mat(c.f("s1"), Hd),
          with_lo(EnfGemmOpts(), LO("lo_fb_w2")));                                                               // de3
   c.launches += enf_launch_ln_bwd(st, c.f("s1"), c.f("e3c"), c.f("erstd"), w->fb_g, c.f("e1"), BC, Hd, c.f("s1"),
-                                  G("fb_g"), G("fb_beta"), 1, 0, tc_fwd ? 1 : 0);                                 // de1 (in place)
-  c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("nbar"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(c.f("gf_W_A"), Hd), opt_acc_big());
-  colsum(c.f("s1"), BC, Hd, c.f("gf_b_A"));
+                                  wg ? G("fb_g") : nullptr, wg ? G("fb_beta") : nullptr, 1, 0, tc_fwd ? 1 : 0);   // de1 (in place)
+  if (wg) {
+    c.gemm(Hd, Hd, (int)BC, enf_mat(c.f("nbar"), 1, Hd), enf_mat(c.f("s1"), Hd), enf_mat(c.f("gf_W_A"), Hd), opt_acc_big());
+    colsum(c.f("s1"), BC, Hd, c.f("gf_b_A"));
+  }
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(c.f("W_A"), 1, Hd), enf_mat(c.f("s0"), Hd),
          with_lo(EnfGemmOpts(), LO("lo_W_A")));                                                                  // dnbar
 
@@ -540,9 +553,11 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
 
   // ---- L backward ----------------------------------------------------------------------------------------
   if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
-  c.gemm(d, d, (int)(BZ * H * d), enf_mat(c.f("Weff"), 1, d), enf_mat(c.f("g_W3"), d), enf_mat(G("mx_w1"), d), opt_acc_big());
-  c.gemm(d, d, (int)(BZ * H), enf_mat(c.f("beff"), 1, d), enf_mat(c.f("g_b3"), d), enf_mat(G("mx_w1"), d), opt_acc());
-  colsum(c.f("g_b3"), BZ * H, d, G("mx_b1"));
+  if (wg) {
+    c.gemm(d, d, (int)(BZ * H * d), enf_mat(c.f("Weff"), 1, d), enf_mat(c.f("g_W3"), d), enf_mat(G("mx_w1"), d), opt_acc_big());
+    c.gemm(d, d, (int)(BZ * H), enf_mat(c.f("beff"), 1, d), enf_mat(c.f("g_b3"), d), enf_mat(G("mx_w1"), d), opt_acc());
+    colsum(c.f("g_b3"), BZ * H, d, G("mx_b1"));
+  }
   float* dWeff = c.f("W3");       // W3 is dead after the pair backward
   c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("g_W3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(dWeff, d),
          with_lo(EnfGemmOpts(), LO("lo_mx_w1")));
@@ -555,20 +570,26 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm((int)BZ, d, d, enf_mat(c.f("g_U"), Hd, 1, d), enf_mat(c.f("A_q"), Hd, 1, d), enf_mat(c.f("dk"), Hd, 1, d), o);
     EnfGemmOpts oa = opt_acc(); oa.batch = H;
     c.gemm((int)BZ, d, 1, enf_mat(c.f("g_kappa"), H, 1, 1), enf_mat(c.f("c_q"), 0, 1, d), enf_mat(c.f("dk"), Hd, 1, d), oa);
-    // dA_q[i,h*d+j] = sum_bz dU[bz,h,i] k[bz,h,j] ; dc_q[h*d+j] = sum_bz dkappa[bz,h] k[bz,h,j]
-    c.gemm(d, d, (int)BZ, enf_mat(c.f("g_U"), 1, Hd, d), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_A_q"), Hd, 1, d), oa);
-    c.gemm(1, d, (int)BZ, enf_mat(c.f("g_kappa"), 0, H, 1), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_c_q"), 0, 1, d), oa);
+    if (wg) {
+      // dA_q[i,h*d+j] = sum_bz dU[bz,h,i] k[bz,h,j] ; dc_q[h*d+j] = sum_bz dkappa[bz,h] k[bz,h,j]
+      c.gemm(d, d, (int)BZ, enf_mat(c.f("g_U"), 1, Hd, d), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_A_q"), Hd, 1, d), oa);
+      c.gemm(1, d, (int)BZ, enf_mat(c.f("g_kappa"), 0, H, 1), enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("gf_c_q"), 0, 1, d), oa);
+    }
   }
-  c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dk"), Hd), enf_mat(G("wk"), Hd), opt_acc());
-  colsum(c.f("dk"), BZ, Hd, G("bk"));
-  c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dv0"), Hd), enf_mat(G("wv"), Hd), opt_acc());
-  colsum(c.f("dv0"), BZ, Hd, G("bv"));
+  if (wg) {
+    c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dk"), Hd), enf_mat(G("wk"), Hd), opt_acc());
+    colsum(c.f("dk"), BZ, Hd, G("bk"));
+    c.gemm(d, Hd, (int)BZ, enf_mat(c.f("ahat"), 1, d), enf_mat(c.f("dv0"), Hd), enf_mat(G("wv"), Hd), opt_acc());
+    colsum(c.f("dv0"), BZ, Hd, G("bv"));
+  }
   c.gemm((int)BZ, d, Hd, enf_mat(c.f("dk"), Hd), enf_mat(w->wk, 1, Hd), enf_mat(c.f("dahat"), d));
   c.gemm((int)BZ, d, Hd, enf_mat(c.f("dv0"), Hd), enf_mat(w->wv, 1, Hd), enf_mat(c.f("dahat"), d), opt_acc());
   c.launches += enf_launch_ln_bwd(st, c.f("dahat"), c.f("acore"), c.f("arstd"), w->ln_attn_g, nullptr, BZ, d, c.f("da0"),
-                                  G("ln_attn_g"), G("ln_attn_b"), 0);
-  c.gemm(L, d, (int)BZ, enf_mat(a, 1, L), enf_mat(c.f("da0"), d), enf_mat(G("stem_w"), d), opt_acc());
-  colsum(c.f("da0"), BZ, d, G("stem_b"));
+                                  wg ? G("ln_attn_g") : nullptr, wg ? G("ln_attn_b") : nullptr, 0);
+  if (wg) {
+    c.gemm(L, d, (int)BZ, enf_mat(a, 1, L), enf_mat(c.f("da0"), d), enf_mat(G("stem_w"), d), opt_acc());
+    colsum(c.f("da0"), BZ, d, G("stem_b"));
+  }
   c.gemm((int)BZ, L, d, enf_mat(c.f("da0"), d), enf_mat(w->stem_w, 1, d), enf_mat(da, L));
   c.launches += enf_launch_latent_record_bwd(st, D, p, c.f("g_lam"), dp);
   if (dsigma) {

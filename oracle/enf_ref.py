@@ -455,6 +455,36 @@ def tree_unflatten(flat):
     return out
 
 
+def inner_loop(cfg: EnfConfig, params, coords, img, p, a, sigma, lrs, num_inner_steps, masks, optimize_gaussian_window=False,
+               n_pos=None):
+    """Restatement of PDETrainer.inner_loop (experiments/fitting/trainers/pde_trainer.py:122-235) with explicit masks:
+    per step loss = mean((nef(coords[mask]) - img[:, mask])^2) (:175-185), grads w.r.t. the per-field latents times the
+    batch size (:207), window gradient zeroed unless optimize_gaussian_window (:210-212), update -lr[key] * grad
+    (:215-218); returns (loss on the last mask, adapted (p, a, sigma)).  `lrs`: dict p_pos, p_ori, a (L,), gaussian_window.
+    Values only (the second-order outer gradient of :255 is not restated)."""
+    B = img.shape[0]
+    n_pos = p.shape[-1] if n_pos is None else n_pos
+    lr_p = torch.empty(p.shape[-1], dtype=p.dtype)
+    lr_p[:n_pos] = float(lrs["p_pos"])
+    if p.shape[-1] > n_pos:
+        lr_p[n_pos:] = float(lrs["p_ori"])
+    lr_a = torch.as_tensor(lrs["a"], dtype=p.dtype).reshape(1, 1, -1)
+    p, a, sigma = p.clone(), a.clone(), sigma.clone()
+    for step in range(num_inner_steps):
+        m = masks[step]
+        pp, aa, ss = p.clone().requires_grad_(True), a.clone().requires_grad_(True), sigma.clone().requires_grad_(True)
+        out = nef_apply(cfg, params, coords[m][None].expand(B, -1, -1), pp, aa, ss)
+        loss = ((out - img[:, m]) ** 2).mean()
+        gp, ga, gs = torch.autograd.grad(loss, (pp, aa, ss), allow_unused=True)
+        p = p - lr_p * gp * B
+        a = a - lr_a * ga * B
+        if optimize_gaussian_window and gs is not None:
+            sigma = sigma - float(lrs["gaussian_window"]) * gs * B
+    m = masks[num_inner_steps]
+    out = nef_apply(cfg, params, coords[m][None].expand(B, -1, -1), p, a, sigma)
+    return ((out - img[:, m]) ** 2).mean(), (p, a, sigma)
+
+
 def fwd_bwd(cfg: EnfConfig, params, x, p, a, sigma, d_out):
     """Forward + reverse pass with cotangent d_out.  Returns out and grads wrt (params, p, a, sigma)."""
     params = tree_map(lambda t: t.detach().clone().requires_grad_(True), params)

@@ -251,6 +251,38 @@ def test_forward_only_matches_training_forward(precision):
     assert rc == -7, lib.enf_last_error()
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 4e-3)])
+def test_first_order_inner_loop_against_oracle(precision, tol):
+    """enf_pde_b200.inner_loop (first-order part) vs the oracle's restatement of PDETrainer.inner_loop
+    (pde_trainer.py:122-235): 3 Meta-SGD steps on per-step query subsets, per-key learning rates, gradients x B, the
+    latents-only backward of the C ABI (dW = NULL).  Tolerances: twice the single-call buckets (errors compound over steps)."""
+    import enf_pde_b200 as E
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="ponita",
+                      embedding_freq_multiplier=(0.05, 0.05))
+    B, C, Z, K = 3, 256, 9, 3
+    params, _, p, a, sigma, _ = make_case(cfg, B, 8, Z, seed=13)
+    coords = R.make_coords(cfg, (16, 16)).double()
+    g = torch.Generator().manual_seed(17)
+    img = torch.randn(B, C, cfg.num_out, generator=g, dtype=torch.float64)
+    masks = [torch.randperm(C, generator=g)[:200] for _ in range(K + 1)]
+    lrs = {"p_pos": torch.tensor([0.5]), "p_ori": torch.tensor([0.5]), "a": torch.full((cfg.latent_dim,), 2.0),
+           "gaussian_window": torch.tensor([0.1])}
+    for opt_w in (False, True):
+        loss_ref, (p_ref, a_ref, s_ref) = R.inner_loop(cfg, params, coords, img, p, a, sigma, lrs, K, masks,
+                                                       optimize_gaussian_window=opt_w, n_pos=2)
+        nef = _nef_for(cfg, precision)
+        P = _to_cuda(params)
+        f = lambda t: t.to("cuda", torch.float32)
+        loss, (pn, an, sn) = E.inner_loop(nef, P, f(coords), f(img), f(p), f(a), f(sigma), lrs, K,
+                                          masks=[m.cuda() for m in masks], optimize_gaussian_window=opt_w)
+        errs = dict(loss=abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)), p=rel_err(pn - f(p), p_ref - p),
+                    a=rel_err(an - f(a), a_ref - a), sigma=rel_err(sn, s_ref))
+        print(precision, opt_w, {k: f"{v:.2e}" for k, v in errs.items()})
+        assert all(v < tol for v in errs.values()), errs
+        if not opt_w:
+            assert torch.equal(sn, f(sigma))               # pde_trainer.py:210-212: window updates are zeroed
+
+
 def test_tensor_core_full_size_ns_subset():
     """BASELINE config 2 at full size through the tensor-core forward: random rows against the oracle."""
     cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
