@@ -194,7 +194,22 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::mbar_wait(bar_p, par);
     tc::tc_fence_after();
     F_STAMP(1);
+    // gamma_q first: GEMM1 is issued as soon as its operand is complete (named barrier 7: warp 0 syncs, the others arrive)
+    // and runs in the shadow of the gamma_v pass
     rff_from_proj<D, false>(tp + lane_off + 16 * cq, sA0, nullptr, C::ABLK, row, 16 * cq);
+    tc::fence_proxy_async();
+    if (warp == 0) {
+      tc::named_sync(7, C::NT);
+      if (tid == 0) {
+        if (z == 0) tc::mbar_wait(bar_w, 0);
+        tc::tc_fence_after();
+        issue_gemm<D>(t0, aA0, aW, C::ABLK, C::WBLK);
+        tc::mma_commit(bar_g1);
+      }
+      __syncwarp();
+    } else {
+      tc::named_arrive(7, C::NT);
+    }
     rff_from_proj<D, false>(tp + lane_off + HD + 16 * cq, sA1, nullptr, C::ABLK, row, 16 * cq);
     F_STAMP(2);
     tc::tc_fence_before();
@@ -202,10 +217,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     __syncthreads();
     F_STAMP(3);
     if (tid == 0) {
-      if (z == 0) tc::mbar_wait(bar_w, 0);
       tc::tc_fence_after();
-      issue_gemm<D>(t0, aA0, aW, C::ABLK, C::WBLK);
-      tc::mma_commit(bar_g1);
       issue_gemm<D>(t1, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g2);
     }
