@@ -231,18 +231,35 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       tc::mbar_wait(bar_p, par);
       tc::tc_fence_after();
       V_STAMP(2);
-      rff_from_proj<D, true>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
+      // sin half first: the K-steps over the sin features (3 split terms) are issued as soon as that half is written
+      // (named barrier 5: the issuing warp syncs, the others arrive) and run in the shadow of the cos half
+      static_assert(D == 128, "sin / cos halves = the two 64-feature blocks");
+      rff_half_from_proj<D, true, true>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
+      tc::fence_proxy_async();
+      if (warp == (MMA_TID >> 5)) {
+        tc::named_sync(5, C::NT);
+        if (tid == MMA_TID) {
+          if (it == 0) tc::mbar_wait(bar_w, 0);
+          tc::tc_fence_after();
+          issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 0, 4, 0);
+          issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 0, 4, 1);
+          issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 0, 4, 1);
+        }
+        __syncwarp();
+      } else {
+        tc::named_arrive(5, C::NT);
+      }
+      rff_half_from_proj<D, true, false>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
       V_STAMP(3);
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
       V_STAMP(4);
       if (tid == MMA_TID) {
-        if (it == 0) tc::mbar_wait(bar_w, 0);
         tc::tc_fence_after();
-        issue_gemm<D>(tT, aGhi, aW, C::ABLK, C::WBLK);
-        issue_gemm<D>(tT, aX, aW, C::ABLK, C::WBLK, 1);
-        issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
+        issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 4, 8, 1);
+        issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 4, 8, 1);
+        issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 4, 8, 1);
         tc::mma_commit(bar_g1);
       }
       // next tile's invariants -> projection operand (overlaps the 3-term GEMM; tP was read by everyone before the barrier)

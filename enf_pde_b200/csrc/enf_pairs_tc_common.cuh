@@ -201,6 +201,41 @@ __device__ __forceinline__ void rff_from_proj(uint32_t t_proj, uint8_t* tile_hi,
   }
 }
 
+// SIN = true: only the sin columns (feature block 0 at D = 128), false: only the cos columns -- lets the MMAs over the
+// first half of K start while the second half of gamma is still being evaluated
+template <int D, bool SPLIT, bool SIN>
+__device__ __forceinline__ void rff_half_from_proj(uint32_t t_proj, uint8_t* tile_hi, uint8_t* tile_lo, uint32_t ablk, int row, int j0) {
+  constexpr int HD = D / 2;
+  float ph[16];
+  tc::tmem_ld16(t_proj, ph);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int c8 = 0; c8 < 16; c8 += 8) {
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = SIN ? __sinf(ph[c8 + t]) : __cosf(ph[c8 + t]);
+    tc::st_row8_bf16(tile_hi, ablk, row, (SIN ? 0 : HD) + j0 + c8, v);
+    if (SPLIT) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] -= tc::round_operand(v[t]);
+      tc::st_row8_bf16(tile_lo, ablk, row, (SIN ? 0 : HD) + j0 + c8, v);
+    }
+  }
+}
+
+// K-steps [kk0, kk1) of issue_gemm (16 features each)
+template <int D>
+__device__ __forceinline__ void issue_gemm_ksteps(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk, int kk0,
+                                                  int kk1, uint32_t accumulate_first) {
+  constexpr uint32_t idesc = tc::make_idesc(ROWS, D, tc::kOperandFmt, 0, 0);
+  const uint32_t a = tc::desc_lo_k(a_addr), b = tc::desc_lo_k(b_addr);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk)
+    if (kk >= kk0 && kk < kk1)
+      tc::mma_f16_lo(d_tmem, a + (((kk >> 2) * ablk + (kk & 3) * 32) >> 4), b + (((kk >> 2) * wblk + (kk & 3) * 32) >> 4), idesc,
+                     (kk > kk0) | accumulate_first);
+}
+
 // D[128 x N=D] = A[128 x K=D] (K-major activation tile) * B (K-major weight image: rows = output feature)
 template <int D>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t ablk, uint32_t wblk, uint32_t accumulate = 0) {
