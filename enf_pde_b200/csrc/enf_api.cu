@@ -175,9 +175,24 @@ struct Ctx {
   bool tc = false;           // tensor-core precision mode: big stage GEMMs run on the tf32 kernels
   bool gemm_failed = false;
   float* f(const char* name) const { return ws + Y->off(name); }
+  // Products issued between begin_group() / end_group() must be mutually independent (no one reads or non-atomically
+  // rewrites another's output): the small ones are collected and go out in ONE launch (their time is launch + pipeline
+  // latency, not flops), the others launch immediately.
+  bool grouping = false;
+  std::vector<EnfGemmProblem> pending;
+  void begin_group() { grouping = true; }
+  void end_group() {
+    grouping = false;
+    if (pending.empty()) return;
+    int r = enf_gemm_group(st, (int)pending.size(), pending.data());
+    if (r < 0) gemm_failed = true; else launches += r;
+    pending.clear();
+  }
   void gemm(int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o = EnfGemmOpts()) {
     EnfGemmOpts oo = o;
     if (!tc) oo.tc = 0;       // callers mark the big tail / W3 products (with_lo, opt_acc_big); honoured in tensor-core mode only
+    if (M <= 0 || N <= 0) return;
+    if (grouping && enf_gemm_groupable(M, N, K, oo)) { pending.push_back(EnfGemmProblem{M, N, K, A, B, C, oo}); return; }
     int r = enf_gemm(st, M, N, K, A, B, C, oo);
     if (r < 0) gemm_failed = true; else launches += r;
   }
@@ -299,6 +314,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
   const int Bx = x_batch_stride == 0 ? 1 : D.B;
   // ---- W: fold weights --------------------------------------------------------------------------
+  c.begin_group();
   c.gemm(d, Hd, d, enf_mat(w->q_wf, d), enf_mat(w->wq, Hd), enf_mat(c.f("A_q"), Hd));
   c.gemm(1, Hd, d, enf_mat(w->q_bf, d), enf_mat(w->wq, Hd), enf_mat(c.f("c_q"), Hd), opt_bias(w->bq));
   c.gemm(d, d, d, enf_mat(w->v_wf, d), enf_mat(w->fv_w1, d), enf_mat(c.f("Wp"), d));
@@ -307,6 +323,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm(1, 2 * Hd, d, enf_mat(w->fv_beta, d), enf_mat(w->fv_w2, 2 * Hd), enf_mat(c.f("b2g"), 2 * Hd), opt_bias(w->fv_b2));
   c.launches += enf_launch_rowscale(st, w->mx_w2, w->mx_g, c.f("M2g"), d, d);
   c.gemm(1, d, d, enf_mat(w->mx_beta, d), enf_mat(w->mx_w2, d), enf_mat(c.f("c2g"), d), opt_bias(w->mx_b2));
+  c.end_group();
   // tail fold (exact algebra, tests/folded_model.py): mixer Dense_1, out_proj and the block FFN's Dense_0 are three
   // linear maps in a row:  e1 = nbar W_A + b_A,  W_A = blockdiag(M2g) wo fb_w1,  b_A = (tile(c2g) wo + bo) fb_w1 + fb_b1
   {
@@ -316,8 +333,10 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
       return fail(ENF_ERR_CUDA, "copy of out_proj bias failed");
     for (int h = 0; h < H; ++h)      // head by head in stream order: a deterministic sum
       c.gemm(1, Hd, d, enf_mat(c.f("c2g"), d), enf_mat(w->wo + (int64_t)h * d * Hd, Hd), enf_mat(c.f("b1"), Hd), opt_acc());
+    c.begin_group();
     c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("W_A"), Hd));
     c.gemm(1, Hd, Hd, enf_mat(c.f("b1"), Hd), enf_mat(w->fb_w1, Hd), enf_mat(c.f("b_A"), Hd), opt_bias(w->fb_b1));
+    c.end_group();
   }
   if (use_tc) {
     EnfSplitList sl;
@@ -333,8 +352,10 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
   c.gemm((int)BZ, d, L, enf_mat(a, L), enf_mat(w->stem_w, d), enf_mat(c.f("a0"), d), opt_bias(w->stem_b));
   c.launches += enf_launch_ln_fwd(st, c.f("a0"), BZ, d, w->ln_attn_g, w->ln_attn_b, c.f("acore"), c.f("ahat"), c.f("arstd"), 0);
+  c.begin_group();
   c.gemm((int)BZ, Hd, d, enf_mat(c.f("ahat"), d), enf_mat(w->wk, Hd), enf_mat(c.f("k"), Hd), opt_bias(w->bk));
   c.gemm((int)BZ, Hd, d, enf_mat(c.f("ahat"), d), enf_mat(w->wv, Hd), enf_mat(c.f("v0"), Hd), opt_bias(w->bv));
+  c.end_group();
   {
     EnfGemmOpts o; o.batch = H;     // U[bz,h,i] = sum_j A_q[i, h*d+j] k[bz,h,j]
     c.gemm((int)BZ, d, d, enf_mat(c.f("k"), Hd, 1, d), enf_mat(c.f("A_q"), 1, Hd, d), enf_mat(c.f("U"), Hd, 1, d), o);
@@ -600,31 +621,36 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   // ---- W backward: unfold the folded-weight gradients --------------------------------------------------------
   if (dW) {
     // tail fold: W_A = P1 fb_w1, b_A = b1 fb_w1 + fb_b1, P1 = blockdiag(M2g) wo, b1 = tile(c2g) wo + bo
+    // every product of this group reads only finished accumulators (gf_*) and weights, and writes its own leaf
+    c.begin_group();
     c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), 1, Hd), enf_mat(c.f("gf_W_A"), Hd), enf_mat(G("fb_w1"), Hd));
-    c.launches += enf_launch_add_outer(st, G("fb_w1"), Hd, c.f("b1"), c.f("gf_b_A"), Hd, Hd);
     c.gemm(Hd, Hd, Hd, enf_mat(c.f("gf_W_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("dP1"), Hd));
     c.gemm(1, Hd, Hd, enf_mat(c.f("gf_b_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("db1"), Hd));
+    c.gemm(d, d, Hd, enf_mat(c.f("gf_A_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_wf"), d));
+    c.gemm(d, Hd, d, enf_mat(w->q_wf, 1, d), enf_mat(c.f("gf_A_q"), Hd), enf_mat(G("wq"), Hd));
+    c.gemm(1, d, Hd, enf_mat(c.f("gf_c_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_bf"), d));
+    c.gemm(d, d, d, enf_mat(c.f("gf_Wp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_wf"), d));
+    c.gemm(d, d, d, enf_mat(w->v_wf, 1, d), enf_mat(c.f("gf_Wp"), d), enf_mat(G("fv_w1"), d));
+    c.gemm(1, d, d, enf_mat(c.f("gf_bp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_bf"), d));
+    c.gemm(1, d, 2 * Hd, enf_mat(c.f("gf_b2g"), 2 * Hd), enf_mat(w->fv_w2, 1, 2 * Hd), enf_mat(G("fv_beta"), d));
+    c.end_group();
+    c.launches += enf_launch_add_outer(st, G("fb_w1"), Hd, c.f("b1"), c.f("gf_b_A"), Hd, Hd);
     {
       const int64_t hb = (int64_t)d * Hd;        // one head's block of rows of wo / P1
       EnfGemmOpts ob; ob.batch = H;
       c.gemm(d, Hd, d, enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("dP1"), Hd, 1, hb), enf_mat(G("wo"), Hd, 1, hb), ob);
       for (int h = 0; h < H; ++h) c.launches += enf_launch_add_outer(st, G("wo") + h * hb, Hd, c.f("c2g"), c.f("db1"), d, Hd);
+      c.begin_group();                 // atomic accumulations into the zero-initialised gf_M2g / gf_c2g: order-free
       for (int h = 0; h < H; ++h) {
         c.gemm(d, d, Hd, enf_mat(c.f("dP1") + h * hb, Hd), enf_mat(w->wo + h * hb, 1, Hd), enf_mat(c.f("gf_M2g"), d), opt_acc());
         c.gemm(1, d, Hd, enf_mat(c.f("db1"), Hd), enf_mat(w->wo + h * hb, 1, Hd), enf_mat(c.f("gf_c2g"), d), opt_acc());
       }
+      c.end_group();
     }
-    c.gemm(d, d, Hd, enf_mat(c.f("gf_A_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_wf"), d));
-    c.gemm(d, Hd, d, enf_mat(w->q_wf, 1, d), enf_mat(c.f("gf_A_q"), Hd), enf_mat(G("wq"), Hd));
     c.launches += enf_launch_add_outer(st, G("wq"), Hd, w->q_bf, c.f("gf_c_q"), d, Hd);
-    c.gemm(1, d, Hd, enf_mat(c.f("gf_c_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_bf"), d));
-    c.gemm(d, d, d, enf_mat(c.f("gf_Wp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_wf"), d));
-    c.gemm(d, d, d, enf_mat(w->v_wf, 1, d), enf_mat(c.f("gf_Wp"), d), enf_mat(G("fv_w1"), d));
     c.launches += enf_launch_add_outer(st, G("fv_w1"), d, w->v_bf, c.f("gf_bp"), d, d);
-    c.gemm(1, d, d, enf_mat(c.f("gf_bp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_bf"), d));
     c.launches += enf_launch_rowdot(st, w->fv_w2, c.f("gf_W2g"), G("fv_g"), d, 2 * Hd);
     c.launches += enf_launch_mul_rows(st, G("fv_w2"), c.f("gf_W2g"), w->fv_g, d, 2 * Hd, w->fv_beta, c.f("gf_b2g"));
-    c.gemm(1, d, 2 * Hd, enf_mat(c.f("gf_b2g"), 2 * Hd), enf_mat(w->fv_w2, 1, 2 * Hd), enf_mat(G("fv_beta"), d));
     c.launches += enf_launch_rowdot(st, w->mx_w2, c.f("gf_M2g"), G("mx_g"), d, d);
     c.launches += enf_launch_mul_rows(st, G("mx_w2"), c.f("gf_M2g"), w->mx_g, d, d, w->mx_beta, c.f("gf_c2g"));
     c.gemm(1, d, d, enf_mat(c.f("gf_c2g"), d), enf_mat(w->mx_w2, 1, d), enf_mat(G("mx_beta"), d));

@@ -99,6 +99,10 @@ struct EnfGemmOpts {
 };
 // C[M,N] (+)= alpha * act(A)[M,K] * B[K,N] (+ bias) (* gelu'(aux)); returns number of kernels launched.
 int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o);
+// several small independent products (batch 1, no split-K, not tensor-core) in one launch; returns the number of launches
+struct EnfGemmProblem { int M, N, K; EnfMat A, B, C; EnfGemmOpts o; };
+bool enf_gemm_groupable(int M, int N, int K, const EnfGemmOpts& o);
+int enf_gemm_group(cudaStream_t st, int n, const EnfGemmProblem* p);
 // tf32 tensor-core path: 1 = launched, 0 = shape not taken (use the fp32 kernel), -1 = configuration error
 int enf_gemm_tc(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o);
 // dst[i] = src[i] - trunc_tf32(src[i]) for up to 8 (src, dst, n) triples in one launch (the B_lo operands)

@@ -33,14 +33,14 @@ __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
+__device__ __forceinline__ void gemm_tile(const GemmKArgs& g, int bx, int by, int bzz) {
   extern __shared__ __align__(16) float gemm_smem[];
   float (*As)[BK][BM + 4] = reinterpret_cast<float (*)[BK][BM + 4]>(gemm_smem);
   float (*Bs)[BK][BN + 4] = reinterpret_cast<float (*)[BK][BN + 4]>(gemm_smem + ST * BK * (BM + 4));
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int bz = blockIdx.z / g.splitk, ks = blockIdx.z % g.splitk;
+  const int m0 = bx * BM, n0 = by * BN;
+  const int bz = bzz / g.splitk, ks = bzz % g.splitk;
   const float* A = g.A + (int64_t)bz * g.sab;
   const float* B = g.B + (int64_t)bz * g.sbb;
   float* C = g.C + (int64_t)bz * g.scb;
@@ -129,7 +129,64 @@ __global__ void __launch_bounds__(256) enf_gemm_kernel(GemmKArgs g) {
   }
 }
 
+__global__ void __launch_bounds__(256) enf_gemm_kernel(const __grid_constant__ GemmKArgs g) { gemm_tile(g, blockIdx.x, blockIdx.y, blockIdx.z); }
+
+// several small independent products in one launch: blockIdx.z selects the problem (batch = 1, no split-K)
+constexpr int kMaxGroup = 12;
+struct GemmGroupArgs { GemmKArgs g[kMaxGroup]; };
+__global__ void __launch_bounds__(256) enf_gemm_group_kernel(const __grid_constant__ GemmGroupArgs G) {
+  const GemmKArgs& g = G.g[blockIdx.z];
+  if ((int)blockIdx.x * BM >= g.M || (int)blockIdx.y * BN >= g.N) return;
+  gemm_tile(g, blockIdx.x, blockIdx.y, 0);
+}
+
+constexpr size_t kGemmSmem = (size_t)ST * BK * ((BM + 4) + (BN + 4)) * sizeof(float);
+bool gemm_configure() {
+  static const bool ok =
+      cudaFuncSetAttribute(enf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) == cudaSuccess &&
+      cudaFuncSetAttribute(enf_gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) == cudaSuccess;
+  return ok;
+}
+
+GemmKArgs pack_args(int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o) {
+  GemmKArgs g;
+  g.A = A.p; g.sam = A.rs; g.sak = A.cs; g.sab = A.bs;
+  g.B = B.p; g.sbk = B.rs; g.sbn = B.cs; g.sbb = B.bs;
+  g.C = const_cast<float*>(C.p); g.scm = C.rs; g.scn = C.cs; g.scb = C.bs;
+  g.bias = o.bias; g.bias_bs = o.bias_bs; g.aux = o.mul_gelu_grad; g.C2 = o.gelu_out; g.round_out = o.round_out;
+  g.M = M; g.N = N; g.K = K; g.act_a = o.act_a; g.accumulate = o.accumulate; g.alpha = o.alpha;
+  g.splitk = 1;
+  g.kchunk = ((K + BK - 1) / BK) * BK;
+  if (g.kchunk < BK) g.kchunk = BK;
+  return g;
+}
+
 }  // namespace
+
+bool enf_gemm_groupable(int M, int N, int K, const EnfGemmOpts& o) {
+  return o.batch == 1 && !o.tc && K <= 1024 && (int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN) <= 64;
+}
+
+int enf_gemm_group(cudaStream_t st, int n, const EnfGemmProblem* p) {
+  if (n <= 0) return 0;
+  if (!gemm_configure()) return -1;
+  int launches = 0;
+  for (int first = 0; first < n; first += kMaxGroup) {
+    const int cnt = n - first < kMaxGroup ? n - first : kMaxGroup;
+    GemmGroupArgs G;
+    int gx = 1, gy = 1;
+    for (int i = 0; i < cnt; ++i) {
+      const EnfGemmProblem& q = p[first + i];
+      G.g[i] = pack_args(q.M, q.N, q.K, q.A, q.B, q.C, q.o);
+      const int tm = (q.M + BM - 1) / BM, tn = (q.N + BN - 1) / BN;
+      if (tm > gx) gx = tm;
+      if (tn > gy) gy = tn;
+    }
+    enf_gemm_group_kernel<<<dim3(gx, gy, cnt), 256, kGemmSmem, st>>>(G);
+    ++launches;
+  }
+  return launches;
+}
 
 int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C, const EnfGemmOpts& o) {
   if (M <= 0 || N <= 0 || o.batch <= 0) return 0;
@@ -138,12 +195,7 @@ int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C,
     int r = enf_gemm_tc(st, M, N, K, A, B, C, o);
     if (r != 0) return r;
   }
-  GemmKArgs g;
-  g.A = A.p; g.sam = A.rs; g.sak = A.cs; g.sab = A.bs;
-  g.B = B.p; g.sbk = B.rs; g.sbn = B.cs; g.sbb = B.bs;
-  g.C = const_cast<float*>(C.p); g.scm = C.rs; g.scn = C.cs; g.scb = C.bs;
-  g.bias = o.bias; g.bias_bs = o.bias_bs; g.aux = o.mul_gelu_grad; g.C2 = o.gelu_out; g.round_out = o.round_out;
-  g.M = M; g.N = N; g.K = K; g.act_a = o.act_a; g.accumulate = o.accumulate; g.alpha = o.alpha;
+  GemmKArgs g = pack_args(M, N, K, A, B, C, o);
   int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int64_t tiles = (int64_t)tiles_m * tiles_n * o.batch;
   int splitk = 1;
@@ -161,10 +213,7 @@ int enf_gemm(cudaStream_t st, int M, int N, int K, EnfMat A, EnfMat B, EnfMat C,
   if (splitk < 1) splitk = 1;
   g.splitk = splitk; g.kchunk = kchunk;
   dim3 grid(tiles_m, tiles_n, o.batch * splitk);
-  constexpr size_t smem = (size_t)ST * BK * ((BM + 4) + (BN + 4)) * sizeof(float);
-  static const bool configured =
-      cudaFuncSetAttribute(enf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
-  if (!configured) return -1;
-  enf_gemm_kernel<<<grid, 256, smem, st>>>(g);
+  if (!gemm_configure()) return -1;
+  enf_gemm_kernel<<<grid, 256, kGemmSmem, st>>>(g);
   return 1;
 }
