@@ -346,7 +346,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_leg(cfg, 6, 1, budget_s=20.0)
+        r = cpu_leg(cfg, 40, 1, budget_s=15.0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     q_total = world * B * C * args.steps
