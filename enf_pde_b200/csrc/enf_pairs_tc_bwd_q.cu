@@ -262,10 +262,13 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
     for (int h = 0; h < H; ++h) dsv_next[h] = row < P.C ? __ldg(P.ds + (bz * P.C + row) * H + h) : 0.f;
     tc::fence_proxy_async();
     __syncthreads();
-    if (tid == MMA_TID) {
-      tc::tc_fence_after();
-      issue_proj(tP, aU, aOm, HD);
-      tc::mma_commit(bar_p);
+    if (warp == (MMA_TID >> 5)) {
+      if (tc::elect_one()) {
+        tc::tc_fence_after();
+        issue_proj(tP, aU, aOm, HD);
+        tc::mma_commit(bar_p);
+      }
+      __syncwarp();
     }
 
     for (int ct = 0; ct < ntiles; ++ct, ++it) {
@@ -293,13 +296,16 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       tc::fence_proxy_async();
       __syncthreads();
       Q_STAMP(32, 4); Q_STAMP(160, 4);
-      if (tid == MMA_TID) {
-        if (it == 0) tc::mbar_wait(bar_w, 0);
-        tc::tc_fence_after();
-        issue_gemm<D>(tT, aGhi, aW, C::ABLK, C::WBLK);
-        issue_gemm<D>(tT, aGlo, aW, C::ABLK, C::WBLK, 1);
-        issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
-        tc::mma_commit(bar_g1);
+      if (warp == (MMA_TID >> 5)) {
+        if (tc::elect_one()) {
+          if (it == 0) tc::mbar_wait(bar_w, 0);
+          tc::tc_fence_after();
+          issue_gemm<D>(tT, aGhi, aW, C::ABLK, C::WBLK);
+          issue_gemm<D>(tT, aGlo, aW, C::ABLK, C::WBLK, 1);
+          issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
+          tc::mma_commit(bar_g1);
+        }
+        __syncwarp();
       }
       // ---- per-row side work, overlapped with the 3-term GEMM: shared by three of the row's four threads ----------------
       if (cq == 0) {
@@ -366,17 +372,20 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       tc::fence_proxy_async();
       __syncthreads();
       Q_STAMP(32, 8); Q_STAMP(160, 8);
-      if (tid == MMA_TID) {
-        tc::tc_fence_after();
-        issue_rowsum<D>(tS2, aGlo, aS, C::ABLK, ct > 0);           // dU (per item)
-        issue_dgrad<D>(tT, aDz, aW, C::ABLK, C::WBLK, 0);          // d gamma_q
-        tc::mma_commit(bar_d);
-        issue_wgrad<D>(tW, aGhi, aDz, C::ABLK, it > 0);            // dW1_q (per CTA)
-        issue_rowsum<D>(tS1, aDz, aS, C::ABLK, it > 0);            // db1q (per CTA)
-        if (ct + 1 < ntiles) {
-          issue_proj(tP, aU, aOm, HD);
-          tc::mma_commit(bar_p);
+      if (warp == (MMA_TID >> 5)) {
+        if (tc::elect_one()) {
+          tc::tc_fence_after();
+          issue_dgrad<D>(tT, aDz, aW, C::ABLK, C::WBLK, 0);          // d gamma_q (first: S3 waits for it)
+          tc::mma_commit(bar_d);
+          issue_rowsum<D>(tS2, aGlo, aS, C::ABLK, ct > 0);           // dU (per item)
+          issue_wgrad<D>(tW, aGhi, aDz, C::ABLK, it > 0);            // dW1_q (per CTA)
+          issue_rowsum<D>(tS1, aDz, aS, C::ABLK, it > 0);            // db1q (per CTA)
+          if (ct + 1 < ntiles) {
+            issue_proj(tP, aU, aOm, HD);
+            tc::mma_commit(bar_p);
+          }
         }
+        __syncwarp();
       }
       // ---- S3: d gamma_q -> dproj (my 16 frequencies: sin columns j, cos columns HD + j) ---------------------------
       tc::mbar_wait(bar_d, par);
@@ -410,10 +419,13 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       tc::fence_proxy_async();
       __syncthreads();
       Q_STAMP(32, 11); Q_STAMP(160, 11);
-      if (tid == MMA_TID) {
-        tc::tc_fence_after();
-        issue_du(tDu, aGlo, aOmT);
-        tc::mma_commit(bar_u);
+      if (warp == (MMA_TID >> 5)) {
+        if (tc::elect_one()) {
+          tc::tc_fence_after();
+          issue_du(tDu, aGlo, aOmT);
+          tc::mma_commit(bar_u);
+        }
+        __syncwarp();
       }
     }
     // ---- item flush --------------------------------------------------------------------------------------------------
