@@ -19,6 +19,20 @@ def field_shard(num_fields: int, rank: int, world: int) -> slice:
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
+def query_shard(num_queries: int, rank: int, world: int) -> slice:
+    """Fallback partition when there are fewer fields than ranks (shallow water runs 4 fields, the ball 1):
+    every rank takes all fields but a contiguous slice of the C coordinate queries.  The decoded field of a query depends
+    on no other query, so the forward needs no exchange; every latent gradient (dp, da, dsigma) and every weight gradient
+    is a SUM over queries, so the backward needs one all-reduce of the latent gradients (B*Z*(P+L+1) floats) next to the
+    weight-gradient one -- `allreduce_grads` packs both into a single collective."""
+    return field_shard(num_queries, rank, world)
+
+
+def choose_partition(num_fields: int, world: int) -> str:
+    """'fields' when every rank gets at least one field (no data-path collective), else 'queries'."""
+    return "fields" if num_fields >= world else "queries"
+
+
 def pack(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     return torch.cat([t.reshape(-1) for t in tensors])
 
@@ -29,6 +43,18 @@ def unpack(flat: torch.Tensor, like: Sequence[torch.Tensor]):
         out.append(flat[off:off + t.numel()].view_as(t))
         off += t.numel()
     return out
+
+
+def allreduce_grads(weight_grads: Sequence[torch.Tensor], latent_grads: Sequence[torch.Tensor] = (), group=None):
+    """Query-sharded backward: sum weight gradients AND latent gradients (dp, da, dsigma) over ranks in ONE collective.
+    Returns (weight_grads, latent_grads).  With field sharding pass no latent gradients (they are rank-local)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(weight_grads), list(latent_grads)
+    both = list(weight_grads) + list(latent_grads)
+    flat = pack(both)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out = unpack(flat, both)
+    return out[:len(weight_grads)], out[len(weight_grads):]
 
 
 def allreduce_weight_grads(grads: Sequence[torch.Tensor], group=None, average: bool = False):

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from enf_pde_b200.dist import field_shard, pack, unpack, allreduce_weight_grads
+from enf_pde_b200.dist import field_shard, query_shard, choose_partition, pack, unpack, allreduce_weight_grads, allreduce_grads
 
 
 def _free_port():
@@ -31,6 +31,39 @@ def _worker(rank, world, port, out):
     ok = ok and all(torch.allclose(a, b / world, atol=1e-5) for a, b in zip(mean, want))
     out[rank] = ok
     dist.destroy_process_group()
+
+
+def _query_worker(rank, world, port, out):
+    """B = 1 field < 2 ranks: shard the queries; the oracle stands in for the CUDA path (same math, CPU).  Summed over
+    ranks, the latent and weight gradients of the per-shard losses must equal those of the full problem (linearity)."""
+    from oracle import enf_ref as R
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    cfg = R.EnfConfig(num_in=2, num_hidden=16, num_heads=2, num_out=1, latent_dim=4, invariant_type="rel_pos_periodic")
+    params = R.nef_init(cfg, seed=0)
+    p, a, sigma = R.init_latents(cfg, 1, 4)
+    x = R.make_coords(cfg, (5, 5))[None]
+    d_out = torch.randn(1, 25, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    assert choose_partition(1, world) == "queries" and choose_partition(8, world) == "fields"
+    sl = query_shard(25, rank, world)
+    _, g_loc, dp_loc, da_loc, ds_loc = R.fwd_bwd(cfg, params, x[:, sl], p, a, sigma, d_out[:, sl])
+    leaves = list(R.tree_flatten(g_loc["params"]).values())
+    wg, (dp, da, ds) = allreduce_grads(leaves, [dp_loc, da_loc, ds_loc])
+    _, g_all, dp_all, da_all, ds_all = R.fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    want = list(R.tree_flatten(g_all["params"]).values())
+    ok = all(torch.allclose(u, v, atol=1e-10) for u, v in zip(wg, want))
+    ok = ok and torch.allclose(dp, dp_all, atol=1e-10) and torch.allclose(da, da_all, atol=1e-10) and torch.allclose(ds, ds_all, atol=1e-10)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_query_sharded_backward_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_query_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
 
 
 def test_field_shards_partition_the_batch():
