@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="fp32: FMA kernels (<=1e-4 bucket); bf16: tcgen05 kernels with 16-bit operands (<=2e-3 bucket)")
+    ap.add_argument("--tc-backward-d64", action="store_true",
+                    help="d = 64 configs in bf16 mode: tcgen05 backward too (ENF_FLAG_TC_BACKWARD_D64; dp of `ponita` reaches 3e-3)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -217,7 +219,7 @@ def main():
 
     inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
     nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True,
-                                         cfg["window"], precision=args.precision)
+                                         cfg["window"], precision=args.precision, tc_backward_d64=args.tc_backward_d64)
     B, Z = cfg["B"], cfg["Z"]
     gen = torch.Generator().manual_seed(1234 + rank)
     p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])

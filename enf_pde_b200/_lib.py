@@ -64,6 +64,7 @@ INVARIANT_KINDS = {
 }
 PREC_FP32, PREC_BF16 = 0, 1
 FLAG_FORWARD_ONLY = 1
+FLAG_TC_BACKWARD_D64 = 2
 
 EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_fwd",
            "enf_xattn_bwd", "enf_last_launch_count", "enf_last_error", "enf_debug_ws_offset", "enf_profile_enable",

@@ -71,9 +71,15 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
-  if (D->flags & ~ENF_FLAG_FORWARD_ONLY) return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
+  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_TC_BACKWARD_D64)) return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
   if (rl) *rl = r;
   return ENF_OK;
+}
+
+// tensor-core backward: d = 128 always, d = 64 on request (ENF_FLAG_TC_BACKWARD_D64, see include/enf_b200.h)
+bool use_tc_bwd(const EnfDesc& D) {
+  return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H) &&
+         (D.d == 128 || (D.flags & ENF_FLAG_TC_BACKWARD_D64));
 }
 
 Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
@@ -89,7 +95,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd);
   {
     // transposed W3 copies: only the fp32-FMA backward reads them
-    const bool tc_both = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H);
+    const bool tc_both = use_tc_bwd(D);
     if (train && !tc_both) Y.add("W3T", BZ * H * d2);
   }
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
@@ -100,7 +106,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     // low parts W - trunc_tf32(W) of the weights those GEMMs multiply by (3-term split product)
     Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
     Y.add("lo_W_A", Hd * Hd); Y.add("lo_fb_w2", Hd * Hd); Y.add("lo_m0_w", Hd * d); Y.add("lo_m1_w", d2); Y.add("lo_mx_w1", d2);
-    if (train && enf_pairs_bwd_tc_supported(D.d, D.H)) {
+    if (train && use_tc_bwd(D)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       const size_t Cpad = (size_t)((D.C + 127) / 128) * 128;      // kernels A / B work on whole 128-query tiles
       Y.add("dthat", BZ * Cpad * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
@@ -389,7 +395,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
     tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
     tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = train ? c.f("slog") : nullptr;
-    tp.that_img = (train && enf_pairs_bwd_tc_supported(D.d, D.H)) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
+    tp.that_img = (train && use_tc_bwd(D)) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
     static const bool trace_fwd = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace_fwd ? reinterpret_cast<long long*>(c.f("dbg_fwd")) : nullptr;
     prof_mark(0, 0, st);
@@ -460,7 +466,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small");
 
   const bool tc_fwd = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);
-  const bool tc_bwd = tc_fwd && enf_pairs_bwd_tc_supported(D.d, D.H);
+  const bool tc_bwd = tc_fwd && use_tc_bwd(D);
   Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y; c.tc = tc_fwd;
   cudaStream_t st = c.st;
   const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;

@@ -407,15 +407,20 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
   __syncthreads();
   tc::tc_fence_after();
   if (!issuer) {
+    // accumulator row (input feature) of this thread: M = 128 keeps row r in TMEM lane r, M = 64 (d = 64) in lane
+    // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
+    const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       float w[32];
       tc::tmem_ld32(tW3 + h * D + my_t, w);
       tc::tmem_ld_wait();
-      float* o = P.g_W3 + ((bz * H + h) * D + row) * D + col0;
+      if (wrow >= 0) {
+        float* o = P.g_W3 + ((bz * H + h) * D + wrow) * D + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(w[j] * inv_gs, w[j + 1] * inv_gs, w[j + 2] * inv_gs, w[j + 3] * inv_gs);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(w[j] * inv_gs, w[j + 1] * inv_gs, w[j + 2] * inv_gs, w[j + 3] * inv_gs);
+      }
     }
   }
   for (int e = tid; e < H * D; e += NTA) P.g_b3[bz * H * D + e] = s_db3[e] * inv_gs;
@@ -445,10 +450,12 @@ int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
 
 }  // namespace
 
-bool enf_pairs_bwd_tc_supported(int d, int H) { return d == 128 && (H == 1 || H == 2); }
+bool enf_pairs_bwd_tc_supported(int d, int H) { return (d == 128 || d == 64) && (H == 1 || H == 2); }
 
 int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
   if (d == 128 && H == 2) return launch_bwd<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_bwd<128, 1>(st, p);
+  if (d == 64 && H == 2) return launch_bwd<64, 2>(st, p);
+  if (d == 64 && H == 1) return launch_bwd<64, 1>(st, p);
   return -1;
 }

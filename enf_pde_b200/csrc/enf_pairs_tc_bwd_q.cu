@@ -61,11 +61,12 @@ __device__ __forceinline__ void issue_rowsum(uint32_t d_tmem, uint32_t act_addr,
     tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_mnmajor(s_addr + kk * 2048, ROWS * 128), idesc,
                 (kk > 0) | accumulate);
 }
-// D[128 x 16] = Dp[128 rows][64] (K-major, one 64-feature block) * OmT[16][64] (K-major)
+// D[128 x 16] = Dp[128 rows][HD <= 64] (K-major, first feature block) * OmT[16][HD] (K-major)
+template <int HD>
 __device__ __forceinline__ void issue_du(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
   constexpr uint32_t idesc = tc::make_idesc(ROWS, 16, tc::kOperandFmt, 0, 0);
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
+  for (int kk = 0; kk < HD / 16; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
 }
 
 // diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA 7, its first
@@ -80,7 +81,10 @@ template <int D, int H>
 __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
   using C = QCfg<D, H>;
   constexpr int HD = C::HD;
-  constexpr int MMA_TID = 384;                        // warp 12, lane 0: a warp without per-row side work
+  constexpr int MMA_TID = C::NT - 128;                // lane 0 of the first warp of the last column quarter
+  // per-row side work by column quarter: 0 = next tile's invariants, kPart0 / kPart1 = the two halves of the previous
+  // tile's window / invariant backward (at d = 64 a row has two threads: quarter 0 also takes the second half)
+  constexpr int kPart0 = 1, kPart1 = C::NQ > 2 ? 2 : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = base + C::OFF_W;
@@ -107,6 +111,9 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
   const int lq = warp & 3, cq = warp >> 2;
   const int row = lq * 32 + lane, col0 = cq * 32;
   const float scale = rsqrtf((float)D);
+  // row (feature) of an M = D accumulator held by my TMEM lane: M = 128 keeps row r in lane r, M = 64 (d = 64) in lane
+  // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
+  const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
 
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) tc::mbar_init(bars + i, 1);
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       // global operands of this tile's side work, requested before the RFF pass: one row record per thread role
       float pre8[8];                                       // cq == 0: xi of tile ct + 1 ; cq == 1, 2: du_v of tile ct - 1
       if (cq == 0) { if (ct + 1 < ntiles) load_xi(ct + 1, pre8); }
-      else if (cq <= 2) { if (ct > 0) load_duv(ct - 1, pre8); }
+      else if (cq == kPart0 || cq == kPart1) { if (ct > 0) load_duv(ct - 1, pre8); }
       Q_STAMP(32, 0); Q_STAMP(160, 0);
       if (it > 0) tc::mbar_wait(bar_u, (it - 1) & 1);     // every MMA of the previous tile is done with the operand tiles
       Q_STAMP(32, 1); Q_STAMP(160, 1);
@@ -326,8 +333,13 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         for (int h = 0; h < H; ++h) { kap_acc[h] += dsv[h]; dw += dsv[h]; }
         s_rx[(((it0 + ct) % 3) * ROWS + row) * C::RX + 16] = dw;
         if (ct + 1 < ntiles) write_invariants(ct + 1, pre8);
-      } else if (cq <= 2 && ct > 0) {
-        row_backward(ct - 1, (it - 1) & 1, cq - 1, pre8);
+        if (kPart1 == 0 && ct > 0) {                       // d = 64: this thread also owns the second half of the row backward
+          float duv[8];
+          load_duv(ct - 1, duv);
+          row_backward(ct - 1, (it - 1) & 1, 1, duv);
+        }
+      } else if ((cq == kPart0 || cq == kPart1) && ct > 0) {
+        row_backward(ct - 1, (it - 1) & 1, cq == kPart0 ? 0 : 1, pre8);
       }
       // ---- E: h1q, dzq ---------------------------------------------------------------------------------------------
       float v[32];
@@ -398,10 +410,9 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c8 = 0; c8 < 16; c8 += 8) {
-          const int col = 16 * cq + c8;                              // < 64: block 0 holds sin, block 1 holds cos (D = 128)
-          const uint32_t off = tc::swz_chunk_off(row, col >> 3);
-          const uint4 qs = *reinterpret_cast<const uint4*>(sGhi + off);
-          const uint4 qc = *reinterpret_cast<const uint4*>(sGhi + C::ABLK + off);
+          const int col = 16 * cq + c8;                              // sin feature `col`, cos feature HD + col
+          const uint4 qs = *reinterpret_cast<const uint4*>(sGhi + tc::swz_chunk_off(row, col >> 3));
+          const uint4 qc = *reinterpret_cast<const uint4*>(sGhi + ((HD + col) >> 6) * C::ABLK + tc::swz_chunk_off(row, ((HD + col) & 63) >> 3));
           const __half2* hs = reinterpret_cast<const __half2*>(&qs);
           const __half2* hc = reinterpret_cast<const __half2*>(&qc);
           float o[8];
@@ -422,19 +433,21 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       if (warp == (MMA_TID >> 5)) {
         if (tc::elect_one()) {
           tc::tc_fence_after();
-          issue_du(tDu, aGlo, aOmT);
+          issue_du<HD>(tDu, aGlo, aOmT);
           tc::mma_commit(bar_u);
         }
         __syncwarp();
       }
     }
     // ---- item flush --------------------------------------------------------------------------------------------------
-    if (cq == 1 || cq == 2) {
+    if (cq == kPart0 || cq == kPart1) {
+      const int part = cq == kPart0 ? 0 : 1;
       float duv[8];
       load_duv(ntiles - 1, duv);
-      row_backward(ntiles - 1, (it - 1) & 1, cq - 1, duv);
-      atomicAdd(&s_dlam[(cq - 1) * 32 + lane], lam_acc);
-    } else {
+      row_backward(ntiles - 1, (it - 1) & 1, part, duv);
+      atomicAdd(&s_dlam[part * 32 + lane], lam_acc);
+    }
+    {
       tc::mbar_wait(bar_u, (it - 1) & 1);
       tc::tc_fence_after();
       if (cq == 0) {
@@ -445,12 +458,14 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         }
       }
     }
-    if (cq == 0) {                                         // dU[h][j], j = my TMEM lane
+    if (cq == 0) {                                         // dU[h][j], j = the accumulator row of my TMEM lane
       float d16[16];
       tc::tmem_ld16(tS2 + lane_off, d16);
       tc::tmem_ld_wait();
+      if (wrow >= 0) {
 #pragma unroll
-      for (int h = 0; h < H; ++h) P.g_U[bz * H * D + h * D + row] = scale * inv_gs * (d16[1 + h] + d16[1 + H + h]);
+        for (int h = 0; h < H; ++h) P.g_U[bz * H * D + h * D + wrow] = scale * inv_gs * (d16[1 + h] + d16[1 + H + h]);
+      }
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -465,14 +480,16 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
     float v[32];
     tc::tmem_ld32(tW + my_t, v);
     tc::tmem_ld_wait();
-    float* o = P.g_q_w1 + (size_t)row * D + col0;
+    if (wrow >= 0) {
+      float* o = P.g_q_w1 + (size_t)wrow * D + col0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * inv_gs);
+      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * inv_gs);
+    }
     if (cq == 0) {
       float d16[16];
       tc::tmem_ld16(tS1 + lane_off, d16);
       tc::tmem_ld_wait();
-      atomicAdd(P.g_q_b1 + row, d16[0] * inv_gs);
+      if (wrow >= 0) atomicAdd(P.g_q_b1 + wrow, d16[0] * inv_gs);
     }
   }
   tc::tc_fence_before();
@@ -495,5 +512,7 @@ int launch_q(cudaStream_t st, const EnfPairTcBwdParams& p) {
 int enf_launch_pairs_bwd_tc_q(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
   if (d == 128 && H == 2) return launch_q<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_q<128, 1>(st, p);
+  if (d == 64 && H == 2) return launch_q<64, 2>(st, p);
+  if (d == 64 && H == 1) return launch_q<64, 1>(st, p);
   return -1;
 }

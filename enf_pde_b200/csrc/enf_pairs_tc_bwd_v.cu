@@ -64,11 +64,12 @@ __device__ __forceinline__ void issue_colsum(uint32_t d_tmem, uint32_t act_addr,
     tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_kmajor(one_addr + (kk >> 2) * 2048 + (kk & 3) * 32), idesc,
                 (kk > 0) | accumulate);
 }
-// D[128 x 16] = Dp[128 rows][64] (K-major, one 64-feature block) * OmT[16][64] (K-major)
+// D[128 x 16] = Dp[128 rows][HD <= 64] (K-major, first feature block) * OmT[16][HD] (K-major)
+template <int HD>
 __device__ __forceinline__ void issue_du_v(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
   constexpr uint32_t idesc = tc::make_idesc(ROWS, 16, tc::kOperandFmt, 0, 0);
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
+  for (int kk = 0; kk < HD / 16; ++kk) tc::mma_f16(d_tmem, tc::desc_kmajor(a_addr + kk * 32), tc::desc_kmajor(b_addr + kk * 32), idesc, kk > 0);
 }
 
 // diagnostics (build with `make TRACE=1`, run with ENF_DEBUG_TRACE=1): clock64() of selected events of CTA 7, its first
@@ -83,7 +84,7 @@ template <int D>
 __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairTcBwdParams P) {
   using C = VCfg<D>;
   constexpr int HD = C::HD;
-  constexpr int MMA_TID = 384;                        // warp 12, lane 0: a warp without per-row side work
+  constexpr int MMA_TID = C::NT - 128;                // lane 0 of the first warp of the last column quarter
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = base + C::OFF_W;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       V_STAMP(2);
       // sin half first: the K-steps over the sin features (3 split terms) are issued as soon as that half is written
       // (named barrier 5: the issuing warp syncs, the others arrive) and run in the shadow of the cos half
-      static_assert(D == 128, "sin / cos halves = the two 64-feature blocks");
+      constexpr int KH = D / 32;                           // K-steps (16 features) per half of gamma
       rff_half_from_proj<D, true, true>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
       tc::fence_proxy_async();
       if (warp == (MMA_TID >> 5)) {
@@ -241,9 +242,9 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         if (tid == MMA_TID) {
           if (it == 0) tc::mbar_wait(bar_w, 0);
           tc::tc_fence_after();
-          issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 0, 4, 0);
-          issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 0, 4, 1);
-          issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 0, 4, 1);
+          issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 0, KH, 0);
+          issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 0, KH, 1);
+          issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 0, KH, 1);
         }
         __syncwarp();
       } else {
@@ -257,9 +258,9 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       V_STAMP(4);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
-        issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 4, 8, 1);
-        issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 4, 8, 1);
-        issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 4, 8, 1);
+        issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, KH, 2 * KH, 1);
+        issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, KH, 2 * KH, 1);
+        issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, KH, 2 * KH, 1);
         tc::mma_commit(bar_g1);
       }
       // next tile's invariants -> projection operand (overlaps the 3-term GEMM; tP was read by everyone before the barrier)
@@ -404,10 +405,9 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c8 = 0; c8 < 16; c8 += 8) {
-          const int col = 16 * cq + c8;                              // < 64: block 0 holds sin, block 1 holds cos (D = 128)
-          const uint32_t off = tc::swz_chunk_off(row, col >> 3);
-          const uint4 qs = *reinterpret_cast<const uint4*>(sGhi + off);
-          const uint4 qc = *reinterpret_cast<const uint4*>(sGhi + C::ABLK + off);
+          const int col = 16 * cq + c8;                              // sin feature `col`, cos feature HD + col
+          const uint4 qs = *reinterpret_cast<const uint4*>(sGhi + tc::swz_chunk_off(row, col >> 3));
+          const uint4 qc = *reinterpret_cast<const uint4*>(sGhi + ((HD + col) >> 6) * C::ABLK + tc::swz_chunk_off(row, ((HD + col) & 63) >> 3));
           const __half2* hs = reinterpret_cast<const __half2*>(&qs);
           const __half2* hc = reinterpret_cast<const __half2*>(&qc);
           float o[8];
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       V_STAMP(19);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
-        issue_du_v(tDu, aX, aOmT);
+        issue_du_v<HD>(tDu, aX, aOmT);
         tc::mma_commit(bar_u);
       }
     }
@@ -442,6 +442,9 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
   __syncthreads();
   tc::tc_fence_after();
   if (it > 0) {
+    // accumulator row (input feature) of this thread: M = 128 keeps row r in TMEM lane r, M = 64 (d = 64) in lane
+    // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
+    const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
     float* dst[2] = {P.g_Wp, P.g_v_w1};
     const uint32_t src[2] = {tWp, tW1};
 #pragma unroll
@@ -449,18 +452,20 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       float v[32];
       tc::tmem_ld32(src[k] + my_t, v);
       tc::tmem_ld_wait();
-      float* o = dst[k] + (size_t)row * D + col0;
+      if (wrow >= 0) {
+        float* o = dst[k] + (size_t)wrow * D + col0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * inv_gs);
+        for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * inv_gs);
+      }
     }
     if (cq == 0) {
       float d16[16];
       tc::tmem_ld16(tS1 + lane_off, d16);
       tc::tmem_ld_wait();
-      atomicAdd(P.g_bp + row, d16[0] * inv_gs);
+      if (wrow >= 0) atomicAdd(P.g_bp + wrow, d16[0] * inv_gs);
       tc::tmem_ld16(tS2 + lane_off, d16);
       tc::tmem_ld_wait();
-      atomicAdd(P.g_v_b1 + row, d16[0] * inv_gs);
+      if (wrow >= 0) atomicAdd(P.g_v_b1 + wrow, d16[0] * inv_gs);
     }
   }
   tc::tc_fence_before();
@@ -482,5 +487,6 @@ int launch_v(cudaStream_t st, const EnfPairTcBwdParams& p) {
 
 int enf_launch_pairs_bwd_tc_v(cudaStream_t st, int d, const EnfPairTcBwdParams& p) {
   if (d == 128) return launch_v<128>(st, p);
+  if (d == 64) return launch_v<64>(st, p);
   return -1;
 }

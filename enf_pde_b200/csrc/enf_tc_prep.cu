@@ -124,13 +124,17 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(int mode, const float
   }
   tc::mbar_wait(&bar_mma, 0);
   tc::tc_fence_after();
-  const int out_rows = (mode == 2) ? D : 128;
+  // accumulator row of this thread: an M = 128 accumulator keeps row r in TMEM lane r; an M = 64 accumulator (mode 2 at
+  // D = 64: dW is 64 x 64) keeps row r in lane 32 (r / 16) + r % 16 -- 16 rows in the lower half of every lane quadrant
+  const int lane = tid & 31;
+  const bool m64 = (mode == 2) && D == 64;
+  const int out_row = m64 ? (lane < 16 ? warp * 16 + lane : -1) : tid;
   for (int c0 = 0; c0 < D; c0 += 32) {
     float v[32];
     tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
     tc::tmem_ld_wait();
-    if (tid < out_rows)
-      for (int i = 0; i < 32; ++i) out[tid * D + c0 + i] = v[i];
+    if (out_row >= 0)
+      for (int i = 0; i < 32; ++i) out[out_row * D + c0 + i] = v[i];
   }
   tc::tc_fence_before();
   __syncthreads();

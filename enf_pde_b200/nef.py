@@ -146,7 +146,7 @@ class EquivariantCrossAttentionNeF:
                  cross_attn_invariant: BaseInvariant, self_attn_invariant: Optional[BaseInvariant] = None,
                  embedding_type: str = "rff", embedding_freq_multiplier=(0.05, 0.1),
                  condition_value_transform: bool = True, use_gaussian_window: bool = True,
-                 precision: str = "fp32"):
+                 precision: str = "fp32", tc_backward_d64: bool = False):
         if num_layers != 0:
             raise NotImplementedError("latent self-attention blocks (num_layers > 0) are not on the accelerated path; "
                                       "every shipped config of the reference uses num_layers: 0")
@@ -165,6 +165,9 @@ class EquivariantCrossAttentionNeF:
         self.condition_value_transform = condition_value_transform
         self.use_gaussian_window = use_gaussian_window
         self.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+        # num_hidden = 64 in tensor-core mode: backward on the tcgen05 kernels too (ENF_FLAG_TC_BACKWARD_D64; off by default:
+        # 3e-3 on dp for `ponita`, see include/enf_b200.h)
+        self.tc_backward_d64 = bool(tc_backward_d64)
 
     # -- nef.init(key, x, p, a, window) (pde_trainer.py:99-102) -----------------------------------------
     def init(self, key, x, p, a, gaussian_window_size=None):
@@ -234,11 +237,11 @@ class EquivariantCrossAttentionNeF:
             raise ValueError(f"gaussian_window_size must have shape {(B, Z, 1)}")
         desc = dict(B=B, C=C, Z=Z, d=self.num_hidden, H=self.num_heads, L=self.latent_dim, O=self.num_out, Dx=Dx,
                     invariant_kind=_lib.INVARIANT_KINDS[inv.invariant_type], use_window=int(self.use_gaussian_window),
-                    precision=self.precision, flags=0)
+                    precision=self.precision, flags=_lib.FLAG_TC_BACKWARD_D64 if self.tc_backward_d64 else 0)
         leaves = params_to_leaves(variables)
         # forward only (validation roll-outs, pde_trainer.py:389-405): nothing is kept for a backward
         if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p, a, sigma, *leaves))):
-            desc["flags"] = _lib.FLAG_FORWARD_ONLY
+            desc["flags"] |= _lib.FLAG_FORWARD_ONLY
         return _XAttnFunction.apply((desc, x_shared), x_arg, p, a, sigma, *leaves)
 
     __call__ = apply

@@ -58,7 +58,12 @@ enum EnfFlags {
   /* forward only: validation / visualisation roll-outs (apply_nef_jitted, pde_trainer.py:389-405;
    * _base_pde_trainer.py:446-457,588-598).  Nothing is saved for a backward (no logits, no operand
    * stash), the workspace is ~10x smaller, enf_xattn_bwd on such a workspace returns ENF_ERR_STATE. */
-  ENF_FLAG_FORWARD_ONLY = 1
+  ENF_FLAG_FORWARD_ONLY = 1,
+  /* tensor-core precision mode at num_hidden = 64: also run the BACKWARD on the tcgen05 kernels (default: the forward
+   * only, the backward on the fp32 kernels).  Opt-in because the 16-bit operand noise of the logit cotangents is
+   * amplified by the cancelling sum over queries in d(pose) of the non-periodic window: measured 3e-3 on dp for
+   * `ponita`, outside the 2e-3 bucket (other invariants and all other gradients are inside it). */
+  ENF_FLAG_TC_BACKWARD_D64 = 2
 };
 
 enum EnfError {

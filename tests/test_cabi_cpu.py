@@ -47,7 +47,7 @@ def test_bad_descriptions_are_rejected_without_a_gpu():
     lib = E.load_library()
     ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, flags=0)
     assert lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**ok))) > 0
-    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=2)):
+    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=4)):
         d = _lib.EnfDesc(**{**ok, **bad})
         assert lib.enf_xattn_workspace_bytes(ctypes.byref(d)) == 0, bad
         assert lib.enf_last_error() != b""

@@ -283,6 +283,33 @@ def test_first_order_inner_loop_against_oracle(precision, tol):
             assert torch.equal(sn, f(sigma))               # pde_trainer.py:210-212: window updates are zeroed
 
 
+@pytest.mark.parametrize("inv,freq,tol", [("rel_pos_periodic", (0.05, 0.1), TOL_BF16), ("ponita", (0.05, 0.01), 5e-3)])
+def test_tensor_core_backward_d64_opt_in(inv, freq, tol):
+    """ENF_FLAG_TC_BACKWARD_D64: the tcgen05 backward at num_hidden = 64 (M = 64 weight-gradient accumulators, two threads per
+    query row).  Inside the 2e-3 bucket for the periodic invariant; `ponita` reaches 3e-3 on dp (cancelling sum of the
+    non-periodic window's pose gradient over queries), which is why the flag is opt-in -- the default backward at d = 64
+    (fp32 kernels) is covered by test_tensor_core_path_against_oracle[plane_d64]."""
+    import enf_pde_b200 as E
+    import types
+    cfg = R.EnfConfig(num_in=2, num_hidden=64, num_heads=2, num_out=1, latent_dim=16, invariant_type=inv, embedding_freq_multiplier=freq)
+    B, C, Z = 3, 300, 25
+    params, x, p, a, sigma, d_out = make_case(cfg, B, C, Z, seed=3)
+    out_ref, dth_ref, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x, p, a, sigma, d_out)
+    iv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=inv, num_in=2))
+    nef = E.EquivariantCrossAttentionNeF(64, 2, 0, 1, 16, iv, iv, "rff", freq, True, True, precision="bf16", tc_backward_d64=True)
+    P = _to_cuda(params)
+    f = lambda t: t.to("cuda", torch.float32)
+    pg, ag, sg = f(p).requires_grad_(True), f(a).requires_grad_(True), f(sigma).requires_grad_(True)
+    out = nef.apply(P, f(x), pg, ag, sg)
+    out.backward(f(d_out))
+    errs = dict(out=rel_err(out.detach(), out_ref), dp=rel_err(pg.grad, dp_ref), da=rel_err(ag.grad, da_ref), ds=rel_err(sg.grad, ds_ref))
+    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(P["params"])
+    scale = max(float(v.abs().max()) for v in fr.values())
+    errs["dtheta"] = max(float((fg[k].grad.double().cpu() - fr[k]).abs().max()) / scale for k in fr)
+    print(inv, {k: f"{v:.2e}" for k, v in errs.items()}, "launches", E.last_launch_counts())
+    assert all(v < tol for v in errs.values()), errs
+
+
 def test_tensor_core_full_size_ns_subset():
     """BASELINE config 2 at full size through the tensor-core forward: random rows against the oracle."""
     cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
