@@ -27,7 +27,7 @@ template <int D, int H> struct TcCfg {
   static constexpr uint32_t WBLK = D * 128;            // bytes of one 64-feature block of a weight image
   static constexpr uint32_t ABLK = ROWS * 128;         // bytes of one 64-feature block of an activation tile
   static constexpr uint32_t ATILE = (D / 64) * ABLK;
-  static constexpr int TMEM_COLS = 3 * D <= 256 ? 256 : 512;   // T0 | T1 | RFF phases (D columns)
+  static constexpr int TMEM_COLS = (2 + H) * D <= 256 ? 256 : 512;   // T0 (also the RFF phases of the next latent) | T1 | H softmax accumulators
   // byte offsets inside the 1024-aligned dynamic shared memory
   static constexpr uint32_t OFF_W = 0;                 // W1_q, W1_v, W' images
   static constexpr uint32_t OFF_S = 3 * WIMG;          // W3[z,0] stage
@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = *s_tmem;
-  const uint32_t t0 = tm, t1 = tm + D, tp = tm + 2 * D;
+  // T0 doubles as the landing zone of the next latent's RFF phases (issued once E4_0 has read it), which leaves H x D columns
+  // for the softmax-weighted accumulators: they live in TMEM (tcgen05.ld / st once per latent and head), not in 64 registers
+  // per thread, so that the epilogues have registers for more than one dependent chain in flight.
+  const uint32_t t0 = tm, t1 = tm + D, tp = tm, tacc = tm + 2 * D;
   const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
   const uint32_t my_t = lane_off + col0;      // lane-quadrant / column offset of this warp
 
@@ -170,13 +173,17 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   }
 
   int xw = 0;                                  // which exchange buffer is next
-  float acc[H][32];
   float m_run[H], l_run[H];
+  {
+    float zero[32];
 #pragma unroll
-  for (int h = 0; h < H; ++h) {
-    m_run[h] = -INFINITY; l_run[h] = 0.f;
+    for (int j = 0; j < 32; ++j) zero[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[h][j] = 0.f;
+    for (int h = 0; h < H; ++h) {
+      m_run[h] = -INFINITY; l_run[h] = 0.f;
+      tc::tmem_st32(tacc + h * D + my_t, zero);
+    }
+    tc::tmem_st_wait();
   }
 
   for (int z = 0; z < P.Z; ++z) {
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       if (tid == 0) {
         if (z == 0) tc::mbar_wait(bar_w, 0);
         tc::tc_fence_after();
-        issue_gemm<D>(t0, aA0, aW, C::ABLK, C::WBLK);
+        issue_gemm<D>(t1, aA0, aW, C::ABLK, C::WBLK);         // T0 still holds the v half of the phases
         tc::mma_commit(bar_g1);
       }
       __syncwarp();
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     F_STAMP(3);
     if (tid == 0) {
       tc::tc_fence_after();
-      issue_gemm<D>(t1, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
+      issue_gemm<D>(t0, aA1, aW + C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(bar_g2);
     }
     const float win = s_win[par * ROWS + row];
@@ -228,35 +235,33 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::mbar_wait(bar_g1, par);
     tc::tc_fence_after();
     F_STAMP(5);
-    tc::tmem_ld32(t0 + my_t, v);
+    tc::tmem_ld32(t1 + my_t, v);
     tc::tmem_ld_wait();
     {
-      float part[H];
+      float2 part[H];                          // even / odd columns (packed FFMA2)
 #pragma unroll
-      for (int h = 0; h < H; ++h) part[h] = 0.f;
+      for (int h = 0; h < H; ++h) part[h] = tc::splat2(0.f);
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
         const float4 bb = *reinterpret_cast<const float4*>(s_bias + col0 + j4);
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-        float hq[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) hq[t] = fmaxf(v[j4 + t] + bv[t], 0.f);
+        float2 h01 = tc::add2(tc::ld2(v + j4), make_float2(bb.x, bb.y)), h23 = tc::add2(tc::ld2(v + j4 + 2), make_float2(bb.z, bb.w));
+        h01.x = fmaxf(h01.x, 0.f); h01.y = fmaxf(h01.y, 0.f); h23.x = fmaxf(h23.x, 0.f); h23.y = fmaxf(h23.y, 0.f);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const float4 uu = *reinterpret_cast<const float4*>(s_uz + h * D + col0 + j4);
-          part[h] = fmaf(hq[0], uu.x, part[h]); part[h] = fmaf(hq[1], uu.y, part[h]);
-          part[h] = fmaf(hq[2], uu.z, part[h]); part[h] = fmaf(hq[3], uu.w, part[h]);
+          part[h] = tc::fma2(h01, make_float2(uu.x, uu.y), part[h]);
+          part[h] = tc::fma2(h23, make_float2(uu.z, uu.w), part[h]);
         }
       }
 #pragma unroll
-      for (int h = 0; h < H; ++h) s_spart[(cq * ROWS + row) * H + h] = part[h];
+      for (int h = 0; h < H; ++h) s_spart[(cq * ROWS + row) * H + h] = part[h].x + part[h].y;
     }
     // ---- (d) E2: h1v = relu(T1 + b1v) -> A0 ----------------------------------------------------------------
     F_STAMP(6);
     tc::mbar_wait(bar_g2, par);
     tc::tc_fence_after();
     F_STAMP(7);
-    tc::tmem_ld32(t1 + my_t, v);
+    tc::tmem_ld32(t0 + my_t, v);
     tc::tmem_ld_wait();
 #pragma unroll
     for (int c8 = 0; c8 < 32; c8 += 8) {
@@ -265,7 +270,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       const float4 b1 = *reinterpret_cast<const float4*>(s_bias + D + col0 + c8 + 4);
       const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o[t] = fmaxf(v[c8 + t] + bv[t], 0.f);
+      for (int t = 0; t < 8; t += 2) {
+        const float2 pre = tc::add2(tc::ld2(v + c8 + t), tc::ld2(bv + t));
+        o[t] = fmaxf(pre.x, 0.f); o[t + 1] = fmaxf(pre.y, 0.f);
+      }
       tc::st_row8_bf16(sA0, C::ABLK, row, col0 + c8, o);
     }
     F_STAMP(8);
@@ -305,29 +313,20 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::tmem_ld32(t0 + my_t, v);
     tc::tmem_ld_wait();
     {
-      float st[2] = {0.f, 0.f};
-#pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(s_bias + 2 * D + col0 + j4);
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float g = gelu_fast(v[j4 + t] + bv[t]);
-          v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
-        }
-      }
+      float st[2];
+      gelu_rowsums32(v, s_bias + 2 * D + col0, st);
       F_STAMP(12);
       xw = 0;
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
       F_STAMP(13);
       const float mu = st[0] * (1.f / D);
       const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
-      const float nm = -mu * rstd;
+      const float2 rstd2 = tc::splat2(rstd), nm2 = tc::splat2(-mu * rstd);
 #pragma unroll
       for (int c8 = 0; c8 < 32; c8 += 8) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = fmaf(v[c8 + t], rstd, nm);
+        for (int t = 0; t < 8; t += 2) tc::st2(o + t, tc::fma2(tc::ld2(v + c8 + t), rstd2, nm2));
         tc::st_row8_bf16(sA1, C::ABLK, row, col0 + c8, o);
       }
     }
@@ -357,17 +356,6 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     if (more) {
       write_invariants(s_lam_next, par ^ 1);
       tc::fence_proxy_async();
-      if (warp == 0) {
-        tc::named_sync(6, C::NT);
-        if (tid == 0) {
-          tc::tc_fence_after();
-          issue_proj(tp, aU, aOm, D);
-          tc::mma_commit(bar_p);
-        }
-        __syncwarp();
-      } else {
-        tc::named_arrive(6, C::NT);
-      }
     }
     // ---- (f) E4: per head  m = T + b3 ; n = LN(gelu(m)) ; acc += p n --------------------------------------------
 #pragma unroll
@@ -381,41 +369,54 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       }
       tc::tmem_ld32((h == 0 ? t0 : t1) + my_t, v);
       tc::tmem_ld_wait();
-      float st[2] = {0.f, 0.f};
-#pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float g = gelu_fast(v[j4 + t] + bv[t]);
-          v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
+      if (h == 0 && more) {                   // T0 has been read by this thread: when everybody has, the next latent's phases land there
+        tc::tc_fence_before();
+        if (warp == 0) {
+          tc::named_sync(6, C::NT);
+          if (tid == 0) {
+            tc::tc_fence_after();
+            issue_proj(tp, aU, aOm, D);
+            tc::mma_commit(bar_p);
+          }
+          __syncwarp();
+        } else {
+          tc::named_arrive(6, C::NT);
         }
       }
+      float st[2];
+      gelu_rowsums32(v, s_b3 + h * D + col0, st);
+      float a[32];                            // the accumulator slab: requested now, first touched after the exchange
+      tc::tmem_ld32(tacc + h * D + my_t, a);
       xw = (h + 1) & 1;                       // E4_0 -> buffer 1 (the logit partials are dead), E4_1 -> buffer 0
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
       float mu = st[0] * (1.f / D);
       float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
-      float pr = pw[h] * rstd;
-      float tz = -pr * mu;
+      const float pr = pw[h] * rstd;
+      const float2 pr2 = tc::splat2(pr), tz2 = tc::splat2(-pr * mu), corr2 = tc::splat2(corr[h]);
+      tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[h][j] = fmaf(v[j], pr, fmaf(acc[h][j], corr[h], tz));
+      for (int j = 0; j < 32; j += 2) tc::st2(a + j, tc::fma2(tc::ld2(v + j), pr2, tc::fma2(tc::ld2(a + j), corr2, tz2)));
+      tc::tmem_st32(tacc + h * D + my_t, a);
       F_STAMP(17 + 2 * h);
     }
     if (tid == 0 && P.that_img) tc::bulk_wait_read0();      // the stash has been read out of A1 before the next latent overwrites it
+    tc::tmem_st_wait();
     tc::tc_fence_before();
     __syncthreads();
     F_STAMP(20);
   }
 
-  if (row_valid) {
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
+  for (int h = 0; h < H; ++h) {
+    float a[32];
+    tc::tmem_ld32(tacc + h * D + my_t, a);    // (warp-collective: outside the row_valid branch)
+    tc::tmem_ld_wait();
+    if (row_valid) {
       float inv_l = 1.f / l_run[h];
       float* o = P.nbar + (((int64_t)b * P.C + c0 + row) * H + h) * D + col0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(acc[h][j] * inv_l, acc[h][j + 1] * inv_l, acc[h][j + 2] * inv_l, acc[h][j + 3] * inv_l);
+        *reinterpret_cast<float4*>(o + j) = make_float4(a[j] * inv_l, a[j + 1] * inv_l, a[j + 2] * inv_l, a[j + 3] * inv_l);
       if (cq == 0) P.lse[((int64_t)b * P.C + c0 + row) * H + h] = m_run[h] + logf(l_run[h]);
     }
   }

@@ -33,6 +33,99 @@ __device__ __forceinline__ void gelu_fast_both(float x, float& g, float& dg) {
   dg = fmaf(g * fmaf(-2.f, s, 2.f), fmaf(3.f * c1, x2, c0), s);
 }
 
+// the same two functions on a pair of elements: FFMA2 / FMUL2 (tc::fma2 / mul2), each lane bit-identical to the scalar code above
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  const float2 x2 = tc::mul2(x, x);
+  const float2 a = tc::mul2(x, tc::fma2(tc::splat2(c1), x2, tc::splat2(c0)));
+  const float2 t = make_float2(tanh_fast(a.x), tanh_fast(a.y));
+  return tc::mul2(x, tc::fma2(tc::splat2(0.5f), t, tc::splat2(0.5f)));
+}
+__device__ __forceinline__ void gelu_fast_both2(float2 x, float2& g, float2& dg) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  const float2 x2 = tc::mul2(x, x);
+  const float2 a = tc::mul2(x, tc::fma2(tc::splat2(c1), x2, tc::splat2(c0)));
+  const float2 t = make_float2(tanh_fast(a.x), tanh_fast(a.y));
+  const float2 s = tc::fma2(tc::splat2(0.5f), t, tc::splat2(0.5f));
+  g = tc::mul2(x, s);
+  dg = tc::fma2(tc::mul2(g, tc::fma2(tc::splat2(-2.f), s, tc::splat2(2.f))), tc::fma2(tc::splat2(3.f * c1), x2, tc::splat2(c0)), s);
+}
+
+// Two independent pairs at once, written stage by stage: ptxas keeps the source order of these chains when registers are
+// tight (it otherwise runs one dependent FMUL2 -> FFMA2 -> FMUL2 -> MUFU -> FFMA2 -> FMUL2 chain after the other, 45
+// cycles of latency per pair with nothing of the same warp to fill it).
+__device__ __forceinline__ void gelu_fast2x2(float2 xa, float2 xb, float2& ga, float2& gb) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float2 pa = tc::mul2(xa, xa), pb = tc::mul2(xb, xb);
+  pa = tc::fma2(tc::splat2(c1), pa, tc::splat2(c0)); pb = tc::fma2(tc::splat2(c1), pb, tc::splat2(c0));
+  pa = tc::mul2(xa, pa); pb = tc::mul2(xb, pb);
+  pa.x = tanh_fast(pa.x); pb.x = tanh_fast(pb.x); pa.y = tanh_fast(pa.y); pb.y = tanh_fast(pb.y);
+  pa = tc::fma2(tc::splat2(0.5f), pa, tc::splat2(0.5f)); pb = tc::fma2(tc::splat2(0.5f), pb, tc::splat2(0.5f));
+  ga = tc::mul2(xa, pa); gb = tc::mul2(xb, pb);
+}
+__device__ __forceinline__ void gelu_fast_both2x2(float2 xa, float2 xb, float2& ga, float2& gb, float2& dga, float2& dgb) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  const float2 x2a = tc::mul2(xa, xa), x2b = tc::mul2(xb, xb);
+  float2 pa = tc::fma2(tc::splat2(c1), x2a, tc::splat2(c0)), pb = tc::fma2(tc::splat2(c1), x2b, tc::splat2(c0));
+  pa = tc::mul2(xa, pa); pb = tc::mul2(xb, pb);
+  pa.x = tanh_fast(pa.x); pb.x = tanh_fast(pb.x); pa.y = tanh_fast(pa.y); pb.y = tanh_fast(pb.y);
+  const float2 sa = tc::fma2(tc::splat2(0.5f), pa, tc::splat2(0.5f)), sb = tc::fma2(tc::splat2(0.5f), pb, tc::splat2(0.5f));
+  ga = tc::mul2(xa, sa); gb = tc::mul2(xb, sb);
+  const float2 ra = tc::fma2(tc::splat2(3.f * c1), x2a, tc::splat2(c0)), rb = tc::fma2(tc::splat2(3.f * c1), x2b, tc::splat2(c0));
+  const float2 qa = tc::mul2(ga, tc::fma2(tc::splat2(-2.f), sa, tc::splat2(2.f))), qb = tc::mul2(gb, tc::fma2(tc::splat2(-2.f), sb, tc::splat2(2.f)));
+  dga = tc::fma2(qa, ra, sa); dgb = tc::fma2(qb, rb, sb);
+}
+
+// v[j] <- g_j = gelu(v[j] + bias[j]) over a thread's 32 columns (bias: 16-byte aligned, shared memory); st = {sum g, sum g^2}
+// (even / odd partial sums).  The LayerNorm statistics of the forward (E3, E4) in packed form, eight columns at a time and
+// stage by stage, so that four independent chains (and their eight MUFU.TANH) are in flight per warp.
+__device__ __forceinline__ void gelu_rowsums32(float (&v)[32], const float* bias, float (&st)[2]) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float2 s0 = tc::splat2(0.f), s1 = tc::splat2(0.f);
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c8), b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
+    float2 x[4], p[4];
+    x[0] = tc::add2(tc::ld2(v + c8), make_float2(b0.x, b0.y)); x[1] = tc::add2(tc::ld2(v + c8 + 2), make_float2(b0.z, b0.w));
+    x[2] = tc::add2(tc::ld2(v + c8 + 4), make_float2(b1.x, b1.y)); x[3] = tc::add2(tc::ld2(v + c8 + 6), make_float2(b1.z, b1.w));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::mul2(x[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(c1), p[i], tc::splat2(c0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::mul2(x[i], p[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p[i].x = tanh_fast(p[i].x); p[i].y = tanh_fast(p[i].y); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(0.5f), p[i], tc::splat2(0.5f));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = tc::mul2(x[i], p[i]); tc::st2(v + c8 + 2 * i, x[i]); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s0 = tc::add2(s0, x[i]); s1 = tc::fma2(x[i], x[i], s1); }
+  }
+  st[0] = s0.x + s0.y; st[1] = s1.x + s1.y;
+}
+
+// cos of two RFF phases on the FMA pipe (packed), so that the XU pipe (4 lanes per scheduler: a warp-wide MUFU takes 8
+// cycles) only evaluates the sines: k = rint(ph / pi) by the magic-number add, r = ph - k pi (two-term Cody-Waite),
+// cos(ph) = (-1)^k P(r^2) with a degree-4 fit of cos(sqrt(y)) on [0, (pi/2)^2].  |error| <= 2.2e-7 for |ph| <= 300
+// (MUFU.COS: 3.6e-7 inside [-pi, pi], growing with |ph|).  Every kernel takes gamma from these helpers, so the
+// backward's recompute reproduces the forward's features bit for bit.
+__device__ __forceinline__ float2 cos2_fma(float2 ph) {
+  const float kMagic = 12582912.f;                      // 1.5 * 2^23: bit 0 of the sum is the parity of k
+  const float2 t = tc::fma2(ph, tc::splat2(0.318309886f), tc::splat2(kMagic));
+  const float2 k = tc::add2(t, tc::splat2(-kMagic));
+  float2 r = tc::fma2(k, tc::splat2(-3.14159274f), ph);
+  r = tc::fma2(k, tc::splat2(8.74227766e-8f), r);        // pi = 3.14159274f - 8.74227766e-8
+  const float2 y = tc::mul2(r, r);
+  float2 p = tc::fma2(y, tc::splat2(2.3121236154111102e-05f), tc::splat2(-0.001385227427817881f));
+  p = tc::fma2(y, p, tc::splat2(0.04166339337825775f));
+  p = tc::fma2(y, p, tc::splat2(-0.4999989867210388f));
+  p = tc::fma2(y, p, tc::splat2(0.9999999403953552f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) ^ (__float_as_uint(t.x) << 31)),
+                     __uint_as_float(__float_as_uint(p.y) ^ (__float_as_uint(t.y) << 31)));
+}
+
 struct Rec { float u[6]; float w; float c; };   // invariants, window value, raw cosine (spherical windows)
 
 // invariant row i of one (query, latent) pair: u_i = post(row_i(Lam, xi))
@@ -189,7 +282,10 @@ __device__ __forceinline__ void rff_from_proj(uint32_t t_proj, uint8_t* tile_hi,
   for (int c8 = 0; c8 < 16; c8 += 8) {
     float sn[8], cs[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { sn[t] = __sinf(ph[c8 + t]); cs[t] = __cosf(ph[c8 + t]); }
+    for (int t = 0; t < 8; t += 2) {
+      sn[t] = __sinf(ph[c8 + t]); sn[t + 1] = __sinf(ph[c8 + t + 1]);
+      tc::st2(cs + t, cos2_fma(tc::ld2(ph + c8 + t)));
+    }
     tc::st_row8_bf16(tile_hi, ablk, row, j0 + c8, sn);
     tc::st_row8_bf16(tile_hi, ablk, row, HD + j0 + c8, cs);
     if (SPLIT) {
@@ -213,7 +309,10 @@ __device__ __forceinline__ void rff_half_from_proj(uint32_t t_proj, uint8_t* til
   for (int c8 = 0; c8 < 16; c8 += 8) {
     float v[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = SIN ? __sinf(ph[c8 + t]) : __cosf(ph[c8 + t]);
+    for (int t = 0; t < 8; t += 2) {
+      if (SIN) { v[t] = __sinf(ph[c8 + t]); v[t + 1] = __sinf(ph[c8 + t + 1]); }
+      else tc::st2(v + t, cos2_fma(tc::ld2(ph + c8 + t)));
+    }
     tc::st_row8_bf16(tile_hi, ablk, row, (SIN ? 0 : HD) + j0 + c8, v);
     if (SPLIT) {
 #pragma unroll
