@@ -301,28 +301,21 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
         float dg[32];
         uint32_t gh[16];                               // g, packed to fp16 once the row sums have seen it in fp32 (it only re-enters
                                                        // through the small LayerNorm projection term of dm): 16 registers instead of 32
-        float st[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_b3 + h * D + col0 + j4);
-          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float g;
-            gelu_fast_both(v[j4 + t] + bv[t], g, dg[j4 + t]);
-            v[j4 + t] = g; st[0] += g; st[1] = fmaf(g, g, st[1]);
-          }
-        }
+        float st[4];
+        gelu_both_rowsums32(v, s_b3 + h * D + col0, dg, st);
         // the cotangent rows were requested one phase ago; touching them only now keeps their L2 latency off the gelu pass
+        {
+          float2 s2 = tc::splat2(0.f), s3 = tc::splat2(0.f);
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[j4 >> 3]) + ((j4 & 4) >> 1);     // dnb[j4 .. j4 + 3], packed
-          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
-          st[2] = fmaf(d01.x, v[j4], st[2]); st[2] = fmaf(d01.y, v[j4 + 1], st[2]);
-          st[2] = fmaf(d23.x, v[j4 + 2], st[2]); st[2] = fmaf(d23.y, v[j4 + 3], st[2]);
-          st[3] += (d01.x + d01.y) + (d23.x + d23.y);
-          gh[j4 >> 1] = tc::pack_bf16(v[j4], v[j4 + 1]);
-          gh[(j4 >> 1) + 1] = tc::pack_bf16(v[j4 + 2], v[j4 + 3]);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[j4 >> 3]) + ((j4 & 4) >> 1);     // dnb[j4 .. j4 + 3], packed
+            const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
+            s2 = tc::fma2(d01, tc::ld2(v + j4), s2); s3 = tc::add2(s3, d01);
+            s2 = tc::fma2(d23, tc::ld2(v + j4 + 2), s2); s3 = tc::add2(s3, d23);
+            gh[j4 >> 1] = tc::pack_bf16(v[j4], v[j4 + 1]);
+            gh[(j4 >> 1) + 1] = tc::pack_bf16(v[j4 + 2], v[j4 + 3]);
+          }
+          st[2] = s2.x + s2.y; st[3] = s3.x + s3.y;
         }
         A_STAMP(32, 4 + 8 * h);
         row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
@@ -350,8 +343,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
-            dg[c8 + 2 * t] = fmaf(-gv.x, kb, fmaf(ka, dv.x, kc)) * dg[c8 + 2 * t];
-            dg[c8 + 2 * t + 1] = fmaf(-gv.y, kb, fmaf(ka, dv.y, kc)) * dg[c8 + 2 * t + 1];
+            tc::st2(dg + c8 + 2 * t, tc::mul2(tc::fma2(gv, tc::splat2(-kb), tc::fma2(tc::splat2(ka), dv, tc::splat2(kc))), tc::ld2(dg + c8 + 2 * t)));
           }
           tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dg + c8);
         }

@@ -360,16 +360,13 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           for (int h = 0; h < H; ++h) uu[h] = *reinterpret_cast<const float4*>(s_us + h * D + col0 + c8 + q4);
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float hq = fmaxf(v[c8 + q4 + t] + bv[t], 0.f);
-            float a = 0.f;
+          for (int t = 0; t < 4; t += 2) {
+            const float2 pre = tc::add2(tc::ld2(v + c8 + q4 + t), tc::ld2(bv + t));
+            float2 a = tc::mul2(tc::splat2(dsv[0]), t == 0 ? make_float2(uu[0].x, uu[0].y) : make_float2(uu[0].z, uu[0].w));
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-              const float uh = t == 0 ? uu[h].x : t == 1 ? uu[h].y : t == 2 ? uu[h].z : uu[h].w;
-              a = fmaf(dsv[h], uh, a);
-            }
-            oh[q4 + t] = hq;
-            oz[q4 + t] = hq > 0.f ? a : 0.f;
+            for (int h = 1; h < H; ++h) a = tc::fma2(tc::splat2(dsv[h]), t == 0 ? make_float2(uu[h].x, uu[h].y) : make_float2(uu[h].z, uu[h].w), a);
+            oh[q4 + t] = fmaxf(pre.x, 0.f); oh[q4 + t + 1] = fmaxf(pre.y, 0.f);
+            oz[q4 + t] = pre.x > 0.f ? a.x : 0.f; oz[q4 + t + 1] = pre.y > 0.f ? a.y : 0.f;
           }
         }
         tc::st_row8_bf16(sGlo, C::ABLK, row, col0 + c8, oh);
@@ -418,9 +415,8 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           float o[8];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 sn = __half22float2(hs[t]), cs = __half22float2(hc[t]);
-            o[2 * t] = cs.x * dsn[c8 + 2 * t] - sn.x * dcs[c8 + 2 * t];
-            o[2 * t + 1] = cs.y * dsn[c8 + 2 * t + 1] - sn.y * dcs[c8 + 2 * t + 1];
+            const float2 nsn = __half22float2(__hneg2(hs[t])), cs = __half22float2(hc[t]);       // d sin = cos, d cos = -sin
+            tc::st2(o + 2 * t, tc::fma2(nsn, tc::ld2(dcs + c8 + 2 * t), tc::mul2(cs, tc::ld2(dsn + c8 + 2 * t))));
           }
           tc::st_row8_bf16(sGlo, C::ABLK, row, col, o);             // h1q's MMA was issued before the dgrad: it is complete
         }

@@ -106,6 +106,76 @@ __device__ __forceinline__ void gelu_rowsums32(float (&v)[32], const float* bias
   st[0] = s0.x + s0.y; st[1] = s1.x + s1.y;
 }
 
+// Same pass for the backward kernels: v[j] <- g_j, dg[j] <- gelu'(v[j] + bias[j]); st[0] = sum g, st[1] = sum g^2.
+__device__ __forceinline__ void gelu_both_rowsums32(float (&v)[32], const float* bias, float (&dg)[32], float (&st)[4]) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float2 s0 = tc::splat2(0.f), s1 = tc::splat2(0.f);
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c8), b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
+    float2 x[4], x2[4], p[4], r[4];
+    x[0] = tc::add2(tc::ld2(v + c8), make_float2(b0.x, b0.y)); x[1] = tc::add2(tc::ld2(v + c8 + 2), make_float2(b0.z, b0.w));
+    x[2] = tc::add2(tc::ld2(v + c8 + 4), make_float2(b1.x, b1.y)); x[3] = tc::add2(tc::ld2(v + c8 + 6), make_float2(b1.z, b1.w));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x2[i] = tc::mul2(x[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(c1), x2[i], tc::splat2(c0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::mul2(x[i], p[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p[i].x = tanh_fast(p[i].x); p[i].y = tanh_fast(p[i].y); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = tc::fma2(tc::splat2(3.f * c1), x2[i], tc::splat2(c0));       // in the shadow of the tanh
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(0.5f), p[i], tc::splat2(0.5f));          // s
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = tc::mul2(x[i], p[i]); tc::st2(v + c8 + 2 * i, x[i]); }       // g
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x2[i] = tc::mul2(x[i], tc::fma2(tc::splat2(-2.f), p[i], tc::splat2(2.f)));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::st2(dg + c8 + 2 * i, tc::fma2(x2[i], r[i], p[i]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s0 = tc::add2(s0, x[i]); s1 = tc::fma2(x[i], x[i], s1); }
+  }
+  st[0] = s0.x + s0.y; st[1] = s1.x + s1.y;
+}
+
+// Eight columns of the LayerNorm / gelu backward's first pass with everything it feeds folded in (register-minimal form of
+// the pass above): x = v + bias; g = gelu(x) -> gh (packed fp16, after the row sums have seen it in fp32); dg = gelu'(x);
+// s0 += g, s1 += g^2, s2 += dth g, s3 += dth, with dth the (packed fp16) cotangent of the LayerNorm output.
+__device__ __forceinline__ void gelu_both_stats8(const float* v, const float* bias, const uint4& dth, float* dg, uint32_t* gh, float2& s0,
+                                                 float2& s1, float2& s2, float2& s3) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+  float2 x[4], x2[4], p[4];
+  x[0] = tc::add2(tc::ld2(v), make_float2(b0.x, b0.y)); x[1] = tc::add2(tc::ld2(v + 2), make_float2(b0.z, b0.w));
+  x[2] = tc::add2(tc::ld2(v + 4), make_float2(b1.x, b1.y)); x[3] = tc::add2(tc::ld2(v + 6), make_float2(b1.z, b1.w));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x2[i] = tc::mul2(x[i], x[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(c1), x2[i], tc::splat2(c0));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = tc::mul2(x[i], p[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { p[i].x = tanh_fast(p[i].x); p[i].y = tanh_fast(p[i].y); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x2[i] = tc::fma2(tc::splat2(3.f * c1), x2[i], tc::splat2(c0));       // in the shadow of the tanh
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(0.5f), p[i], tc::splat2(0.5f));          // s
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = tc::mul2(x[i], p[i]);                                         // g
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tc::st2(dg + 2 * i, tc::fma2(tc::mul2(x[i], tc::fma2(tc::splat2(-2.f), p[i], tc::splat2(2.f))), x2[i], p[i]));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&dth);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 d = __half22float2(h2[i]);
+    s0 = tc::add2(s0, x[i]); s1 = tc::fma2(x[i], x[i], s1);
+    s2 = tc::fma2(d, x[i], s2); s3 = tc::add2(s3, d);
+    gh[i] = tc::pack_bf16(x[i].x, x[i].y);
+  }
+}
+
 // cos of two RFF phases on the FMA pipe (packed), so that the XU pipe (4 lanes per scheduler: a warp-wide MUFU takes 8
 // cycles) only evaluates the sines: k = rint(ph / pi) by the magic-number add, r = ph - k pi (two-term Cody-Waite),
 // cos(ph) = (-1)^k P(r^2) with a degree-4 fit of cos(sqrt(y)) on [0, (pi/2)^2].  |error| <= 2.2e-7 for |ph| <= 300
@@ -284,6 +354,9 @@ __device__ __forceinline__ void rff_from_proj(uint32_t t_proj, uint8_t* tile_hi,
 #pragma unroll
     for (int t = 0; t < 8; t += 2) {
       sn[t] = __sinf(ph[c8 + t]); sn[t + 1] = __sinf(ph[c8 + t + 1]);
+#ifdef ENF_COS_MUFU_SPLIT
+      if (SPLIT) { cs[t] = __cosf(ph[c8 + t]); cs[t + 1] = __cosf(ph[c8 + t + 1]); } else
+#endif
       tc::st2(cs + t, cos2_fma(tc::ld2(ph + c8 + t)));
     }
     tc::st_row8_bf16(tile_hi, ablk, row, j0 + c8, sn);
@@ -311,6 +384,9 @@ __device__ __forceinline__ void rff_half_from_proj(uint32_t t_proj, uint8_t* til
 #pragma unroll
     for (int t = 0; t < 8; t += 2) {
       if (SIN) { v[t] = __sinf(ph[c8 + t]); v[t + 1] = __sinf(ph[c8 + t + 1]); }
+#ifdef ENF_COS_MUFU_SPLIT
+      else if (SPLIT) { v[t] = __cosf(ph[c8 + t]); v[t + 1] = __cosf(ph[c8 + t + 1]); }
+#endif
       else tc::st2(v + t, cos2_fma(tc::ld2(ph + c8 + t)));
     }
     tc::st_row8_bf16(tile_hi, ablk, row, (SIN ? 0 : HD) + j0 + c8, v);
