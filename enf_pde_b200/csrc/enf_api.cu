@@ -115,6 +115,8 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
       Y.add("dbg", 8192);
       // fp16 operand images of `that` per (field, latent, 128-query tile), stashed by the forward for backward kernel A
       Y.add("that_img", BZ * (size_t)((D.C + 127) / 128) * 128 * d / 2);
+      // rstd * gelu' of the same layer (fp16), stashed for backward kernel B: with `that` it is all the LayerNorm / gelu backward needs
+      Y.add("dgr", BZ * Cpad * d / 2); Y.add("trstd", BZ * Cpad);
     }
   }
   Y.add("xi", BC * ENF_F_XI);
@@ -396,6 +398,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
     tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = train ? c.f("slog") : nullptr;
     tp.that_img = (train && use_tc_bwd(D)) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
+    tp.dgr = (train && use_tc_bwd(D)) ? reinterpret_cast<uint4*>(c.f("dgr")) : nullptr;
+    tp.trstd = (train && use_tc_bwd(D)) ? c.f("trstd") : nullptr;
     static const bool trace_fwd = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace_fwd ? reinterpret_cast<long long*>(c.f("dbg_fwd")) : nullptr;
     prof_mark(0, 0, st);
@@ -549,6 +553,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.U = pp.U; tp.b3 = pp.b3; tp.slog = c.f("slog"); tp.lse = pp.lse; tp.nbar = pp.nbar;
     tp.dnbar = c.f("s0"); tp.Dg = c.f("Dg"); tp.gmax = c.f("gmax"); tp.dnb16 = reinterpret_cast<uint4*>(c.f("dnb16"));
     tp.that_img = reinterpret_cast<const uint8_t*>(c.f("that_img"));
+    tp.dgr = reinterpret_cast<const uint4*>(c.f("dgr")); tp.trstd = c.f("trstd");
     static const bool trace = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace ? reinterpret_cast<long long*>(c.f("dbg")) : nullptr;
     tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");

@@ -177,6 +177,9 @@ struct EnfPairTcParams {
   float* nbar; float* lse; float* slog;      // slog [B,Z,C,H]: logits incl. window (saved for the backward), may be null
   uint8_t* that_img;                         // [B,Z,ceil(C/128)] operand images (128 rows x d, fp16, swizzled) of that = LN(gelu(.)),
                                              // stashed for backward kernel A; may be null (forward only / SIMT backward)
+  uint4* dgr;                                // gelu'(tpre) of the same layer, fp16, in backward kernel B's load order (the chunked
+                                             // order of dthat below); stashed together with that_img, null when that is
+  float* trstd;                              // [B,Z,ceil(C/128)*128] reciprocal standard deviation of that LayerNorm (with dgr)
   long long* dbg;                            // optional clock64() trace of one CTA (diagnostics; null in production)
 };
 bool enf_pairs_fwd_tc_supported(int d, int H);
@@ -195,6 +198,8 @@ struct EnfPairTcBwdParams {
   const float* U; const float* b3;
   const float* slog; const float* lse; const float* nbar;   // forward state
   const uint8_t* that_img;                   // [B,Z,ceil(C/128)] that operand images stashed by the forward
+  const uint4* dgr;                          // gelu'(tpre), fp16, chunked order of dthat (stashed by the forward for kernel B)
+  const float* trstd;                        // [B,Z,ceil(C/128)*128] rstd of the LayerNorm producing that (stashed by the forward)
   const float* dnbar;                        // [B,C,H,d] cotangent of nbar
   float* Dg;                                 // [B,C,H]   dnbar16 . nbar              (written by the prep kernels)
   float* gmax;                               // [1]       max |dnbar| (zero-initialised; written by the prep kernels)

@@ -35,7 +35,9 @@ template <int D, int H> struct TcCfg {
   static constexpr uint32_t OFF_A1 = OFF_A0 + ATILE;
   static constexpr uint32_t OFF_U = OFF_A1 + ATILE;    // projection operand: invariants of the 128 rows (2 atoms)
   static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;   // projection operand: [Omega_q | Omega_v] (D / 64 atoms)
-  static constexpr uint32_t OFF_F = OFF_OM + (D / 64) * kProjAtom;    // float arrays start here
+  // staging of the backward's stash rstd * gelu' (one activation tile): the W3 stage buffer where that is large enough (d = 128)
+  static constexpr uint32_t OFF_G = OFF_OM + (D / 64) * kProjAtom;
+  static constexpr uint32_t OFF_F = OFF_G + (WIMG >= ATILE ? 0 : ATILE);    // float arrays start here
   // float arrays (counts)
   // per-latent vectors are double buffered (cp.async prefetch of the next latent): [2] x { Lam 64 | U H*D | b3 H*D | kappa, sigma 8 }
   static constexpr int F_LAT = 64 + 2 * H * D + 8;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
   uint8_t* sA1 = base + C::OFF_A1;
   uint8_t* sU = base + C::OFF_U;
   uint8_t* sOm = base + C::OFF_OM;
+  uint8_t* sG = C::WIMG >= C::ATILE ? sS : base + C::OFF_G;
   float* f = reinterpret_cast<float*>(base + C::OFF_F);
   float* s_lat = f; f += 2 * C::F_LAT;        // [2] per-latent vectors of this and the next latent
   float* s_win = f; f += C::F_WIN;            // [2][ROWS]: window values of this and the next latent
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       l_run[h] = l_run[h] * corr[h] + pw[h];
       m_run[h] = m_new;
     }
+    uint32_t dgh[16];                          // my 32 columns of the backward's stash gelu'(tpre) (fp16), parked E3 -> E4_0
     // ---- (e) E3: g = gelu(T0 + b'), row statistics, LayerNorm -> A1 ----
     F_STAMP(10);
     tc::mbar_wait(bar_g3, par);
@@ -314,7 +318,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
     tc::tmem_ld_wait();
     {
       float st[2];
-      gelu_rowsums32(v, s_bias + 2 * D + col0, st);
+      if (P.dgr) gelu_rowsums32_stash(v, s_bias + 2 * D + col0, dgh, st);      // + gelu' of this layer, packed, for the backward
+      else gelu_rowsums32(v, s_bias + 2 * D + col0, st);
       F_STAMP(12);
       xw = 0;
       row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
@@ -329,6 +334,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
         for (int t = 0; t < 8; t += 2) tc::st2(o + t, tc::fma2(tc::ld2(v + c8 + t), rstd2, nm2));
         tc::st_row8_bf16(sA1, C::ABLK, row, col0 + c8, o);
       }
+      if (P.dgr && cq == 0) P.trstd[(size_t)bz * gridDim.x * ROWS + c0 + row] = rstd;
     }
     F_STAMP(14);
     tc::cp_async_wait_all();                  // the next latent's vectors (requested at the top) are visible after this barrier
@@ -363,20 +369,32 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       tc::mbar_wait(&bar_g4[h], par);
       tc::tc_fence_after();
       F_STAMP(16 + 2 * h);
-      if (h == 0 && tid == 0 && more) {       // stage buffer is free: prefetch next latent's W3[.,0]
-        tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
-        tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
-      }
       tc::tmem_ld32((h == 0 ? t0 : t1) + my_t, v);
       tc::tmem_ld_wait();
-      if (h == 0 && more) {                   // T0 has been read by this thread: when everybody has, the next latent's phases land there
+      if (h == 0 && (more || P.dgr)) {
+        // GEMM4_0 is complete, so the W3 stage buffer is free: it stages the backward's stash rstd * gelu' (in kernel B's load
+        // order [column quarter][chunk][row] x 16 bytes), which then leaves by ONE bulk store -- 64 STG.128 per CTA in a burst
+        // stalled every warp on the SM's store path instead.  T0 has been read by this thread: when everybody has, the next
+        // latent's phases land there.
+        if (P.dgr) {
+          uint4* stage = reinterpret_cast<uint4*>(sG) + cq * 4 * ROWS + row;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) stage[q * ROWS] = make_uint4(dgh[4 * q], dgh[4 * q + 1], dgh[4 * q + 2], dgh[4 * q + 3]);
+          tc::fence_proxy_async();
+        }
         tc::tc_fence_before();
         if (warp == 0) {
           tc::named_sync(6, C::NT);
           if (tid == 0) {
-            tc::tc_fence_after();
-            issue_proj(tp, aU, aOm, D);
-            tc::mma_commit(bar_p);
+            if (more) {
+              tc::tc_fence_after();
+              issue_proj(tp, aU, aOm, D);
+              tc::mma_commit(bar_p);
+            }
+            if (P.dgr) {
+              tc::bulk_s2g(P.dgr + ((size_t)bz * gridDim.x + blockIdx.x) * (C::ATILE / 16), sG, C::ATILE);
+              tc::bulk_commit();
+            }
           }
           __syncwarp();
         } else {
@@ -399,7 +417,13 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPai
       tc::tmem_st32(tacc + h * D + my_t, a);
       F_STAMP(17 + 2 * h);
     }
-    if (tid == 0 && P.that_img) tc::bulk_wait_read0();      // the stash has been read out of A1 before the next latent overwrites it
+    if (tid == 0) {
+      if (P.that_img) tc::bulk_wait_read0();   // the stashes have been read out of A1 / the stage buffer before they are overwritten
+      if (more) {                              // stage buffer: next latent's W3[.,0] (needed by its GEMM4_0, most of a latent away)
+        tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
+        tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+      }
+    }
     tc::tmem_st_wait();
     tc::tc_fence_before();
     __syncthreads();

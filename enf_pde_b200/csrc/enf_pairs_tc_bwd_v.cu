@@ -4,9 +4,10 @@
 // Persistent CTAs walk (field, latent) items; per item they walk the field's query tiles (128 rows each):
 //     S1  gamma_v (hi | lo fp16 split) from the RFF phases the tensor core left in TMEM
 //     M1  T    = gamma_v W1_v                 (3-term split product: the relu mask decides whole gradient entries)
+//     E3  (in M1's shadow) dtpre = (dthat - mean(dthat) - that mean(dthat that)) * (rstd gelu'(tpre))   -> operand tile
+//         = LayerNorm / gelu backward from three fp16 streams: dthat (kernel A) and the forward's stashes `that`, `dgr` (+ rstd per row);
+//         nothing of the layer above h1v is recomputed here (no h1v W' product, no tanh)
 //     E2  h1v  = relu(T + b1v)  -> operand tile ; mask bits stay in a register
-//     M2  T    = h1v W'
-//     E3  tpre = T + b' ; g, g' ; that = LN(g) ; dtpre = LNbwd(dthat from kernel A) g'          -> operand tile
 //     M3  T    = dtpre W'^T     dW' += h1v^T dtpre     db' += dtpre^T 1
 //     E4  dzv  = T [h1v > 0]                                                                    -> operand tile
 //     M4  T    = dzv W1_v^T (d gamma_v)     dW1_v += gamma_v^T dzv     db1v += dzv^T 1
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
   float* s_bias = f; f += 2 * D;                      // b1v | bp
   float* s_exch = f; f += C::NQ * ROWS * 4;          // one buffer: a single exchange per tile, block barriers in between
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
-  uint64_t *bar_w = bars, *bar_p = bars + 1, *bar_g1 = bars + 2, *bar_g2 = bars + 3, *bar_g3 = bars + 4, *bar_g3b = bars + 5,
+  uint64_t *bar_w = bars, *bar_p = bars + 1, *bar_g1 = bars + 2, *bar_t = bars + 3, *bar_g3 = bars + 4, *bar_g3b = bars + 5,
            *bar_g4 = bars + 6, *bar_u = bars + 7;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -214,10 +215,12 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       const int c0 = ct * ROWS;
       const bool valid = c0 + row < P.C;
       const int64_t pr = bz * P.C + c0 + row;
-      // cotangent of that (kernel A), my 32 columns, fp16: in flight until E3
-      uint4 dthq[4];
+      // my 32 columns of the three fp16 streams of E3: cotangent of that (kernel A), that and rstd * gelu' (stashed by the
+      // forward); requested here, first touched after S1
+      uint4 dthq[4], dgq[4];
+      const int64_t chunked = ((bz * ntiles + ct) * C::NQ + cq) * 4 * ROWS + row;
       {
-        const uint4* src = reinterpret_cast<const uint4*>(P.dthat) + ((bz * ntiles + ct) * C::NQ + cq) * 4 * ROWS + row;
+        const uint4* src = reinterpret_cast<const uint4*>(P.dthat) + chunked;
 #pragma unroll
         for (int q = 0; q < 4; ++q) dthq[q] = valid ? __ldg(src + q * ROWS) : make_uint4(0u, 0u, 0u, 0u);
       }
@@ -225,6 +228,10 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       if (it > 0) {                                        // every MMA of the previous tile is done with the operand tiles
         tc::mbar_wait(bar_u, (it - 1) & 1);
         tc::tc_fence_after();
+      }
+      if (tid == MMA_TID) {                                // the `that` operand image of this tile -> the (free) dtpre tile: E3 reads
+        tc::mbar_expect_tx(bar_t, C::ATILE);               // its own chunks from there and overwrites them in place
+        tc::bulk_g2s(sDt, P.that_img + (size_t)(bz * ntiles + ct) * C::ATILE, C::ATILE, bar_t);
       }
       if (cq == 1 && ct > 0) store_du(ct - 1, (it - 1) & 1);      // previous tile's du -> duv (the item's last tile: at its flush)
       // ---- S1: gamma_v hi / lo ---------------------------------------------------------------------------------
@@ -250,6 +257,12 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       } else {
         tc::named_arrive(5, C::NT);
       }
+      {                                                    // second stream of E3 (all CTAs reach their tile tops together: the
+        const uint4* srg = P.dgr + chunked;                // requests are staggered so that they do not queue behind each other)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dgq[q] = valid ? __ldg(srg + q * ROWS) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const float trs = valid ? __ldg(P.trstd + (size_t)bz * ntiles * ROWS + c0 + row) : 0.f;
       rff_half_from_proj<D, true, false>(tP + lane_off + 16 * cq, sGhi, sX, C::ABLK, row, 16 * cq);
       V_STAMP(3);
       tc::tc_fence_before();
@@ -263,12 +276,52 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, KH, 2 * KH, 1);
         tc::mma_commit(bar_g1);
       }
-      // next tile's invariants -> projection operand (overlaps the 3-term GEMM; tP was read by everyone before the barrier)
-      if (cq == 0 && ct + 1 < ntiles) {                    // (loading xi here, not a phase earlier: it would only be spilled across S1)
-        float xi_next[8];
-        load_xi(ct + 1, xi_next);
-        write_invariants(xi_next);
+      // ---- in the shadow of the 3-term GEMM: E3 and the next tile's invariants -----------------------------------------
+      float xi_next[8];
+      if (cq == 0 && ct + 1 < ntiles) load_xi(ct + 1, xi_next);      // requested now, used after E3
+      {
+        // LayerNorm backward needs the row sums  sum_j dth_j  and  sum_j dth_j that_j
+        uint4 thq[4];
+        tc::mbar_wait(bar_t, par);
+        {
+          const uint8_t* trow = sDt + (col0 >> 6) * C::ABLK;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            thq[q] = valid ? *reinterpret_cast<const uint4*>(trow + tc::swz_chunk_off(row, ((col0 & 63) >> 3) + q)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float st[2];
+        {
+          float2 s2 = tc::splat2(0.f), s3 = tc::splat2(0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __half2* hd = reinterpret_cast<const __half2*>(&dthq[q]);
+            const __half2* ht = reinterpret_cast<const __half2*>(&thq[q]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 d = __half22float2(hd[t]);
+              s2 = tc::fma2(d, __half22float2(ht[t]), s2); s3 = tc::add2(s3, d);
+            }
+          }
+          st[0] = s2.x + s2.y; st[1] = s3.x + s3.y;
+        }
+        xw = 0;
+        row_exchange<C::NQ, 2>(s_exch, xw, cq, row, lq, st);
+        const float2 nm2 = tc::splat2(-st[0] * (1.f / D) * trs), nm1 = tc::splat2(-st[1] * (1.f / D) * trs), rs2 = tc::splat2(trs);
+        // dtpre = rstd (dth - m1 - that m2) g'
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __half2* hd = reinterpret_cast<const __half2*>(&dthq[q]);
+          const __half2* ht = reinterpret_cast<const __half2*>(&thq[q]);
+          const __half2* hg = reinterpret_cast<const __half2*>(&dgq[q]);
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            tc::st2(o + 2 * t, tc::mul2(tc::fma2(__half22float2(ht[t]), nm2, tc::fma2(__half22float2(hd[t]), rs2, nm1)), __half22float2(hg[t])));
+          tc::st_row8_bf16(sDt, C::ABLK, row, col0 + 8 * q, o);
+        }
       }
+      // next tile's invariants -> projection operand (tP was read by everyone before the barrier)
+      if (cq == 0 && ct + 1 < ntiles) write_invariants(xi_next);
       // ---- E2: h1v, mask ---------------------------------------------------------------------------------------------
       float v[32];
       V_STAMP(5);
@@ -299,76 +352,17 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       V_STAMP(8);
       if (tid == MMA_TID) {
         tc::tc_fence_after();
-        issue_gemm<D>(tT, aX, aWp, C::ABLK, C::WBLK);
-        tc::mma_commit(bar_g2);
-        if (ct + 1 < ntiles) {                             // phases of the next tile (sU was written before the barrier)
-          issue_proj(tP, aU, aOm, HD);
-          tc::mma_commit(bar_p);
-        }
-      }
-      // ---- E3: tpre -> g, g', that ; dtpre ------------------------------------------------------------------------
-      tc::mbar_wait(bar_g2, par);
-      tc::tc_fence_after();
-      V_STAMP(9);
-      tc::tmem_ld32(tT + my_t, v);
-      tc::tmem_ld_wait();
-      {
-        // one pass, one exchange: with g = gelu(tpre), that = (g - mu) rstd the LayerNorm backward needs
-        //   sum_j dth_j   and   sum_j dth_j that_j = rstd (sum dth g - mu sum dth)
-        float dg[32];
-        uint32_t gh[16];                                   // g packed to fp16 once the row sums have seen it in fp32 (16 registers, not 32)
-        float st[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + D + col0 + j4);
-          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-          const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[j4 >> 3]) + ((j4 & 4) >> 1);     // dthat[j4 .. j4 + 3], still packed
-          const float2 d01 = __half22float2(h2[0]), d23 = __half22float2(h2[1]);
-          const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
-          float g[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            gelu_fast_both(v[j4 + t] + bv[t], g[t], dg[j4 + t]);
-            st[0] += g[t]; st[1] = fmaf(g[t], g[t], st[1]);
-            st[2] = fmaf(dv[t], g[t], st[2]); st[3] += dv[t];
-          }
-          gh[j4 >> 1] = tc::pack_bf16(g[0], g[1]);
-          gh[(j4 >> 1) + 1] = tc::pack_bf16(g[2], g[3]);
-        }
-        xw = 0;
-        row_exchange<C::NQ, 4>(s_exch, xw, cq, row, lq, st);
-        const float mu = st[0] * (1.f / D);
-        const float rstd = rsqrtf(fmaxf(st[1] * (1.f / D) - mu * mu, 0.f) + 1e-6f);
-        const float m1 = st[3] * (1.f / D), m2 = rstd * (st[2] - mu * st[3]) * (1.f / D);
-        // dtpre = rstd (dth - m1 - that m2) g'   with that = (g - mu) rstd, constants folded
-        const float kc = rstd * (mu * rstd * m2 - m1), kb = rstd * rstd * m2;
-#pragma unroll
-        for (int c8 = 0; c8 < 32; c8 += 8) {
-          const __half2* h2 = reinterpret_cast<const __half2*>(&dthq[c8 >> 3]);
-          const __half2* g2 = reinterpret_cast<const __half2*>(&gh[c8 >> 1]);
-          float o[8];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
-            o[2 * t] = fmaf(-gv.x, kb, fmaf(rstd, dv.x, kc)) * dg[c8 + 2 * t];
-            o[2 * t + 1] = fmaf(-gv.y, kb, fmaf(rstd, dv.y, kc)) * dg[c8 + 2 * t + 1];
-          }
-          tc::st_row8_bf16(sDt, C::ABLK, row, col0 + c8, o);
-        }
-      }
-      V_STAMP(10);
-      tc::tc_fence_before();
-      tc::fence_proxy_async();
-      __syncthreads();
-      V_STAMP(11);
-      if (tid == MMA_TID) {
-        tc::tc_fence_after();
         issue_dgrad<D>(tT, aDt, aWp, C::ABLK, C::WBLK, 0);          // d h1v
         tc::mma_commit(bar_g3);
         issue_wgrad<D>(tWp, aX, aDt, C::ABLK, it > 0);              // dW' (per CTA)
         issue_colsum<D>(tS1, aDt, aOne, C::ABLK, it > 0);           // db' (per CTA)
         tc::mma_commit(bar_g3b);
+        if (ct + 1 < ntiles) {                             // phases of the next tile (sU was written before the barrier)
+          issue_proj(tP, aU, aOm, HD);
+          tc::mma_commit(bar_p);
+        }
       }
+      V_STAMP(9); V_STAMP(10); V_STAMP(11);
       // ---- E4: dzv = d h1v [h1v > 0] ----------------------------------------------------------------------------------
       tc::mbar_wait(bar_g3, par);
       tc::tc_fence_after();

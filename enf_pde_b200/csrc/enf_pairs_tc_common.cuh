@@ -113,7 +113,7 @@ __device__ __forceinline__ void gelu_both_rowsums32(float (&v)[32], const float*
 #pragma unroll
   for (int c8 = 0; c8 < 32; c8 += 8) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias + c8), b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
-    float2 x[4], x2[4], p[4], r[4];
+    float2 x[4], x2[4], p[4];
     x[0] = tc::add2(tc::ld2(v + c8), make_float2(b0.x, b0.y)); x[1] = tc::add2(tc::ld2(v + c8 + 2), make_float2(b0.z, b0.w));
     x[2] = tc::add2(tc::ld2(v + c8 + 4), make_float2(b1.x, b1.y)); x[3] = tc::add2(tc::ld2(v + c8 + 6), make_float2(b1.z, b1.w));
 #pragma unroll
@@ -125,15 +125,49 @@ __device__ __forceinline__ void gelu_both_rowsums32(float (&v)[32], const float*
 #pragma unroll
     for (int i = 0; i < 4; ++i) { p[i].x = tanh_fast(p[i].x); p[i].y = tanh_fast(p[i].y); }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = tc::fma2(tc::splat2(3.f * c1), x2[i], tc::splat2(c0));       // in the shadow of the tanh
+    for (int i = 0; i < 4; ++i) x2[i] = tc::fma2(tc::splat2(3.f * c1), x2[i], tc::splat2(c0));      // in the shadow of the tanh
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(0.5f), p[i], tc::splat2(0.5f));          // s
 #pragma unroll
     for (int i = 0; i < 4; ++i) { x[i] = tc::mul2(x[i], p[i]); tc::st2(v + c8 + 2 * i, x[i]); }       // g
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x2[i] = tc::mul2(x[i], tc::fma2(tc::splat2(-2.f), p[i], tc::splat2(2.f)));
+    for (int i = 0; i < 4; ++i) tc::st2(dg + c8 + 2 * i, tc::fma2(tc::mul2(x[i], tc::fma2(tc::splat2(-2.f), p[i], tc::splat2(2.f))), x2[i], p[i]));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tc::st2(dg + c8 + 2 * i, tc::fma2(x2[i], r[i], p[i]));
+    for (int i = 0; i < 4; ++i) { s0 = tc::add2(s0, x[i]); s1 = tc::fma2(x[i], x[i], s1); }
+  }
+  st[0] = s0.x + s0.y; st[1] = s1.x + s1.y;
+}
+
+// The forward's E3 when the backward's stash is requested: as gelu_rowsums32, plus dgh[j/2] <- gelu'(v[j] + bias[j]) packed to
+// fp16 on the spot (16 registers; the fp32 derivative is never held).  g and the row sums are bit-identical to gelu_rowsums32.
+__device__ __forceinline__ void gelu_rowsums32_stash(float (&v)[32], const float* bias, uint32_t (&dgh)[16], float (&st)[2]) {
+  const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  float2 s0 = tc::splat2(0.f), s1 = tc::splat2(0.f);
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c8), b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
+    float2 x[4], x2[4], p[4];
+    x[0] = tc::add2(tc::ld2(v + c8), make_float2(b0.x, b0.y)); x[1] = tc::add2(tc::ld2(v + c8 + 2), make_float2(b0.z, b0.w));
+    x[2] = tc::add2(tc::ld2(v + c8 + 4), make_float2(b1.x, b1.y)); x[3] = tc::add2(tc::ld2(v + c8 + 6), make_float2(b1.z, b1.w));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x2[i] = tc::mul2(x[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(c1), x2[i], tc::splat2(c0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::mul2(x[i], p[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p[i].x = tanh_fast(p[i].x); p[i].y = tanh_fast(p[i].y); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x2[i] = tc::fma2(tc::splat2(3.f * c1), x2[i], tc::splat2(c0));      // in the shadow of the tanh
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = tc::fma2(tc::splat2(0.5f), p[i], tc::splat2(0.5f));          // s
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = tc::mul2(x[i], p[i]); tc::st2(v + c8 + 2 * i, x[i]); }       // g
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 d = tc::fma2(tc::mul2(x[i], tc::fma2(tc::splat2(-2.f), p[i], tc::splat2(2.f))), x2[i], p[i]);
+      dgh[(c8 >> 1) + i] = tc::pack_bf16(d.x, d.y);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { s0 = tc::add2(s0, x[i]); s1 = tc::fma2(x[i], x[i], s1); }
   }
