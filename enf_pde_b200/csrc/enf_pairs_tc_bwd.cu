@@ -298,11 +298,15 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
         A_STAMP(32, 3 + 8 * h);
         // one pass, one exchange: with g = gelu(m), n = (g - mu) rstd the row sums the LayerNorm backward needs are
         //   sum_j dnb_j n_j = rstd (sum dnb g - mu sum dnb)   and   sum_j dnb_j
-        float dg[32];
+        uint32_t dgh[16];                              // gelu', packed to fp16 inside the pass (dm is rounded to fp16 for the MMAs anyway)
         uint32_t gh[16];                               // g, packed to fp16 once the row sums have seen it in fp32 (it only re-enters
                                                        // through the small LayerNorm projection term of dm): 16 registers instead of 32
         float st[4];
-        gelu_both_rowsums32(v, s_b3 + h * D + col0, dg, st);
+        {
+          float st01[2];
+          gelu_rowsums32_stash(v, s_b3 + h * D + col0, dgh, st01);
+          st[0] = st01[0]; st[1] = st01[1];
+        }
         // the cotangent rows were requested one phase ago; touching them only now keeps their L2 latency off the gelu pass
         {
           float2 s2 = tc::splat2(0.f), s3 = tc::splat2(0.f);
@@ -337,13 +341,16 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
         uint8_t* sDh = sDm + h * C::ATILE;
         if (h == 0 && ct > 0) tc::mbar_wait(bar_gb, par ^ 1);      // every MMA of the previous tile is done with the dm tiles
 #pragma unroll
-        for (int c8 = 0; c8 < 32; c8 += 8) {           // dm overwrites g' in place
+        float (&dg)[32] = v;                           // g (fp32) is dead: its registers take dm
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[c8 >> 3]);
           const __half2* g2 = reinterpret_cast<const __half2*>(&gh[c8 >> 1]);
+          const __half2* d2 = reinterpret_cast<const __half2*>(&dgh[c8 >> 1]);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
-            tc::st2(dg + c8 + 2 * t, tc::mul2(tc::fma2(gv, tc::splat2(-kb), tc::fma2(tc::splat2(ka), dv, tc::splat2(kc))), tc::ld2(dg + c8 + 2 * t)));
+            tc::st2(dg + c8 + 2 * t, tc::mul2(tc::fma2(gv, tc::splat2(-kb), tc::fma2(tc::splat2(ka), dv, tc::splat2(kc))), __half22float2(d2[t])));
           }
           tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dg + c8);
         }
