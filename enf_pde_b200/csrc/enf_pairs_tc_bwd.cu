@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
         uint8_t* sDh = sDm + h * C::ATILE;
         if (h == 0 && ct > 0) tc::mbar_wait(bar_gb, par ^ 1);      // every MMA of the previous tile is done with the dm tiles
 #pragma unroll
-        float (&dg)[32] = v;                           // g (fp32) is dead: its registers take dm
+        uint32_t dmh[16];                              // dm as the fp16 operand words the MMAs read; the bias column sums add the same words
 #pragma unroll
         for (int c8 = 0; c8 < 32; c8 += 8) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&dnq[c8 >> 3]);
@@ -350,9 +350,10 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 dv = __half22float2(h2[t]), gv = __half22float2(g2[t]);
-            tc::st2(dg + c8 + 2 * t, tc::mul2(tc::fma2(gv, tc::splat2(-kb), tc::fma2(tc::splat2(ka), dv, tc::splat2(kc))), __half22float2(d2[t])));
+            const float2 dm = tc::mul2(tc::fma2(gv, tc::splat2(-kb), tc::fma2(tc::splat2(ka), dv, tc::splat2(kc))), __half22float2(d2[t]));
+            dmh[(c8 >> 1) + t] = tc::pack_bf16(dm.x, dm.y);
           }
-          tc::st_row8_bf16(sDh, C::ABLK, row, col0 + c8, dg + c8);
+          tc::st_row8_words(sDh, C::ABLK, row, col0 + c8, dmh + (c8 >> 1));
         }
         A_STAMP(32, 21 + 3 * h);
         tc::fence_proxy_async();
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
         if (h + 1 < H) load_dnb(ct, h + 1);
         else if (ct + 1 < ntiles) load_dnb(ct + 1, 0);
         {
-          float cs = warp_colsum32(dg, lane);
+          float cs = warp_colsum32_h2(dmh, lane);
           A_STAMP(32, 23 + 3 * h);
           atomicAdd(&s_db3[h * D + col0 + lane], cs);
         }

@@ -227,4 +227,10 @@ __device__ __forceinline__ void st_row8_bf16(uint8_t* tile, uint32_t block_bytes
   *reinterpret_cast<uint4*>(dst) = q;
 }
 
+// same, from four already packed words (features col0 .. col0 + 7)
+__device__ __forceinline__ void st_row8_words(uint8_t* tile, uint32_t block_bytes, int row, int col0, const uint32_t* w) {
+  uint8_t* dst = tile + (col0 >> 6) * block_bytes + swz_chunk_off(row, (col0 & 63) >> 3);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 }  // namespace tc
