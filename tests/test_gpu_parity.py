@@ -327,3 +327,33 @@ def test_tensor_core_full_size_ns_subset():
         out = nef.apply(P, f(x), f(p), f(a), f(sigma))
     out_ref = R.nef_apply(cfg, params, x[bsel][:, sub], p[bsel], a[bsel], sigma[bsel])
     assert rel_err(out[bsel][:, sub], out_ref) < TOL_BF16
+
+
+def test_tensor_core_full_size_ns_backward_subset():
+    """BASELINE config 2 at full size through the tensor-core forward AND backward (every tile / item path of the persistent
+    kernels, 32 query tiles per latent): a cotangent supported on random rows gives the oracle's latent gradients for that
+    subset (queries are independent); tolerance 2e-3.  A dense cotangent on top of it must not move them beyond the
+    tolerance either (the power-of-two gradient scale is taken from max |d nbar| over the whole batch)."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1))
+    B, C, Z = 32, 4096, 64
+    params, _, p, a, sigma, _ = make_case(cfg, B, 8, Z, seed=7)
+    x = R.make_coords(cfg, (64, 64)).float().double()[None].expand(B, -1, -1)
+    g = torch.Generator().manual_seed(11)
+    sub = torch.randperm(C, generator=g)[:24]
+    bsel = [0, 13, 31]
+    d_out = torch.zeros(B, C, 1, dtype=torch.float64)
+    d_out[:, sub] = torch.randn(B, 24, 1, generator=g, dtype=torch.float64)
+    out, _, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="bf16")
+    out_ref, _, dp_ref, da_ref, ds_ref = R.fwd_bwd(cfg, params, x[bsel][:, sub], p[bsel], a[bsel], sigma[bsel], d_out[bsel][:, sub])
+    errs = dict(out=rel_err(out[bsel][:, sub], out_ref), dp=rel_err(dp[bsel], dp_ref), da=rel_err(da[bsel], da_ref),
+                ds=rel_err(ds[bsel], ds_ref))
+    print("full-size tc backward", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < TOL_BF16 for v in errs.values()), errs
+    # linearity in the cotangent at full size: grads(d1 + d2) = grads(d1) + grads(d2) within the tolerance
+    d2 = torch.randn(B, C, 1, generator=g, dtype=torch.float64) * 0.05
+    _, _, dp2, da2, ds2 = _api_fwd_bwd(cfg, params, x, p, a, sigma, d2, precision="bf16")
+    _, _, dp12, da12, ds12 = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out + d2, precision="bf16")
+    lin = dict(dp=rel_err(dp12, dp + dp2), da=rel_err(da12, da + da2), ds=rel_err(ds12, ds + ds2))
+    print("full-size tc backward, linearity", {k: f"{v:.2e}" for k, v in lin.items()})
+    assert all(v < TOL_BF16 for v in lin.values()), lin
