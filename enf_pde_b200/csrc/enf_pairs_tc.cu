@@ -2,18 +2,22 @@
 //
 // One CTA owns 128 coordinate queries of one field (= the 128 TMEM lanes / UMMA M) and loops over the
 // field's Z latents.  Per latent the chain of equivariant_cross_attention.py:86-144 runs as
-//     E0q  gamma_q -> smem A0 (bf16, 128B swizzle)        GEMM1  A0 x W1_q      -> TMEM T0
-//     E0v  gamma_v -> smem A1                             GEMM2  A1 x W1_v      -> TMEM T1
-//     E1   T0: relu, dot with folded U[z,h] -> logits s ; online-softmax statistics
-//     E2   T1: relu -> A0                                 GEMM3  A0 x W'        -> T0
+//     E0q  gamma_q -> smem A0 (fp16, 128B swizzle)        GEMM1  A0 x W1_q      -> TMEM T1
+//     E0v  gamma_v -> smem A1                             GEMM2  A1 x W1_v      -> TMEM T0
+//     E1   T1: relu, dot with folded U[z,h] -> logits s ; online-softmax statistics
+//     E2   T0: relu -> A0                                 GEMM3  A0 x W'        -> T0
 //     E3   T0: gelu, LayerNorm -> A1                      GEMM4h A1 x W3[z,h]   -> T0 / T1
-//     E4h  Th: gelu, LayerNorm, acc_h += p * n                                       (registers)
+//     E4h  Th: gelu, LayerNorm, acc_h = acc_h corr + p n                             (TMEM, tcgen05.ld / st)
 // with tcgen05.mma (kind::f16, fp16 operands, fp32 accumulators in TMEM) issued by one thread, weights
 // resident in shared memory as pre-swizzled images, the per-latent W3 images streamed by the bulk-copy
-// (TMA) engine, tcgen05.ld feeding the elementwise epilogues, and D/32 threads per query row so that
-// the softmax accumulators (H x d fp32 per row) stay in registers.  Per pair, HBM only sees what is saved for
-// the backward: the logits and (optionally) the fp16 operand tile of `that`, bulk-stored straight from shared memory.  MMA and epilogues overlap where the chain allows it
-// (GEMM1 | E0v, GEMM2 | E1, GEMM3 | softmax update, GEMM4_1 | E4_0).
+// (TMA) engine, tcgen05.ld feeding the elementwise epilogues, D/32 threads per query row.  TMEM holds the two working
+// regions T0 / T1 (T0 also receives the next latent's RFF phases once E4_0 has read it) and the H softmax-weighted
+// accumulators (H x d fp32 per row): keeping those out of the register file is what lets ptxas keep several dependent
+// chains of the epilogues in flight.  The epilogues use packed fp32 pairs (FFMA2 / FMUL2 / FADD2) and evaluate the cosines
+// of the RFF phases on the FMA pipe (the XU pipe only sees the sines and the tanh of the gelus).  Per pair, HBM only sees
+// what is saved for the backward: the logits, the fp16 operand tile of `that` (bulk-stored straight from shared memory) and
+// gelu'(tpre) / rstd of that layer for backward kernel B (staged in the W3 stage buffer, one bulk store per latent).  MMA
+// and epilogues overlap where the chain allows it (GEMM1 | E0v, GEMM2 | E1, GEMM3 | softmax update, GEMM4_1 | E4_0).
 #include "enf_pairs_tc_common.cuh"
 
 namespace {

@@ -287,52 +287,7 @@ __device__ __forceinline__ Rec pair_record(const Params& P, const float* lam, co
   return r;
 }
 
-// my 32 columns of gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)] (rff.py:84-93) -> 16-bit, swizzled A tile.
-// om = Omega pre-scaled by 2 pi, [6][D/2].
-template <int D>
-__device__ __forceinline__ void rff_to_tile(const Rec& r, int I, const float* om, uint8_t* tile, uint32_t ablk, int row, int col0) {
-  constexpr int HD = D / 2;
-  const bool is_cos = col0 >= HD;
-  const int j0 = is_cos ? col0 - HD : col0;
-#pragma unroll
-  for (int c8 = 0; c8 < 32; c8 += 8) {
-    float v[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = j0 + c8 + t;
-      float proj = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
-      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
-    }
-    tc::st_row8_bf16(tile, ablk, row, col0 + c8, v);
-  }
-}
-
-// same, as a two-term 16-bit split: tile_hi gets round16(gamma), tile_lo gets round16(gamma - round16(gamma))
-template <int D>
-__device__ __forceinline__ void rff_to_tile_split(const Rec& r, int I, const float* om, uint8_t* tile_hi, uint8_t* tile_lo,
-                                                  uint32_t ablk, int row, int col0) {
-  constexpr int HD = D / 2;
-  const bool is_cos = col0 >= HD;
-  const int j0 = is_cos ? col0 - HD : col0;
-#pragma unroll
-  for (int c8 = 0; c8 < 32; c8 += 8) {
-    float v[8], lo[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = j0 + c8 + t;
-      float proj = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) if (i < I) proj = fmaf(r.u[i], om[i * HD + j], proj);
-      v[t] = is_cos ? __cosf(proj) : __sinf(proj);
-      lo[t] = v[t] - tc::round_operand(v[t]);
-    }
-    tc::st_row8_bf16(tile_hi, ablk, row, col0 + c8, v);
-    tc::st_row8_bf16(tile_lo, ablk, row, col0 + c8, lo);
-  }
-}
-
+// gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)] (rff.py:84-93)
 // ---- RFF projection on the tensor core ---------------------------------------------------------------------------
 // proj[row][n] = 2 pi sum_i u[row][i] Omega[i][n] as ONE small MMA per 128-row tile (M = 128, N = #frequencies, K = 32)
 // instead of I FMAs + I shared loads per output element.  fp16 operands carry a two-term split of both factors so the
