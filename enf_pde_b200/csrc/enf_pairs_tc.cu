@@ -61,7 +61,7 @@ template <int D, int H> struct TcCfg {
 #endif
 
 template <int D, int H>
-__global__ void __launch_bounds__(TcCfg<D, H>::NT, 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
+__global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
   using C = TcCfg<D, H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)

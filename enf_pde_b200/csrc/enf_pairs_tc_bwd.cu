@@ -138,7 +138,7 @@ using tc::named_sync;
 // SEP = true: a 17th warp issues (96 registers per thread: the register file is granted in units of 4 warps);
 // SEP = false: warp 0 issues between its own epilogue phases (it SYNCs on the named barriers, the others ARRIVE), 128 registers.
 template <int D, int H, bool SEP>
-__global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2 : 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   using A = ACfg<D, H>;
   constexpr int NTA = C::NT + (SEP ? 32 : 0);         // epilogue threads (+ the issue warp)
@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
     for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 0) tc::tmem_alloc<512>(s_tmem);
+  // two working regions + H weight-gradient accumulators; at d = 64 that is half of TMEM (and of shared memory, and 128
+  // registers per thread for 256 threads): two CTAs per SM, each filling the other's MMA / barrier waits
+  constexpr int kTmemCols = (2 + H) * D <= 256 ? 256 : 512;
+  if (warp == 0) tc::tmem_alloc<kTmemCols>(s_tmem);
   for (int e = tid; e < H * D; e += NTA) { s_b3[e] = P.b3[bz * H * D + e]; s_db3[e] = 0.f; }
   float gs, inv_gs;
   load_scale(P.gmax, gs, inv_gs);
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), 1) pairs_bw
   for (int e = tid; e < H * D; e += NTA) P.g_b3[bz * H * D + e] = s_db3[e] * inv_gs;
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<512>(tm);
+  if (warp == 0) tc::tmem_dealloc<kTmemCols>(tm);
 }
 
 template <int D, int H>
