@@ -65,15 +65,20 @@ INVARIANT_KINDS = {
 PREC_FP32, PREC_BF16 = 0, 1
 FLAG_FORWARD_ONLY = 1
 FLAG_TC_BACKWARD_D64 = 2
+FLAG_RECOMPUTE = 4
+FLAG_OUT_BF16 = 8
+ABI_VERSION = 2
 
-EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_fwd",
-           "enf_xattn_bwd", "enf_last_launch_count", "enf_last_error", "enf_debug_ws_offset", "enf_profile_enable",
-           "enf_profile_collect", "enf_debug_tc_gemm", "enf_debug_gemm")
+EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_chunk_for_cap",
+           "enf_xattn_dispatch", "enf_workspace_release", "enf_xattn_fwd", "enf_xattn_bwd", "enf_last_launch_count",
+           "enf_last_error", "enf_debug_ws_offset", "enf_profile_enable", "enf_profile_collect", "enf_debug_tc_gemm",
+           "enf_debug_gemm")
 
 
 class EnfDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("B", "C", "Z", "d", "H", "L", "O", "Dx", "invariant_kind", "use_window", "precision", "flags")]
+                ("B", "C", "Z", "d", "H", "L", "O", "Dx", "invariant_kind", "use_window", "precision", "flags",
+                 "chunk_fields")] + [("reserved", ctypes.c_int32 * 3)]
 
 
 class EnfWeights(ctypes.Structure):
@@ -105,6 +110,12 @@ def load():
     lib.enf_xattn_workspace_bytes.restype = ctypes.c_size_t
     lib.enf_xattn_workspace_bytes.argtypes = [ctypes.POINTER(EnfDesc)]
     vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    lib.enf_xattn_chunk_for_cap.restype = ctypes.c_int
+    lib.enf_xattn_chunk_for_cap.argtypes = [ctypes.POINTER(EnfDesc), ctypes.c_size_t]
+    lib.enf_xattn_dispatch.restype = ctypes.c_int
+    lib.enf_xattn_dispatch.argtypes = [ctypes.POINTER(EnfDesc), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    lib.enf_workspace_release.restype = None
+    lib.enf_workspace_release.argtypes = [vp]
     lib.enf_xattn_fwd.restype = ctypes.c_int
     lib.enf_xattn_fwd.argtypes = [ctypes.POINTER(EnfDesc), ctypes.POINTER(EnfWeights), vp, i64, vp, vp, vp, vp, vp,
                                   ctypes.c_size_t, vp]
@@ -123,10 +134,17 @@ def load():
     lib.enf_debug_tc_gemm.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.enf_debug_gemm.restype = ctypes.c_int
     lib.enf_debug_gemm.argtypes = [ctypes.c_int] * 4 + [vp, i64, i64, vp, i64, i64, vp, vp, i64, vp, vp, vp, ctypes.c_int, vp]
-    if lib.enf_abi_version() != 1:
+    if lib.enf_abi_version() != ABI_VERSION:
         raise EnfLibraryError("libenf_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def dispatch(desc):
+    """(pair forward on tcgen05?, pair backward on tcgen05?) for an EnfDesc -- what the library will actually run."""
+    f, b = ctypes.c_int(0), ctypes.c_int(0)
+    check(load().enf_xattn_dispatch(ctypes.byref(desc), ctypes.byref(f), ctypes.byref(b)), "enf_xattn_dispatch")
+    return bool(f.value), bool(b.value)
 
 
 def check(rc, what):

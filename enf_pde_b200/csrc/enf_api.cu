@@ -71,7 +71,12 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
-  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_TC_BACKWARD_D64)) return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
+  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_TC_BACKWARD_D64 | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16))
+    return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
+  if ((D->flags & ENF_FLAG_OUT_BF16) && (!(D->flags & ENF_FLAG_FORWARD_ONLY) || !enf_thin_supported(D->d, D->O)))
+    return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_OUT_BF16 needs ENF_FLAG_FORWARD_ONLY and num_out <= 4");
+  if (D->chunk_fields < 0 || D->reserved[0] || D->reserved[1] || D->reserved[2])
+    return fail(ENF_ERR_BAD_DESC, "chunk_fields must be >= 0 and the reserved fields 0");
   if (rl) *rl = r;
   return ENF_OK;
 }
@@ -80,6 +85,14 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
 bool use_tc_bwd(const EnfDesc& D) {
   return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H) &&
          (D.d == 128 || (D.flags & ENF_FLAG_TC_BACKWARD_D64));
+}
+
+// fields per backward chunk: everything O(B*C*Z) that only lives between the pair kernels of one chunk is sized by this.
+// Default (stash) mode: one chunk = the whole batch.
+int chunk_fields(const EnfDesc& D) {
+  if (!(D.flags & ENF_FLAG_RECOMPUTE) || !use_tc_bwd(D)) return D.B;
+  int n = D.chunk_fields > 0 ? D.chunk_fields : 4;
+  return n < D.B ? n : D.B;
 }
 
 Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
@@ -96,7 +109,9 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   {
     // transposed W3 copies: only the fp32-FMA backward reads them
     const bool tc_both = use_tc_bwd(D);
-    if (train && !tc_both) Y.add("W3T", BZ * H * d2);
+    // ... and, there, the cotangent of Weff gets a buffer of its own (the tensor-core backward never reads the fp32 W3
+    // again, so it reuses that one): a backward leaves the forward state intact and can be repeated
+    if (train && !tc_both) { Y.add("W3T", BZ * H * d2); Y.add("dWeff", BZ * H * d2); }
   }
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
     Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
@@ -109,14 +124,17 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     if (train && use_tc_bwd(D)) {
       Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
       const size_t Cpad = (size_t)((D.C + 127) / 128) * 128;      // kernels A / B work on whole 128-query tiles
-      Y.add("dthat", BZ * Cpad * d / 2); Y.add("ds_tc", BC * (size_t)D.Z * H); Y.add("Dg", BC * H);
+      // per-(query, latent) tensors that live between the pair kernels of ONE backward chunk: all fields in the default
+      // (stash) mode, chunk_fields fields with ENF_FLAG_RECOMPUTE
+      const size_t cZ = (size_t)chunk_fields(D) * D.Z, cC = (size_t)chunk_fields(D) * D.C;
+      Y.add("dthat", cZ * Cpad * d / 2); Y.add("ds_tc", cC * (size_t)D.Z * H); Y.add("Dg", BC * H);
       Y.add("dnb16", (size_t)D.B * Cpad * Hd / 2);
-      Y.add("duv", BC * (size_t)D.Z * 8);
+      Y.add("duv", cC * (size_t)D.Z * 8);
       Y.add("dbg", 8192);
       // fp16 operand images of `that` per (field, latent, 128-query tile), stashed by the forward for backward kernel A
-      Y.add("that_img", BZ * (size_t)((D.C + 127) / 128) * 128 * d / 2);
+      Y.add("that_img", cZ * Cpad * d / 2);
       // rstd * gelu' of the same layer (fp16), stashed for backward kernel B: with `that` it is all the LayerNorm / gelu backward needs
-      Y.add("dgr", BZ * Cpad * d / 2); Y.add("trstd", BZ * Cpad);
+      Y.add("dgr", cZ * Cpad * d / 2); Y.add("trstd", cZ * Cpad);
     }
   }
   Y.add("xi", BC * ENF_F_XI);
@@ -124,7 +142,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("e1", BC * Hd); Y.add("e3c", BC * Hd); Y.add("erstd", BC); Y.add("e3", BC * Hd);
   Y.add("fo", BC * Hd); Y.add("o1p", BC * d); Y.add("o2p", BC * d);
   if (!train) return Y;
-  Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("s2", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
+  Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
   Y.add("dbeff", BZ * Hd); Y.add("dk", BZ * Hd); Y.add("dv0", BZ * Hd); Y.add("dahat", BZ * d); Y.add("da0", BZ * d);
   // ---- accumulators, zeroed at the start of each bwd ----
   Y.acc_begin = Y.total;
@@ -145,22 +163,31 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
 }
 
 std::mutex g_mu;
-std::map<void*, EnfDesc> g_fwd_state;     // workspaces that currently hold a forward
+struct FwdState { EnfDesc D; int64_t xbs; };
+std::map<void*, FwdState> g_fwd_state;    // workspaces that currently hold a forward (erased by enf_workspace_release)
 
 // optional live timing of the two fused pair kernels (bench.py's roofline line): a ring of CUDA event
 // pairs per kernel, recorded on the call's stream; enf_profile_collect drains it.
 constexpr int kProfRing = 256;
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[2][kProfRing][2];
-bool g_prof_created[2][kProfRing];
+int g_prof_dev[2][kProfRing];             // device the slot's events were created on (-1: none); events are per device
+bool g_prof_init = false;
 long g_prof_count[2] = {0, 0};
 void prof_mark(int which, int edge, cudaStream_t st) {
   if (!g_prof_on) return;
+  if (!g_prof_init) {
+    for (int w = 0; w < 2; ++w) for (int i = 0; i < kProfRing; ++i) g_prof_dev[w][i] = -1;
+    g_prof_init = true;
+  }
   int slot = (int)(g_prof_count[which] % kProfRing);
-  if (!g_prof_created[which][slot]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_prof_dev[which][slot] != dev) {
+    if (g_prof_dev[which][slot] >= 0) { cudaEventDestroy(g_prof_ev[which][slot][0]); cudaEventDestroy(g_prof_ev[which][slot][1]); }
     cudaEventCreate(&g_prof_ev[which][slot][0]);
     cudaEventCreate(&g_prof_ev[which][slot][1]);
-    g_prof_created[which][slot] = true;
+    g_prof_dev[which][slot] = dev;
   }
   cudaEventRecord(g_prof_ev[which][slot][edge], st);
   if (edge == 1) g_prof_count[which]++;
@@ -228,6 +255,61 @@ EnfPairParams pair_params(const EnfDesc& D, const EnfRecordLayout& rl, const Enf
   return p;
 }
 
+bool check_weights(const EnfWeights* w);
+
+// parameters of the tensor-core pair forward; `stash`: also write the backward's operand stash (that_img / dgr / trstd)
+EnfPairTcParams tc_fwd_params(const EnfDesc& D, const EnfRecordLayout& rl, const EnfWeights& w, const Ctx& c, const EnfPairParams& pp,
+                              bool keep_logits, bool stash) {
+  EnfPairTcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.B = D.B; tp.C = D.C; tp.Z = D.Z; tp.I = rl.I;
+  tp.row_kind = rl.row_kind; tp.win_kind = rl.win_kind; tp.win_row = rl.win_row; tp.nsq = rl.nsq;
+  tp.xi = pp.xi; tp.xi_bs = pp.xi_bs; tp.lam = pp.lam; tp.sigma = pp.sigma;
+  tp.q_omega = w.q_omega; tp.v_omega = w.v_omega; tp.q_b1 = w.q_b1; tp.v_b1 = w.v_b1; tp.bp = c.f("bp");
+  tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
+  tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
+  tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = keep_logits ? c.f("slog") : nullptr;
+  tp.that_img = stash ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
+  tp.dgr = stash ? reinterpret_cast<uint4*>(c.f("dgr")) : nullptr;
+  tp.trstd = stash ? c.f("trstd") : nullptr;
+  return tp;
+}
+// restrict a pair-forward launch to the fields [b0, b0 + nb): every per-field / per-latent pointer moves; the operand stash
+// is chunk-local (it always starts at its buffer's base)
+void shift_fields(EnfPairTcParams& tp, const EnfDesc& D, int b0, int nb) {
+  const int64_t bz = (int64_t)b0 * D.Z, bc = (int64_t)b0 * D.C, Hd = (int64_t)D.H * D.d;
+  tp.B = nb;
+  tp.xi += b0 * tp.xi_bs; tp.lam += bz * ENF_LAM_SIZE; if (tp.sigma) tp.sigma += bz;
+  tp.img_W3 += bz * D.H * (int64_t)D.d * D.d * 2;
+  tp.U += bz * Hd; tp.kappa += bz * D.H; tp.b3 += bz * Hd; tp.nbar += bc * Hd; tp.lse += bc * D.H;
+  if (tp.slog) tp.slog += bz * D.C * D.H;
+}
+// same for the pair backward: the A -> B -> C hand-over tensors (dthat, ds, duv) and the stash are chunk-local
+void shift_fields(EnfPairTcBwdParams& tp, const EnfDesc& D, int b0, int nb) {
+  const int64_t bz = (int64_t)b0 * D.Z, bc = (int64_t)b0 * D.C, Hd = (int64_t)D.H * D.d;
+  const int64_t ntiles = (D.C + 127) / 128;
+  tp.B = nb;
+  tp.xi += b0 * tp.xi_bs; tp.lam += bz * ENF_LAM_SIZE; if (tp.sigma) tp.sigma += bz;
+  tp.img_W3 += bz * D.H * (int64_t)D.d * D.d * 2;
+  tp.U += bz * Hd; tp.b3 += bz * Hd; tp.slog += bz * D.C * D.H; tp.lse += bc * D.H; tp.nbar += bc * Hd;
+  tp.dnbar += bc * Hd; tp.Dg += bc * D.H; tp.dnb16 += (int64_t)b0 * ntiles * 128 * Hd / 8;
+  tp.g_W3 += bz * D.H * (int64_t)D.d * D.d; tp.g_b3 += bz * Hd;
+  tp.g_U += bz * Hd; tp.g_kappa += bz * D.H; tp.g_lam += bz * ENF_LAM_SIZE; tp.g_sigma += bz;
+}
+
+// argument checks shared by enf_xattn_fwd and enf_xattn_bwd
+int check_call(const EnfDesc& D, const EnfWeights* w, const float* x, int64_t x_batch_stride, const float* p, const float* a,
+               const float* sigma, void* workspace) {
+  if (!w || !x || !p || !a || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
+  if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
+  if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ENF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  return ENF_OK;
+}
+
 bool check_weights(const EnfWeights* w) {
   const float* const* p = reinterpret_cast<const float* const*>(w);
   for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) if (!p[i]) return false;
@@ -287,6 +369,34 @@ size_t enf_xattn_workspace_bytes(const EnfDesc* desc) {
   return make_layout(*desc, rl).total * sizeof(float);
 }
 
+int enf_xattn_chunk_for_cap(const EnfDesc* desc, size_t cap_bytes) {
+  EnfRecordLayout rl;
+  if (validate(desc, &rl) != ENF_OK) return 0;
+  EnfDesc D = *desc;
+  D.flags |= ENF_FLAG_RECOMPUTE;
+  int lo = 0, hi = D.B;                     // the workspace grows monotonically with chunk_fields: bisect
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    D.chunk_fields = mid;
+    if (make_layout(D, rl).total * sizeof(float) <= cap_bytes) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+int enf_xattn_dispatch(const EnfDesc* desc, int* fwd_tc, int* bwd_tc) {
+  int rc = validate(desc, nullptr);
+  if (rc != ENF_OK) return rc;
+  const bool f = desc->precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(desc->d, desc->H);
+  if (fwd_tc) *fwd_tc = f ? 1 : 0;
+  if (bwd_tc) *bwd_tc = (f && use_tc_bwd(*desc) && !(desc->flags & ENF_FLAG_FORWARD_ONLY)) ? 1 : 0;
+  return ENF_OK;
+}
+
+void enf_workspace_release(void* workspace) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_fwd_state.erase(workspace);
+}
+
 int64_t enf_debug_ws_offset(const EnfDesc* desc, const char* name, int64_t* num_floats) {
   EnfRecordLayout rl;
   if (validate(desc, &rl) != ENF_OK || !name) return -1;
@@ -304,17 +414,12 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   int rc = validate(desc, &rl);
   if (rc != ENF_OK) return rc;
   const EnfDesc& D = *desc;
-  if (!w || !x || !p || !a || !out || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
-  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
-  if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
-  if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
+  if (!out) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if ((rc = check_call(D, w, x, x_batch_stride, p, a, sigma, workspace)) != ENF_OK) return rc;
   const bool use_tc = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);   // other shapes: fp32 kernels
   const bool train = !(D.flags & ENF_FLAG_FORWARD_ONLY);
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
   Layout Y = make_layout(D, rl);
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small: see enf_xattn_workspace_bytes");
-  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ENF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
 
   Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y; c.tc = use_tc;
   cudaStream_t st = c.st;
@@ -388,18 +493,9 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.launches += enf_launch_weight_image(st, c.f("v_w1T"), c.f("img_v_w1"), nullptr, d, d, 1);
     c.launches += enf_launch_weight_image(st, c.f("WpT"), c.f("img_Wp"), nullptr, d, d, 1);
     c.launches += enf_launch_weight_image_T(st, c.f("W3"), c.f("img_W3"), d, d, (int)(BZ * H));
-    EnfPairTcParams tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.B = D.B; tp.C = D.C; tp.Z = D.Z; tp.I = rl.I;
-    tp.row_kind = rl.row_kind; tp.win_kind = rl.win_kind; tp.win_row = rl.win_row; tp.nsq = rl.nsq;
-    tp.xi = pp.xi; tp.xi_bs = pp.xi_bs; tp.lam = pp.lam; tp.sigma = pp.sigma;
-    tp.q_omega = w->q_omega; tp.v_omega = w->v_omega; tp.q_b1 = w->q_b1; tp.v_b1 = w->v_b1; tp.bp = c.f("bp");
-    tp.img_q_w1 = (const uint8_t*)c.f("img_q_w1"); tp.img_v_w1 = (const uint8_t*)c.f("img_v_w1");
-    tp.img_Wp = (const uint8_t*)c.f("img_Wp"); tp.img_W3 = (const uint8_t*)c.f("img_W3");
-    tp.U = pp.U; tp.kappa = pp.kappa; tp.b3 = pp.b3; tp.nbar = pp.nbar; tp.lse = pp.lse; tp.slog = train ? c.f("slog") : nullptr;
-    tp.that_img = (train && use_tc_bwd(D)) ? reinterpret_cast<uint8_t*>(c.f("that_img")) : nullptr;
-    tp.dgr = (train && use_tc_bwd(D)) ? reinterpret_cast<uint4*>(c.f("dgr")) : nullptr;
-    tp.trstd = (train && use_tc_bwd(D)) ? c.f("trstd") : nullptr;
+    // ENF_FLAG_RECOMPUTE: no per-pair operand stash now; the backward rebuilds it chunk by chunk
+    const bool stash = train && use_tc_bwd(D) && !(D.flags & ENF_FLAG_RECOMPUTE);
+    EnfPairTcParams tp = tc_fwd_params(D, rl, *w, c, pp, train, stash);
     static const bool trace_fwd = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace_fwd ? reinterpret_cast<long long*>(c.f("dbg_fwd")) : nullptr;
     prof_mark(0, 0, st);
@@ -414,6 +510,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.launches += nl;
 
   // ---- Q: per-query tail ----------------------------------------------------------------------------
+  const int out_bf16 = (D.flags & ENF_FLAG_OUT_BF16) ? 1 : 0;
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("nbar"), Hd), enf_mat(c.f("W_A"), Hd), enf_mat(c.f("e1"), Hd),
          with_lo(opt_bias(c.f("b_A")), use_tc ? c.f("lo_W_A") : nullptr));
   c.launches += enf_launch_ln_fwd(st, c.f("e1"), BC, Hd, w->fb_g, w->fb_beta, c.f("e3c"), c.f("e3"), c.f("erstd"), 1);
@@ -427,14 +524,14 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm((int)BC, d, Hd, enf_mat(c.f("fo_act"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
     o.bias = w->m1_b; o.gelu_out = c.f("o2_act"); o.b_lo = c.f("lo_m1_w");
     c.gemm((int)BC, d, d, enf_mat(c.f("o1_act"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
-    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2_act"), w->m2_w, w->m2_b, out, BC, d, O, 0);
+    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2_act"), w->m2_w, w->m2_b, out, BC, d, O, 0, out_bf16);
     else c.gemm((int)BC, O, d, enf_mat(c.f("o2_act"), d), enf_mat(w->m2_w, O), enf_mat(out, O), opt_bias(w->m2_b));
   } else {
     c.gemm((int)BC, Hd, Hd, enf_mat(c.f("e3"), Hd), enf_mat(w->fb_w2, Hd), enf_mat(c.f("fo"), Hd), opt_bias(w->fb_b2));
     EnfGemmOpts o; o.act_a = 1;
     o.bias = w->m0_b; c.gemm((int)BC, d, Hd, enf_mat(c.f("fo"), Hd), enf_mat(w->m0_w, d), enf_mat(c.f("o1p"), d), o);
     o.bias = w->m1_b; c.gemm((int)BC, d, d, enf_mat(c.f("o1p"), d), enf_mat(w->m1_w, d), enf_mat(c.f("o2p"), d), o);
-    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2p"), w->m2_w, w->m2_b, out, BC, d, O, 1);
+    if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2p"), w->m2_w, w->m2_b, out, BC, d, O, 1, out_bf16);
     else { o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o); }
   }
   if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
@@ -442,7 +539,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing fwd: ") + cudaGetErrorString(e));
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (train) g_fwd_state[workspace] = D; else g_fwd_state.erase(workspace);
+    if (train) g_fwd_state[workspace] = FwdState{D, x_batch_stride}; else g_fwd_state.erase(workspace);
   }
   g_launches = c.launches;
   return ENF_OK;
@@ -456,15 +553,14 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   int rc = validate(desc, &rl);
   if (rc != ENF_OK) return rc;
   const EnfDesc& D = *desc;
-  if (!w || !x || !p || !a || !d_out || !dp || !da || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
-  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
-  if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set");
   if (D.flags & ENF_FLAG_FORWARD_ONLY) return fail(ENF_ERR_STATE, "a forward-only description (ENF_FLAG_FORWARD_ONLY) has no backward");
+  if (!d_out || !dp || !da) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if ((rc = check_call(D, w, x, x_batch_stride, p, a, sigma, workspace)) != ENF_OK) return rc;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_fwd_state.find(workspace);
-    if (it == g_fwd_state.end() || memcmp(&it->second, &D, sizeof(EnfDesc)) != 0)
-      return fail(ENF_ERR_STATE, "enf_xattn_bwd needs the workspace of a matching enf_xattn_fwd call");
+    if (it == g_fwd_state.end() || memcmp(&it->second.D, &D, sizeof(EnfDesc)) != 0 || it->second.xbs != x_batch_stride)
+      return fail(ENF_ERR_STATE, "enf_xattn_bwd needs the workspace of a matching enf_xattn_fwd call (same description, same x_batch_stride)");
   }
   Layout Y = make_layout(D, rl);
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small");
@@ -562,7 +658,28 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.g_Wp = c.f("gf_Wp"); tp.g_bp = c.f("gf_bp");
     tp.g_U = c.f("g_U"); tp.g_kappa = c.f("g_kappa"); tp.g_lam = c.f("g_lam"); tp.g_sigma = c.f("g_sigma");
     prof_mark(1, 0, st);
-    nl = enf_launch_pairs_bwd_tc(st, d, H, tp);
+    // once per backward: the power-of-two gradient scale, the fp16 cotangent of nbar in kernel A's load order, Dg
+    nl = enf_launch_pairs_bwd_tc_prep(st, d, H, tp);
+    // then the three pair kernels, field chunk by field chunk.  Default: one chunk (the forward stashed the operands of
+    // every field).  ENF_FLAG_RECOMPUTE: the forward kept nothing per pair; each chunk's stash is rebuilt first by re-running
+    // the fused pair forward on those fields (bit-identical: same kernel, same inputs).
+    const bool recompute = (D.flags & ENF_FLAG_RECOMPUTE) != 0;
+    const int nb_max = chunk_fields(D);
+    for (int b0 = 0; b0 < D.B && nl >= 0; b0 += nb_max) {
+      const int nb = D.B - b0 < nb_max ? D.B - b0 : nb_max;
+      if (recompute) {
+        EnfPairTcParams fp = tc_fwd_params(D, rl, *w, c, pp, true, true);
+        shift_fields(fp, D, b0, nb);
+        const int r = enf_launch_pairs_fwd_tc(st, d, H, fp);
+        if (r < 0) { nl = -1; break; }
+        nl += r;
+      }
+      EnfPairTcBwdParams cp = tp;
+      shift_fields(cp, D, b0, nb);
+      const int r = enf_launch_pairs_bwd_tc_main(st, d, H, cp);
+      if (r < 0) { nl = -1; break; }
+      nl += r;
+    }
     prof_mark(1, 1, st);
   } else {
     c.launches += enf_launch_transpose(st, w->q_w1, c.f("q_w1T"), d, d, 1);
@@ -590,7 +707,9 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm(d, d, (int)(BZ * H), enf_mat(c.f("beff"), 1, d), enf_mat(c.f("g_b3"), d), enf_mat(G("mx_w1"), d), opt_acc());
     colsum(c.f("g_b3"), BZ * H, d, G("mx_b1"));
   }
-  float* dWeff = c.f("W3");       // W3 is dead after the pair backward
+  // cotangent of Weff.  The tensor-core backward never reads the fp32 W3 (only its operand images), so it is free scratch
+  // there; the fp32 backward re-reads W3 on every call and gets a buffer of its own -- either way a backward can be repeated.
+  float* dWeff = tc_bwd ? c.f("W3") : c.f("dWeff");
   c.gemm((int)(BZ * H * d), d, d, enf_mat(c.f("g_W3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(dWeff, d),
          with_lo(EnfGemmOpts(), LO("lo_mx_w1")));
   c.gemm((int)(BZ * H), d, d, enf_mat(c.f("g_b3"), d), enf_mat(w->mx_w1, 1, d), enf_mat(c.f("dbeff"), d));

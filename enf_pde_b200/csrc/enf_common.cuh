@@ -114,7 +114,8 @@ int enf_launch_rowscale(cudaStream_t st, const float* W, const float* g, float* 
 int enf_launch_colsum(cudaStream_t st, const float* G, int64_t M, int N, int64_t ld, float* out, const float* mul, int64_t ld_mul);
 // decode MLP's last layer (d -> O, O <= 4): out = act(A) W + b ; dX = (dO W^T) gelu'(pre) ; dW += act(A)^T dO, db += colsum(dO)
 bool enf_thin_supported(int d, int O);
-int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a);
+int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a,
+                        int out_bf16 = 0);     // out_bf16: `out` is a bfloat16 buffer (ENF_FLAG_OUT_BF16)
 int enf_launch_thin_dgrad(cudaStream_t st, const float* dO, const float* W, const float* pre, float* dX, int64_t M, int d, int O);
 int enf_launch_thin_wgrad(cudaStream_t st, const float* A, const float* dO, float* dW, float* db, int64_t M, int d, int O, int act_a);
 int enf_launch_ln_fwd(cudaStream_t st, const float* in, int64_t M, int N, const float* g, const float* b,
@@ -215,6 +216,8 @@ struct EnfPairTcBwdParams {
   long long* dbg;                            // optional clock64() trace of one CTA (diagnostics; null in production)
 };
 bool enf_pairs_bwd_tc_supported(int d, int H);
-int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);
+// prep (once per backward, whole batch): gradient scale, fp16 cotangent of nbar, Dg;  main: kernels A, B, C on p.B fields
+int enf_launch_pairs_bwd_tc_prep(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);
+int enf_launch_pairs_bwd_tc_main(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);
 int enf_launch_pairs_bwd_tc_v(cudaStream_t st, int d, const EnfPairTcBwdParams& p);          // kernel B (value path, bottom), called by the above
 int enf_launch_pairs_bwd_tc_q(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p);   // kernel C (query path), called by the above

@@ -141,10 +141,16 @@ __global__ void __launch_bounds__(256) enf_gemm_group_kernel(const __grid_consta
 }
 
 constexpr size_t kGemmSmem = (size_t)ST * BK * ((BM + 4) + (BN + 4)) * sizeof(float);
+// the attribute is per DEVICE (and above the 48 KB default), so it is remembered per device ordinal, not per process
 bool gemm_configure() {
-  static const bool ok =
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev >= 0 && dev < 64 && done[dev]) return true;
+  const bool ok =
       cudaFuncSetAttribute(enf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) == cudaSuccess &&
       cudaFuncSetAttribute(enf_gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) == cudaSuccess;
+  if (ok && dev >= 0 && dev < 64) done[dev] = true;
   return ok;
 }
 

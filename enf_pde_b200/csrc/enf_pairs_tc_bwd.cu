@@ -433,14 +433,19 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
 }
 
 template <int D, int H>
-int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
-  using C = BwdCfg<D, H>;
+int launch_prep(cudaStream_t st, const EnfPairTcBwdParams& p) {
   const int64_t n4 = (int64_t)p.B * p.C * H * D / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   bwd_prep_max_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(p.dnbar), n4, const_cast<float*>(p.gmax));
   if (cudaMemsetAsync(p.Dg, 0, (size_t)p.B * p.C * H * sizeof(float), st) != cudaSuccess) return -1;
   bwd_prep_pack_kernel<D><<<148 * 8, 256, 0, st>>>(p.dnbar, p.nbar, p.B, p.C, H, p.gmax, p.dnb16, p.Dg);
+  return 2;
+}
+
+template <int D, int H>
+int launch_main(cudaStream_t st, const EnfPairTcBwdParams& p) {
+  using C = BwdCfg<D, H>;
   size_t smem_a = ACfg<D, H>::SMEM_BYTES;
   constexpr bool kSepIssueWarp = false;
   if (cudaFuncSetAttribute(pairs_bwd_tc_a_kernel<D, H, kSepIssueWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) return -1;
@@ -448,17 +453,25 @@ int launch_bwd(cudaStream_t st, const EnfPairTcBwdParams& p) {
   pairs_bwd_tc_a_kernel<D, H, kSepIssueWarp><<<grid, C::NT + (kSepIssueWarp ? 32 : 0), smem_a, st>>>(p);
   if (enf_launch_pairs_bwd_tc_v(st, D, p) < 0) return -1;
   if (enf_launch_pairs_bwd_tc_q(st, D, H, p) < 0) return -1;
-  return 5;
+  return 3;
 }
 
 }  // namespace
 
 bool enf_pairs_bwd_tc_supported(int d, int H) { return (d == 128 || d == 64) && (H == 1 || H == 2); }
 
-int enf_launch_pairs_bwd_tc(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
-  if (d == 128 && H == 2) return launch_bwd<128, 2>(st, p);
-  if (d == 128 && H == 1) return launch_bwd<128, 1>(st, p);
-  if (d == 64 && H == 2) return launch_bwd<64, 2>(st, p);
-  if (d == 64 && H == 1) return launch_bwd<64, 1>(st, p);
+int enf_launch_pairs_bwd_tc_prep(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
+  if (d == 128 && H == 2) return launch_prep<128, 2>(st, p);
+  if (d == 128 && H == 1) return launch_prep<128, 1>(st, p);
+  if (d == 64 && H == 2) return launch_prep<64, 2>(st, p);
+  if (d == 64 && H == 1) return launch_prep<64, 1>(st, p);
+  return -1;
+}
+
+int enf_launch_pairs_bwd_tc_main(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
+  if (d == 128 && H == 2) return launch_main<128, 2>(st, p);
+  if (d == 128 && H == 1) return launch_main<128, 1>(st, p);
+  if (d == 64 && H == 2) return launch_main<64, 2>(st, p);
+  if (d == 64 && H == 1) return launch_main<64, 1>(st, p);
   return -1;
 }

@@ -1,5 +1,7 @@
 // Small per-query (X), per-latent (L) and per-weight (W) stage kernels around the fused pair
 // kernels: invariant records, LayerNorm rows, FiLM effective weights, reductions.  All fp32.
+#include <cuda_bf16.h>
+
 #include "enf_common.cuh"
 
 namespace {
@@ -508,7 +510,7 @@ namespace {
 // out[m,o] = sum_k act(A[m,k]) W[k,o] + b[o]; one warp per row, float4 lanes over k
 template <int O>
 __global__ void __launch_bounds__(256) thin_out_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ b,
-                                                       float* __restrict__ out, int64_t M, int d, int act_a) {
+                                                       float* __restrict__ out, int64_t M, int d, int act_a, int out_bf16) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -530,7 +532,10 @@ __global__ void __launch_bounds__(256) thin_out_kernel(const float* __restrict__
     for (int o = 0; o < O; ++o) acc[o] = warp_sum(acc[o]);
     if (lane == 0) {
 #pragma unroll
-      for (int o = 0; o < O; ++o) out[m * O + o] = acc[o] + b[o];
+      for (int o = 0; o < O; ++o) {
+        if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[m * O + o] = __float2bfloat16_rn(acc[o] + b[o]);
+        else out[m * O + o] = acc[o] + b[o];
+      }
     }
   }
 }
@@ -585,13 +590,14 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict
 }  // namespace
 
 bool enf_thin_supported(int d, int O) { return O >= 1 && O <= 4 && d % 4 == 0; }
-int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a) {
+int enf_launch_thin_out(cudaStream_t st, const float* A, const float* W, const float* b, float* out, int64_t M, int d, int O, int act_a,
+                        int out_bf16) {
   int blocks = (int)((M + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
   switch (O) {
-    case 1: thin_out_kernel<1><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
-    case 2: thin_out_kernel<2><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
-    case 3: thin_out_kernel<3><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
-    case 4: thin_out_kernel<4><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a); break;
+    case 1: thin_out_kernel<1><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a, out_bf16); break;
+    case 2: thin_out_kernel<2><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a, out_bf16); break;
+    case 3: thin_out_kernel<3><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a, out_bf16); break;
+    case 4: thin_out_kernel<4><<<blocks, 256, 0, st>>>(A, W, b, out, M, d, act_a, out_bf16); break;
     default: return -1;
   }
   return 1;

@@ -11,6 +11,7 @@ p, a and the window size; none w.r.t. the coordinates, which the reference never
 """
 import ctypes
 import math
+import weakref
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -88,7 +89,11 @@ class _XAttnFunction(torch.autograd.Function):
         if nbytes == 0:
             raise _lib.EnfLibraryError("bad problem description: " + lib.enf_last_error().decode())
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        out = torch.empty(desc.B, desc.C, desc.O, dtype=torch.float32, device=x.device)
+        # the library keys its forward state on the workspace address: drop the entry when the buffer dies, so that a later
+        # allocation at the same address can never pass for this forward
+        weakref.finalize(ws, lib.enf_workspace_release, ctypes.c_void_p(ws.data_ptr()))
+        out_dtype = torch.bfloat16 if desc.flags & _lib.FLAG_OUT_BF16 else torch.float32
+        out = torch.empty(desc.B, desc.C, desc.O, dtype=out_dtype, device=x.device)
         w = _weights_struct(leaves)
         stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         xbs = 0 if x_shared else desc.C * desc.Dx
@@ -102,12 +107,14 @@ class _XAttnFunction(torch.autograd.Function):
         ctx.launches_fwd = lib.enf_last_launch_count()
         _XAttnFunction.last_launches = [ctx.launches_fwd, 0]
         ctx.forward_only = bool(desc_kw.get("flags", 0) & _lib.FLAG_FORWARD_ONLY)
-        _XAttnFunction.last_ws = (desc_kw, ws)      # diagnostics (enf_debug_ws_offset views); the buffer lives until the next forward
+        # diagnostics (enf_debug_ws_offset views, tests): a WEAK reference -- the workspace (GBs) dies with its autograd node
+        _XAttnFunction.last_ws = (desc_kw, weakref.ref(ws), nbytes)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_out):
+        # repeatable (retain_graph=True): enf_xattn_bwd leaves the forward state in the workspace intact
         lib = _lib.load()
         saved = list(ctx.saved_tensors)
         x, p, a = saved[:3]
@@ -146,7 +153,8 @@ class EquivariantCrossAttentionNeF:
                  cross_attn_invariant: BaseInvariant, self_attn_invariant: Optional[BaseInvariant] = None,
                  embedding_type: str = "rff", embedding_freq_multiplier=(0.05, 0.1),
                  condition_value_transform: bool = True, use_gaussian_window: bool = True,
-                 precision: str = "fp32", tc_backward_d64: bool = False):
+                 precision: str = "fp32", tc_backward_d64: bool = False, recompute: bool = False, chunk_fields: int = 0,
+                 workspace_cap_bytes: Optional[int] = None, out_bf16: bool = False):
         if num_layers != 0:
             raise NotImplementedError("latent self-attention blocks (num_layers > 0) are not on the accelerated path; "
                                       "every shipped config of the reference uses num_layers: 0")
@@ -168,6 +176,11 @@ class EquivariantCrossAttentionNeF:
         # num_hidden = 64 in tensor-core mode: backward on the tcgen05 kernels too (ENF_FLAG_TC_BACKWARD_D64; off by default:
         # 3e-3 on dp for `ponita`, see include/enf_b200.h)
         self.tc_backward_d64 = bool(tc_backward_d64)
+        # bounded-memory training (ENF_FLAG_RECOMPUTE): no per-(query, latent) stash; the backward re-runs the pair forward
+        # per chunk of `chunk_fields` fields (0: library default), or of as many fields as fit `workspace_cap_bytes`
+        self.recompute = bool(recompute) or workspace_cap_bytes is not None
+        self.chunk_fields, self.workspace_cap_bytes = int(chunk_fields), workspace_cap_bytes
+        self.out_bf16 = bool(out_bf16)       # forward-only calls return bfloat16 (ENF_FLAG_OUT_BF16, num_out <= 4)
 
     # -- nef.init(key, x, p, a, window) (pde_trainer.py:99-102) -----------------------------------------
     def init(self, key, x, p, a, gaussian_window_size=None):
@@ -242,6 +255,17 @@ class EquivariantCrossAttentionNeF:
         # forward only (validation roll-outs, pde_trainer.py:389-405): nothing is kept for a backward
         if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p, a, sigma, *leaves))):
             desc["flags"] |= _lib.FLAG_FORWARD_ONLY
+            if self.out_bf16:
+                desc["flags"] |= _lib.FLAG_OUT_BF16
+        elif self.recompute:
+            desc["flags"] |= _lib.FLAG_RECOMPUTE
+            desc["chunk_fields"] = self.chunk_fields
+            if self.workspace_cap_bytes is not None:
+                n = _lib.load().enf_xattn_chunk_for_cap(ctypes.byref(_lib.EnfDesc(**desc)), int(self.workspace_cap_bytes))
+                if n <= 0:
+                    raise _lib.EnfLibraryError(f"workspace_cap_bytes={self.workspace_cap_bytes} is too small for this problem "
+                                               "even with one field per backward chunk")
+                desc["chunk_fields"] = n
         return _XAttnFunction.apply((desc, x_shared), x_arg, p, a, sigma, *leaves)
 
     __call__ = apply

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ENF_B200_ABI_VERSION 1
+#define ENF_B200_ABI_VERSION 2
 
 /* cfg.nef.invariant_type -> get_ca_invariant (enf/steerable_attention/invariant/__init__.py:47-78) */
 enum EnfInvariantKind {
@@ -63,7 +63,17 @@ enum EnfFlags {
    * only, the backward on the fp32 kernels).  Opt-in because the 16-bit operand noise of the logit cotangents is
    * amplified by the cancelling sum over queries in d(pose) of the non-periodic window: measured 3e-3 on dp for
    * `ponita`, outside the 2e-3 bucket (other invariants and all other gradients are inside it). */
-  ENF_FLAG_TC_BACKWARD_D64 = 2
+  ENF_FLAG_TC_BACKWARD_D64 = 2,
+  /* bounded-memory training (tensor-core precision mode): the forward keeps NO per-(query, latent) tensor for the
+   * backward; enf_xattn_bwd walks the fields in chunks of EnfDesc.chunk_fields and re-runs the fused pair forward on each
+   * chunk to rebuild that chunk's operand stash before its backward kernels.  The workspace then scales with
+   * chunk_fields instead of B for everything that is O(B*C*Z) (use enf_xattn_chunk_for_cap to size it against a byte
+   * budget); the price is one extra pair-forward pass per backward.  Results are bit-identical to the default (stash)
+   * mode.  A no-op for the fp32 kernels, which always recompute. */
+  ENF_FLAG_RECOMPUTE = 4,
+  /* forward only, num_out <= 4: `out` is written as bfloat16 [B,C,O] instead of float32 (validation / visualisation
+   * roll-outs decode B*T fields over the full grid, _base_pde_trainer.py:446-457). */
+  ENF_FLAG_OUT_BF16 = 8
 };
 
 enum EnfError {
@@ -83,7 +93,7 @@ typedef struct EnfDesc {
   int32_t B;               /* fields (signals) in the call                                */
   int32_t C;               /* coordinate queries per field                                */
   int32_t Z;               /* latents per field                                           */
-  int32_t d;               /* num_hidden  (multiple of 16, <= 128)                        */
+  int32_t d;               /* num_hidden  (16, 32, 64 or 128)                             */
   int32_t H;               /* num_heads   (1..4)                                          */
   int32_t L;               /* latent_dim                                                  */
   int32_t O;               /* num_out                                                     */
@@ -92,6 +102,8 @@ typedef struct EnfDesc {
   int32_t use_window;      /* use_gaussian_window                                         */
   int32_t precision;       /* EnfPrecision                                                */
   int32_t flags;           /* EnfFlags (0 = training: the workspace keeps the state enf_xattn_bwd needs) */
+  int32_t chunk_fields;    /* ENF_FLAG_RECOMPUTE: fields per backward chunk (0 = default: min(B, 4)); else ignored */
+  int32_t reserved[3];     /* must be 0                                                   */
 } EnfDesc;
 
 /* The parameter leaves of nef.init(...)['params'] (Flax tree), as device pointers.
@@ -139,6 +151,19 @@ int enf_pose_dim(int invariant_kind, int Dx);
  * it carries the forward state (softmax statistics, decode-MLP activations, per-latent folds). */
 size_t enf_xattn_workspace_bytes(const EnfDesc* desc);
 
+/* ENF_FLAG_RECOMPUTE: the largest chunk_fields (1..B) whose workspace fits in cap_bytes; 0 if even one field per chunk
+ * does not fit (or on a bad description).  `desc->chunk_fields` is ignored. */
+int enf_xattn_chunk_for_cap(const EnfDesc* desc, size_t cap_bytes);
+
+/* Which kernels enf_xattn_fwd / enf_xattn_bwd run for this description (what bench.py labels its lines with):
+ *   *fwd_tc, *bwd_tc = 1 when the fused pair forward / backward run on the tcgen05 kernels, 0 = fp32 FMA kernels.
+ * Returns 0, or a negative EnfError on a bad description.  Either pointer may be NULL. */
+int enf_xattn_dispatch(const EnfDesc* desc, int* fwd_tc, int* bwd_tc);
+
+/* Forget the forward state kept for `workspace` (call before freeing or reusing the buffer for something else).
+ * enf_xattn_bwd may be called any number of times after one enf_xattn_fwd (it does not consume the forward state). */
+void enf_workspace_release(void* workspace);
+
 /* out[B,C,O] = nef.apply(params, x, p, a, sigma)                       (replaces pde_trainer.py:184,478,537)
  *   x      [B,C,Dx]  with x_batch_stride = C*Dx, or ONE shared [C,Dx] grid with x_batch_stride = 0
  *   p      [B,Z,P]   raw latent poses (P = enf_pose_dim), a [B,Z,L], sigma [B,Z,1] (may be NULL iff !use_window)
@@ -146,10 +171,11 @@ size_t enf_xattn_workspace_bytes(const EnfDesc* desc);
 int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w,
                   const float* x, int64_t x_batch_stride,
                   const float* p, const float* a, const float* sigma,
-                  float* out, void* workspace, size_t workspace_bytes, enf_stream_t stream);
+                  float* out, void* workspace, size_t workspace_bytes, enf_stream_t stream);   /* out: bf16 with ENF_FLAG_OUT_BF16 */
 
 /* Reverse pass for cotangent d_out[B,C,O] of the enf_xattn_fwd call last issued on `workspace`
- * with the same arguments.                                      (replaces jax.grad at pde_trainer.py:188,255)
+ * with the same arguments (x_batch_stride included; checked).   (replaces jax.grad at pde_trainer.py:188,255)
+ * Repeatable: the forward state is not consumed, a second call with another cotangent gives that cotangent's gradients.
  *   dW      weight gradients (overwritten); NULL => latent gradients only (ode phase, pde_trainer.py:302)
  *   dp[B,Z,P], da[B,Z,L], dsigma[B,Z,1] overwritten (dsigma may be NULL; zeros if !use_window)
  */

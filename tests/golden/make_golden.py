@@ -58,6 +58,12 @@ CASES = {
                          freq=(0.2, 0.3), window=True),
     "abs_pos": dict(invariant_type="abs_pos", num_in=2, d=16, H=2, L=4, O=1, B=2, C=10, Z=4,
                     freq=(0.2, 0.3), window=True),
+    # BallLatInvariant: the reference's __call__ (ball_lat.py:77-87) concatenates the un-broadcast radii (B,C,1,1) / (B,1,Z,1)
+    # and raises.  The fixture runs the reference's NeF, its window (ball_lat.py:36-52) and the first four invariants as
+    # written, through a subclass whose __call__ is the reference's body with ONLY those two radii broadcast to (B,C,Z,1)
+    # -- what ball.py:90-92 does for the same quantities (BallLatFixed below).
+    "ball_lat": dict(invariant_type="ball_lat", num_in=3, d=16, H=2, L=4, O=2, B=2, C=14, Z=5,
+                     freq=(0.2, 0.5), window=True),
 }
 
 
@@ -83,12 +89,34 @@ def unflatten(flat):
     return out
 
 
+def ball_lat_fixed():
+    import jax.numpy as jnp
+    from enf.steerable_attention.invariant.ball_lat import BallLatInvariant
+
+    class BallLatFixed(BallLatInvariant):
+        def __call__(self, x, p):
+            B, C, Z = x.shape[0], x.shape[1], p.shape[1]
+            try:                               # the reference's own body: fails on the concatenate (documented quirk)
+                return super().__call__(x, p)
+            except ValueError:
+                pass
+            phi_x = jnp.broadcast_to(x[:, :, None, 0], (B, C, Z))[..., None]
+            theta_x = jnp.broadcast_to(x[:, :, None, 1], (B, C, Z))[..., None]
+            phi_p = jnp.broadcast_to(p[:, None, :, 0], (B, C, Z))[..., None]
+            theta_p = jnp.broadcast_to(p[:, None, :, 1], (B, C, Z))[..., None]
+            r_x = jnp.broadcast_to(x[:, :, 2][:, :, None, None], (B, C, Z, 1))
+            r_p = jnp.broadcast_to(p[:, :, 3][:, None, :, None], (B, C, Z, 1))
+            return jnp.concatenate([theta_x, theta_p, jnp.cos(phi_x - phi_p), jnp.sin(phi_x - phi_p), r_x, r_p], axis=-1)
+
+    return BallLatFixed()
+
+
 def build_case(name, c, rng):
     cfg = types.SimpleNamespace(invariant_type=c["invariant_type"], num_in=c["num_in"])
-    ca_inv = get_ca_invariant(cfg)
+    ca_inv = ball_lat_fixed() if c["invariant_type"] == "ball_lat" else get_ca_invariant(cfg)
     nef = EquivariantCrossAttentionNeF(
         num_hidden=c["d"], num_heads=c["H"], num_layers=0, num_out=c["O"], latent_dim=c["L"],
-        self_attn_invariant=get_sa_invariant(cfg), cross_attn_invariant=ca_inv,
+        self_attn_invariant=ca_inv if c["invariant_type"] == "ball_lat" else get_sa_invariant(cfg), cross_attn_invariant=ca_inv,
         embedding_type="rff", embedding_freq_multiplier=list(c["freq"]),
         condition_value_transform=True, use_gaussian_window=c["window"])
     B, C, Z = c["B"], c["C"], c["Z"]
@@ -98,7 +126,7 @@ def build_case(name, c, rng):
         p = latent_utils.init_positions_polar(None, (B, Z, 2))
         x = np.stack([rng.uniform(0, 2 * np.pi, (B, C)), rng.uniform(0.05, np.pi - 0.05, (B, C))], -1)
         sigma0 = 2 * np.pi / int(round((Z // 2) ** 0.5))
-    elif t == "ball":
+    elif t in ("ball", "ball_lat"):
         p = latent_utils.init_positions_ball(None, (B, Z, 4))
         x = np.stack([rng.uniform(0, 2 * np.pi, (B, C)), rng.uniform(0.05, np.pi - 0.05, (B, C)),
                       rng.uniform(0, 1, (B, C))], -1)
@@ -169,8 +197,26 @@ def build_case(name, c, rng):
     return rec
 
 
+def latent_fixture():
+    """Outputs of the reference's own latent initialisers (enf/latents/utils.py) for the BASELINE shapes: pins
+    enf_pde_b200/latents.py (the product's restatement) independently of the oracle's."""
+    rec = {}
+    for Z, n in ((25, 2), (64, 2), (27, 3)):
+        rec[f"grid_{Z}_{n}"] = np.asarray(latent_utils.init_positions_grid(None, (2, Z, n)), np.float64)
+    for Z in (18, 8, 128):
+        rec[f"polar_{Z}"] = np.asarray(latent_utils.init_positions_polar(None, (2, Z, 2)), np.float64)
+    for Z in (25, 256):
+        rec[f"ball_{Z}"] = np.asarray(latent_utils.init_positions_ball(None, (2, Z, 4)), np.float64)
+    rec["ori_25"] = np.asarray(latent_utils.init_ori_rotation_invariant_s2(None, (2, 25, 2)), np.float64)
+    return rec
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "latent_init.npz"), **latent_fixture())
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         rec = build_case(name, c, rng)
         path = os.path.join(HERE, f"ref_{name}.npz")

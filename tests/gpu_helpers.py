@@ -9,7 +9,7 @@ import torch
 from enf_pde_b200 import _lib
 from enf_pde_b200.nef import _weights_struct, params_to_leaves
 from folded_model import Folded, LEAF_PATHS
-from helpers import rel_err
+from helpers import rel_err, leaf_errs
 
 
 def desc_for(cfg, B, C, Z, precision=0):
@@ -84,9 +84,7 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
     errs["dp"] = rel_err(dp.cpu(), dp_ref)
     errs["da"] = rel_err(da.cpu(), da_ref)
     errs["dsigma"] = rel_err(dsig.cpu(), ds_ref) if cfg.use_gaussian_window else 0.0
-    gscale = max(float(G[k].abs().max()) for k in G)
-    for leaf, g in zip(_lib.LEAVES, grads):
-        errs["gw_" + leaf] = float((g.cpu().double() - G[leaf]).abs().max()) / max(gscale, 1e-30)
-        errs["self_" + leaf] = rel_err(g.cpu(), G[leaf])
+    for leaf, e in leaf_errs({n: g.cpu() for n, g in zip(_lib.LEAVES, grads)}, {n: G[n] for n in _lib.LEAVES}).items():
+        errs["gw_" + leaf] = e            # per leaf, floored (helpers.leaf_errs)
     res = dict(out=out, dp=dp, da=da, dsigma=dsig, grads=grads, launches=lib.enf_last_launch_count())
     return res, errs

@@ -39,6 +39,38 @@ def rel_err(got, want):
     return (got - want).abs().max().item() / denom
 
 
+def rms_err(got, want):
+    """rms(got - want) / rms(want): the second, averaged bound kept next to rel_err's max-norm one."""
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    denom = want.pow(2).mean().sqrt().item()
+    num = (got - want).pow(2).mean().sqrt().item()
+    return num if denom == 0.0 else num / denom
+
+
+LEAF_FLOOR = 1e-2
+
+
+def leaf_errs(got, want, floor=LEAF_FLOOR):
+    """PER-LEAF weight-gradient errors: max |got - want| over a leaf divided by that leaf's own largest reference entry,
+    with a floor of `floor` x the largest entry over all leaves (a leaf whose true gradient is (near) zero -- the frozen RFF
+    coefficients, a bias behind a dead unit -- has no scale of its own).  `got`, `want`: flat {name: tensor} dicts."""
+    gmax = max(float(v.abs().max()) for v in want.values())
+    out = {}
+    for k, w in want.items():
+        w = w.double().cpu()
+        g = torch.as_tensor(got[k]).double().cpu()
+        scale = max(float(w.abs().max()), floor * gmax, 1e-300)
+        out[k] = float((g - w).abs().max()) / scale
+    return out
+
+
+def worst_leaf(got, want, floor=LEAF_FLOOR):
+    e = leaf_errs(got, want, floor)
+    k = max(e, key=e.get)
+    return e[k], k
+
+
 def make_case(cfg, B, C, Z, seed=0, dtype=torch.float64, polar_grid=None, perturb=0.1, jitter=0.05):
     """Seeded synthetic inputs + weights for a config (poses from the reference's initialisers, jittered)."""
     g = torch.Generator().manual_seed(seed)

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.enf_abi_version() == 1
+    assert lib.enf_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     names = re.findall(r"\*\s*([a-z0-9_]+)", body)
     assert tuple(names) == _lib.LEAVES
     assert len(_lib.LEAVES) == 46 and set(_lib.LEAF_PATHS) == set(_lib.LEAVES)
-    assert ctypes.sizeof(_lib.EnfDesc) == 48 and ctypes.sizeof(_lib.EnfWeights) == 46 * 8
+    assert ctypes.sizeof(_lib.EnfDesc) == 64 and ctypes.sizeof(_lib.EnfWeights) == 46 * 8
 
 
 def test_invariant_dims_match_reference_classes():
@@ -47,10 +47,47 @@ def test_bad_descriptions_are_rejected_without_a_gpu():
     lib = E.load_library()
     ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, flags=0)
     assert lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**ok))) > 0
-    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=4)):
+    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=16),
+                dict(flags=_lib.FLAG_OUT_BF16), dict(chunk_fields=-1), dict(B=400, Z=64, H=4)):
         d = _lib.EnfDesc(**{**ok, **bad})
         assert lib.enf_xattn_workspace_bytes(ctypes.byref(d)) == 0, bad
         assert lib.enf_last_error() != b""
+
+
+def test_limits_and_dispatch_are_reported():
+    """B*Z*H <= 65535 per call (the stage kernels' grid z-dimension); enf_xattn_dispatch names the kernels a description gets."""
+    lib = E.load_library()
+    ok = dict(B=32, C=4096, Z=64, d=128, H=2, L=16, O=1, Dx=2, invariant_kind=3, use_window=1, precision=1, flags=0)
+    assert _lib.dispatch(_lib.EnfDesc(**ok)) == (True, True)
+    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "precision": 0})) == (False, False)
+    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "d": 32, "H": 3})) == (False, False)          # fp32 kernels in either mode
+    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "flags": _lib.FLAG_FORWARD_ONLY})) == (True, False)
+    big = _lib.EnfDesc(**{**ok, "B": 512})                                                      # 512 * 64 * 2 = 65536
+    assert lib.enf_xattn_workspace_bytes(ctypes.byref(big)) == 0 and b"65535" in lib.enf_last_error()
+    assert lib.enf_xattn_dispatch(ctypes.byref(big), None, None) == -2
+    edge = _lib.EnfDesc(**{**ok, "B": 511, "C": 128, "flags": _lib.FLAG_FORWARD_ONLY})
+    assert lib.enf_xattn_workspace_bytes(ctypes.byref(edge)) > 0
+
+
+def test_recompute_mode_bounds_the_workspace():
+    """ENF_FLAG_RECOMPUTE: nothing O(B*C*Z) is kept between forward and backward; the workspace scales with chunk_fields and
+    enf_xattn_chunk_for_cap inverts that.  ns64 (BASELINE config 2) trains within 2.75 GiB (8.9 GiB with the stash)."""
+    lib = E.load_library()
+    kw = dict(B=32, C=4096, Z=64, d=128, H=2, L=16, O=1, Dx=2, invariant_kind=3, use_window=1, precision=1)
+    size = lambda **o: lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**{**kw, **o})))
+    stash = size(flags=0)
+    sizes = [size(flags=_lib.FLAG_RECOMPUTE, chunk_fields=n) for n in (1, 2, 4, 8, 32)]
+    assert all(a < b for a, b in zip(sizes, sizes[1:])) and sizes[-1] == stash
+    assert size(flags=_lib.FLAG_RECOMPUTE) == sizes[2]                                          # default chunk: 4 fields
+    assert sizes[0] < 2.75 * 2 ** 30 and sizes[0] < 0.32 * stash, sizes[0]
+    d = _lib.EnfDesc(**kw, flags=0)
+    for cap_gib, in (3.0,), (4.0,), (100.0,):
+        n = lib.enf_xattn_chunk_for_cap(ctypes.byref(d), int(cap_gib * 2 ** 30))
+        assert 1 <= n <= 32 and size(flags=_lib.FLAG_RECOMPUTE, chunk_fields=n) <= cap_gib * 2 ** 30
+        assert n == 32 or size(flags=_lib.FLAG_RECOMPUTE, chunk_fields=n + 1) > cap_gib * 2 ** 30
+    assert lib.enf_xattn_chunk_for_cap(ctypes.byref(d), 1 << 20) == 0
+    # the fp32 kernels always recompute: the flag changes nothing there
+    assert size(precision=0, flags=_lib.FLAG_RECOMPUTE) == size(precision=0, flags=0)
 
 
 def test_jax_binding_module_is_importable_and_refuses_without_jax():

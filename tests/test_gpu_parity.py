@@ -1,14 +1,15 @@
 """Parity of the CUDA path (through the C ABI) against the oracle, on a B200.  `-m gpu`.
 
 Tolerance: BASELINE.json's fp32 bucket, 1e-4, on the metric max|got-want| / max|want| (helpers.rel_err),
-for the decoded field and for the latent gradients; weight gradients are held to the same number
-relative to the largest weight-gradient entry."""
+for the decoded field and for the latent gradients (plus the same bound on rms(got-want) / rms(want)); weight
+gradients are held to the same number PER LEAF (helpers.leaf_errs: each of the 46 leaves against its own largest
+reference entry, floored at 1e-2 of the largest entry over all leaves)."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import enf_ref as R
-from helpers import golden_names, load_golden, rel_err, make_case
+from helpers import golden_names, load_golden, rel_err, rms_err, leaf_errs, worst_leaf, make_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -62,11 +63,9 @@ def test_golden_through_public_api(name):
     assert rel_err(da, da_ref) < TOL
     if cfg.use_gaussian_window:
         assert rel_err(ds, ds_ref) < TOL
-    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
-    scale = max(float(v.abs().max()) for v in fr.values())
-    for k in fr:
-        err = float((fg[k].double().cpu() - fr[k]).abs().max()) / scale
+    for k, err in leaf_errs(R.tree_flatten(g["params"]), R.tree_flatten(dth_ref["params"])).items():
         assert err < TOL, (k, err)
+    assert rms_err(out, rec["out"]) < TOL and rms_err(dp, dp_ref) < TOL and rms_err(da, da_ref) < TOL
 
 
 CASES = [
@@ -81,6 +80,11 @@ CASES = [
                      embedding_freq_multiplier=(0.05, 0.2)), 1, 90, 18, (6, 3)),
     ("ihc_d32_h3", dict(num_in=3, num_hidden=32, num_heads=3, num_out=1, latent_dim=32, invariant_type="ball",
                         embedding_freq_multiplier=(0.2, 0.5)), 2, 200, 40, None),
+    # BallLatInvariant (ball_lat.py:36-88): the reference's __call__ concatenates un-broadcast radii and raises (:77-87), so
+    # there is no reference-source golden for it; the oracle implements the evident broadcast (oracle/enf_ref.py) and is
+    # itself checked against finite differences in tests/test_oracle_golden.py
+    ("ball_lat_d32", dict(num_in=3, num_hidden=32, num_heads=2, num_out=2, latent_dim=8, invariant_type="ball_lat",
+                          embedding_freq_multiplier=(0.2, 0.5)), 2, 150, 12, None),
     ("ragged_tile", dict(num_in=2, num_hidden=32, num_heads=4, num_out=2, latent_dim=8, invariant_type="rel_pos",
                          embedding_freq_multiplier=(0.2, 0.3)), 2, 33, 1, None),       # C % 32 = 1, single latent
     ("one_query", dict(num_in=1, num_hidden=16, num_heads=1, num_out=1, latent_dim=1, invariant_type="norm_rel_pos",
@@ -106,10 +110,9 @@ def test_config_shapes_against_oracle(case):
             assert float((ds.double().cpu() - ds_ref).abs().max()) < 2e-7 * float(d_out.abs().max())
         else:
             assert rel_err(ds, ds_ref) < TOL
-    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
-    scale = max(float(v.abs().max()) for v in fr.values())
-    for k in fr:
-        assert float((fg[k].double().cpu() - fr[k]).abs().max()) / scale < TOL, k
+    for k, err in leaf_errs(R.tree_flatten(g["params"]), R.tree_flatten(dth_ref["params"])).items():
+        assert err < TOL, (k, err)
+    assert rms_err(out, out_ref) < TOL and rms_err(dp, dp_ref) < TOL and rms_err(da, da_ref) < TOL
 
 
 def test_shared_coordinate_grid_matches_per_field_copy():
@@ -184,10 +187,9 @@ def test_tensor_core_path_against_oracle(case):
     out, g, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="bf16")
     errs = dict(out=rel_err(out, out_ref), dp=rel_err(dp, dp_ref), da=rel_err(da, da_ref),
                 ds=rel_err(ds, ds_ref) if cfg.use_gaussian_window else 0.0)
-    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
-    scale = max(float(v.abs().max()) for v in fr.values())
-    errs["dtheta"] = max(float((fg[k].double().cpu() - fr[k]).abs().max()) / scale for k in fr)
-    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()})
+    errs["dtheta"], worst = worst_leaf(R.tree_flatten(g["params"]), R.tree_flatten(dth_ref["params"]))
+    errs["out_rms"], errs["dp_rms"], errs["da_rms"] = rms_err(out, out_ref), rms_err(dp, dp_ref), rms_err(da, da_ref)
+    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst)
     assert all(v < TOL_BF16 for v in errs.values()), errs
 
 
@@ -215,10 +217,9 @@ def test_tensor_core_multi_tile_against_oracle(case):
     out, g, dp, da, ds = _api_fwd_bwd(cfg, params, x, p, a, sigma, d_out, precision="bf16")
     errs = dict(out=rel_err(out, out_ref), dp=rel_err(dp, dp_ref), da=rel_err(da, da_ref),
                 ds=rel_err(ds, ds_ref) if cfg.use_gaussian_window else 0.0)
-    fr, fg = R.tree_flatten(dth_ref["params"]), R.tree_flatten(g["params"])
-    scale = max(float(v.abs().max()) for v in fr.values())
-    errs["dtheta"] = max(float((fg[k].double().cpu() - fr[k]).abs().max()) / scale for k in fr)
-    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()})
+    errs["dtheta"], worst = worst_leaf(R.tree_flatten(g["params"]), R.tree_flatten(dth_ref["params"]))
+    errs["out_rms"], errs["dp_rms"], errs["da_rms"] = rms_err(out, out_ref), rms_err(dp, dp_ref), rms_err(da, da_ref)
+    print(case[0], {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst)
     assert all(v < TOL_BF16 for v in errs.values()), errs
 
 
@@ -237,12 +238,12 @@ def test_forward_only_matches_training_forward(precision):
     f = lambda t: t.to("cuda", torch.float32)
     pg = f(p).requires_grad_(True)
     out_train = nef.apply(P, f(x), pg, f(a), f(sigma))
-    ws_train = _XAttnFunction.last_ws[1].numel()
+    ws_train = _XAttnFunction.last_ws[2]
     assert _XAttnFunction.last_ws[0]["flags"] == 0
     with torch.no_grad():
         out_inf = nef.apply(P, f(x), f(p), f(a), f(sigma))
     assert _XAttnFunction.last_ws[0]["flags"] == _lib.FLAG_FORWARD_ONLY
-    assert _XAttnFunction.last_ws[1].numel() < ws_train
+    assert _XAttnFunction.last_ws[2] < ws_train
     assert torch.equal(out_inf, out_train.detach())
     lib = _lib.load()
     desc = _lib.EnfDesc(**_XAttnFunction.last_ws[0])

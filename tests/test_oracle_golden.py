@@ -41,3 +41,29 @@ def test_param_tree_names_match_reference_module_structure():
     assert sorted(ours) == sorted(theirs)
     for k in ours:
         assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
+
+
+def test_latent_initialisers_match_reference_source():
+    """enf_pde_b200/latents.py (product) and the oracle's copy, each against outputs of the reference's own
+    enf/latents/utils.py (tests/golden/latent_init.npz, written by make_golden.py)."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN_DIR
+    from enf_pde_b200 import latents as PL
+    z = np.load(os.path.join(GOLDEN_DIR, "latent_init.npz"))
+    for mod in (PL, R):
+        for key in z.files:
+            kind, *dims = key.split("_")
+            want = z[key]
+            if kind == "grid":
+                got = mod.init_positions_grid(2, int(dims[0]), int(dims[1]))
+            elif kind == "polar":
+                n_theta = int(round((int(dims[0]) // 2) ** 0.5))
+                got = mod.init_positions_polar(2, 2 * n_theta, n_theta)
+            elif kind == "ball":
+                got = mod.init_positions_ball(2, int(dims[0]))
+            else:        # orientation angle of the ponita poses (utils.py:106-109)
+                g = mod.init_positions_grid(2, int(dims[0]), 2)
+                got = np.arctan2(g[:, :, 0], g[:, :, 1])[:, :, None]
+            assert got.shape == want.shape, (mod.__name__, key)
+            assert np.abs(got - want).max() < 1e-12, (mod.__name__, key)
