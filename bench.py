@@ -17,6 +17,11 @@ weight gradients) for an MSE loss against synthetic targets.  Prints ONE JSON li
 
 N > 1 (torchrun, one process per GPU): fields shard across ranks with no data-path collective (weak scaling,
 per-rank batch fixed); the outer-loop weight gradients are all-reduced with NCCL inside the timed step.
+  --scaling strong      the config's global batch is SPLIT over the ranks (total work fixed)
+  --partition queries   every rank takes all fields and a slice of the coordinate queries (SURVEY 8e fallback for fewer
+                        fields than ranks); latent gradients join the weight gradients in the all-reduce
+  --forward-only        validation / visualisation roll-out: `nef.apply` under no_grad over --fields signals
+  --recompute           bounded-memory training (ENF_FLAG_RECOMPUTE), chunk size --chunk-fields
 """
 import argparse
 import ctypes
@@ -59,6 +64,22 @@ def flops_per_pair(cfg, I):
 def flops_per_query_tail(cfg):
     d, H, O = cfg["d"], cfg["H"], cfg["O"]
     return 2 * H * d * d + 6 * (H * d) ** 2 + 2 * H * d * d + 2 * d * d + 2 * d * O
+
+
+def pipe_times(cfg, I, pairs, queries, peaks, passes=3.0, sm_mhz=1965.0):
+    """Seconds each pipe needs for one step at 100 %: tensor (contract FLOP / measured dense 16-bit peak), MUFU
+    ((2+H) d transcendentals per pair and pass-pair, 16 / clk / SM), fp32 FMA (the element-wise epilogue work, ~(40+20H) d flop
+    per pair forward, 256 flop / clk / SM).  passes: 3 = fwd + bwd, 1 = forward only."""
+    f_alg, _ = flops_per_pair(cfg, I)
+    d, H = cfg["d"], cfg["H"]
+    clk = sm_mhz * 1e6
+    tensor = passes * (f_alg * pairs + flops_per_query_tail(cfg) * queries) / (peaks["bf16_sustained"] * 1e12)
+    mufu = (2.0 if passes > 1 else 1.0) * (2 + H) * d * pairs / (16 * 148 * clk)      # x2 for fwd + bwd (SURVEY 8d)
+    fma = passes * (40 + 20 * H) * d * pairs / (256 * 148 * clk)
+    return {"tensor": tensor, "mufu": mufu, "fma": fma}
+
+
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12        # 74.4: 128 fp32 FMA lanes / SM / clk at the measured max SM clock
 
 
 def read_peaks():
@@ -170,6 +191,22 @@ def cpu_leg(cfg, steps, warmup, budget_s=25.0):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
 
+def reference_probe():
+    """prefer the real reference (JAX CPU backend) when it can be imported -- from the environment or
+    from a driver-provided install under baseline/_ref -- else the oracle port.  Returns (kind, why)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import jax      # noqa: F401
+        import flax     # noqa: F401
+    except Exception as e:      # noqa: BLE001
+        return "port", f"jax/flax not importable here ({type(e).__name__}); timing the PyTorch-CPU restatement (oracle/enf_ref.py)"
+    if not os.path.isdir("/root/reference") and not os.path.isdir(os.path.join(ref_dir, "enf")):
+        return "port", "jax present but the reference sources are not on this box; timing the oracle port"
+    return "reference", "jax importable: the reference modules could be timed on JAX_PLATFORMS=cpu"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,25 +217,37 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="fp32: FMA kernels (<=1e-4 bucket); bf16: tcgen05 kernels with 16-bit operands (<=2e-3 bucket)")
-    ap.add_argument("--tc-backward-d64", action="store_true",
-                    help="d = 64 configs in bf16 mode: tcgen05 backward too (ENF_FLAG_TC_BACKWARD_D64; dp of `ponita` reaches 3e-3)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch PER GPU (default, the driver's SCALE line); strong: the config's batch split over the GPUs")
+    ap.add_argument("--partition", default="auto", choices=["auto", "fields", "queries"],
+                    help="what is sharded over ranks; auto = fields when every rank gets one, else queries (SURVEY 8e)")
+    ap.add_argument("--forward-only", action="store_true", help="forward-only roll-out line (SURVEY 8f-2)")
+    ap.add_argument("--fields", type=int, default=None, help="override the number of fields per call (forward-only default: 480 = 8 x 60 frames)")
+    ap.add_argument("--out-bf16", action="store_true", help="forward-only: bfloat16 decoded field (ENF_FLAG_OUT_BF16)")
+    ap.add_argument("--recompute", action="store_true", help="bounded-memory training: ENF_FLAG_RECOMPUTE")
+    ap.add_argument("--chunk-fields", type=int, default=0)
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    C = int(math.prod(cfg["grid"]))
-    workload = {"workload": f"{args.config}: {cfg['label']}", "B_per_gpu": cfg["B"], "C": C, "Z": cfg["Z"], "d": cfg["d"],
-                "H": cfg["H"], "invariant": cfg["invariant_type"], "latent_dim": cfg["L"], "num_out": cfg["O"]}
+    C_full = int(math.prod(cfg["grid"]))
+    if args.fields is not None:
+        cfg["B"] = args.fields
+    elif args.forward_only:
+        cfg["B"] = 480 if args.config == "ns64" else cfg["B"]          # pde_trainer.py:389-405: 8 signals x 60 roll-out frames
 
     if args.impl == "reference":
         if rank != 0:
             return
+        kind, why = reference_probe()
+        workload = {"workload": f"{args.config}: {cfg['label']}", "B_per_gpu": cfg["B"], "C": C_full, "Z": cfg["Z"], "d": cfg["d"],
+                    "H": cfg["H"], "invariant": cfg["invariant_type"], "latent_dim": cfg["L"], "num_out": cfg["O"]}
         r = cpu_leg(cfg, max(1, args.steps), args.warmup, budget_s=120.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {**{k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}, "probe": why},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -206,7 +255,8 @@ def main():
     import torch
     import enf_pde_b200 as E
     from enf_pde_b200 import _lib
-    from enf_pde_b200.dist import allreduce_weight_grads
+    from enf_pde_b200.dist import allreduce_weight_grads, allreduce_grads, field_shard, query_shard, choose_partition
+    from enf_pde_b200.nef import _XAttnFunction
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
@@ -217,28 +267,49 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = E.load_library()
 
+    # ---- what this rank owns ---------------------------------------------------------------------------------------------
+    B_global = cfg["B"] * (world if args.scaling == "weak" else 1)
+    partition = args.partition
+    if partition == "auto":
+        partition = "fields" if args.scaling == "weak" else choose_partition(B_global, world)
+    if partition == "fields":
+        B = cfg["B"] if args.scaling == "weak" else len(range(B_global)[field_shard(B_global, rank, world)])
+        q_slice = slice(0, C_full)
+    else:
+        B = B_global if args.scaling == "strong" else cfg["B"]
+        q_slice = query_shard(C_full, rank, world)
+    C = q_slice.stop - q_slice.start
+    Z = cfg["Z"]
+    workload = {"workload": f"{args.config}: {cfg['label']}", "B_per_gpu": B, "C": C_full, "C_per_gpu": C, "Z": Z, "d": cfg["d"],
+                "H": cfg["H"], "invariant": cfg["invariant_type"], "latent_dim": cfg["L"], "num_out": cfg["O"]}
+
     inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
     nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True,
-                                         cfg["window"], precision=args.precision, tc_backward_d64=args.tc_backward_d64)
-    B, Z = cfg["B"], cfg["Z"]
+                                         cfg["window"], precision=args.precision,
+                                         recompute=args.recompute, chunk_fields=args.chunk_fields, out_bf16=args.out_bf16)
     gen = torch.Generator().manual_seed(1234 + rank)
     p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])
     p_h = p_h + 0.02 * torch.randn(p_h.shape, generator=gen)
     a_h = a_h + 0.1 * torch.randn(a_h.shape, generator=gen)
     from enf_pde_b200.latents import make_coords
-    x_h = make_coords(inv, cfg["grid"]).contiguous()                              # (C, Dx), shared by all fields
+    x_h = make_coords(inv, cfg["grid"])[q_slice].contiguous()                     # (C, Dx), shared by all fields
     y_h = torch.randn(B, C, cfg["O"], generator=gen)
     variables = nef.init(0, x_h[None], p_h.to(dev), a_h.to(dev), s_h.to(dev))     # same weights on every rank
     leaves = E.params_to_leaves(variables)
-    for t in leaves:
-        t.requires_grad_(True)
+    if not args.forward_only:
+        for t in leaves:
+            t.requires_grad_(True)
     use_sigma = cfg["window"]
 
     x_d, y_d = x_h.to(dev), y_h.to(dev)
-    p_d, a_d, s_d = (t.to(dev).requires_grad_(True) for t in (p_h, a_h, s_h))
-    n_out = B * C * cfg["O"]
+    p_d, a_d, s_d = (t.to(dev).requires_grad_(not args.forward_only) for t in (p_h, a_h, s_h))
+    n_out = B_global * C_full * cfg["O"] if args.scaling == "strong" else B * C * cfg["O"]
 
     def step_device(x, y, p, a, s):
+        if args.forward_only:
+            with torch.no_grad():
+                out = nef.apply(variables, x[None].expand(B, -1, -1), p, a, s if use_sigma else None)
+            return out
         for t in leaves:
             t.grad = None
         p.grad = a.grad = None
@@ -249,7 +320,11 @@ def main():
         loss = (diff * diff).mean()
         out.backward(diff * (2.0 / n_out))
         if world > 1:
-            allreduce_weight_grads([t.grad for t in leaves])
+            if partition == "queries":      # latent gradients are sums over queries too: one packed collective for both
+                wg, lg = allreduce_grads([t.grad for t in leaves], [p.grad, a.grad] + ([s.grad] if s is not None and s.grad is not None else []))
+                p.grad, a.grad = lg[0], lg[1]
+            else:
+                allreduce_weight_grads([t.grad for t in leaves])
         return loss
 
     def barrier():
@@ -260,6 +335,8 @@ def main():
     # ---- device-resident timing -----------------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         step_device(x_d, y_d, p_d, a_d, s_d)
+    workspace_bytes = _XAttnFunction.last_ws[2]
+    chunk_used = _XAttnFunction.last_ws[0].get("chunk_fields", 0)
     lib.enf_profile_enable(1)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,13 +362,26 @@ def main():
     xh, yh, ph, ah, sh = pin(x_h), pin(y_h), pin(p_h), pin(a_h), pin(s_h)
     dp_host, da_host, ds_host = (torch.empty_like(t).pin_memory() for t in (p_h, a_h, s_h))
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * 4 for t in (xh, yh, ph, ah)) + (sh.numel() * 4 if use_sigma else 0)
-    d2h = 4 + sum(t.numel() * 4 for t in (dp_host, da_host)) + (ds_host.numel() * 4 if use_sigma else 0)
+    out_host = torch.empty(B, C, cfg["O"], dtype=torch.bfloat16 if args.out_bf16 else torch.float32).pin_memory() if args.forward_only else None
+    if args.forward_only:
+        h2d = sum(t.numel() * 4 for t in (xh, ph, ah)) + (sh.numel() * 4 if use_sigma else 0)
+        d2h = out_host.numel() * out_host.element_size()
+    else:
+        h2d = sum(t.numel() * 4 for t in (xh, yh, ph, ah)) + (sh.numel() * 4 if use_sigma else 0)
+        d2h = 4 + sum(t.numel() * 4 for t in (dp_host, da_host)) + (ds_host.numel() * 4 if use_sigma else 0)
 
     def step_e2e():
-        x = xh.to(dev, non_blocking=True); y = yh.to(dev, non_blocking=True)
-        p = ph.to(dev, non_blocking=True).requires_grad_(True); a = ah.to(dev, non_blocking=True).requires_grad_(True)
-        s = sh.to(dev, non_blocking=True).requires_grad_(True) if use_sigma else None
+        x = xh.to(dev, non_blocking=True)
+        p = ph.to(dev, non_blocking=True); a = ah.to(dev, non_blocking=True)
+        s = sh.to(dev, non_blocking=True) if use_sigma else None
+        if args.forward_only:
+            out_host.copy_(step_device(x, None, p, a, s), non_blocking=True)     # the roll-out's decoded fields go back to the host
+            torch.cuda.current_stream().synchronize()
+            return
+        y = yh.to(dev, non_blocking=True)
+        p.requires_grad_(True); a.requires_grad_(True)
+        if s is not None:
+            s.requires_grad_(True)
         loss = step_device(x, y, p, a, s)
         loss_host.copy_(loss, non_blocking=True)
         dp_host.copy_(p.grad, non_blocking=True); da_host.copy_(a.grad, non_blocking=True)
@@ -319,48 +409,90 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (fused pair backward) ----------------------------------------------
+    # ---- roofline of the dominant kernel, labelled from what the library actually dispatched ------------------------------
     peaks = read_peaks()
     I = inv.dim
     f_alg, f_ref = flops_per_pair(cfg, I)
     pairs = B * C * Z
+    desc = _lib.EnfDesc(B=B, C=C, Z=Z, d=cfg["d"], H=cfg["H"], L=cfg["L"], O=cfg["O"], Dx=cfg["num_in"],
+                        invariant_kind=_lib.INVARIANT_KINDS[cfg["invariant_type"]], use_window=int(cfg["window"]),
+                        precision=nef.precision, flags=(_lib.FLAG_FORWARD_ONLY if args.forward_only else 0))
+    fwd_tc, bwd_tc = _lib.dispatch(desc)
+    passes = 1.0 if args.forward_only else 3.0
+    clk_sum = clk.summary()
+    pt = pipe_times(cfg, I, pairs, B * C, peaks, passes=passes, sm_mhz=float(clk_sum.get("sm_max_mhz") or 1965.0))
     bwd_avg = sum(bwd_ms) / len(bwd_ms) if bwd_ms else float("nan")
     fwd_avg = sum(fwd_ms) / len(fwd_ms) if fwd_ms else float("nan")
-    achieved = 2.0 * f_alg * pairs / (bwd_avg * 1e-3) / 1e12 if bwd_ms else None
-    tcmode = args.precision == "bf16"
-    kname = ("fused pair backward = pairs_bwd_tc_a_kernel + pairs_bwd_tc_v_kernel + pairs_bwd_tc_q_kernel (tcgen05, 3 launches timed as one)"
-             if tcmode else "pairs_bwd_kernel (fused pair backward, fp32 FMA)")
+    dom_is_bwd = not args.forward_only
+    dom_tc = bwd_tc if dom_is_bwd else fwd_tc
+    dom_ms = bwd_avg if dom_is_bwd else fwd_avg
+    dom_flop = (2.0 if dom_is_bwd else 1.0) * f_alg * pairs
+    achieved = dom_flop / (dom_ms * 1e-3) / 1e12 if dom_ms == dom_ms else None
+    tag = f"<{cfg['d']},{cfg['H']}>"
+    if dom_is_bwd:
+        kname = (f"fused pair backward = pairs_bwd_tc_a_kernel{tag} + pairs_bwd_tc_v_kernel + pairs_bwd_tc_q_kernel (tcgen05, 3 launches"
+                 + (" per field chunk + the chunk's recomputed pairs_fwd_tc_kernel" if args.recompute and bwd_tc else "") + " timed as one)"
+                 if bwd_tc else f"pairs_bwd_kernel<{cfg['d']}> (fused pair backward, fp32 FMA)")
+    else:
+        kname = f"pairs_fwd_tc_kernel{tag} (tcgen05)" if fwd_tc else f"pairs_fwd_kernel<{cfg['d']}> (fp32 FMA)"
+    if dom_tc:
+        bound = max(pt, key=pt.get)             # the pipe that needs the most time at 100 %
+        peak, peak_src = peaks["bf16_sustained"], peaks["source"] + ", dense bf16 sustained"
+        # achieved / peak stay in tensor TFLOP/s (the contract's unit); when another pipe binds, the fraction of THAT roof is the
+        # bound's time at 100 % over the kernel's share of it
+        frac = achieved / peak if achieved else None
+    else:
+        bound = "fp32-fma"                       # every GEMM of the fp32 kernels runs on the FMA pipe
+        peak, peak_src = FP32_FMA_PEAK_TFLOPS, "nominal: 148 SM x 128 FMA lanes x 2 x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)"
+        frac = achieved / peak if achieved else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu --set full captures
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.config}:{args.precision}", {}).get("bwd_dram_bytes")
-    roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved,
-                "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-                "traffic": traffic, "peak_source": peaks["source"] + ", dense bf16 sustained",
-                "algorithmic_flop_per_launch": 2.0 * f_alg * pairs, "kernel_ms_avg": bwd_avg, "kernel_share_of_step": bwd_avg * args.steps / ms if bwd_ms else None,
+            tj = json.load(f).get(f"{args.config}:{args.precision}", {})
+        traffic = tj.get("bwd_dram_bytes" if dom_is_bwd else "fwd_dram_bytes") if (B, C) == (CONFIGS[args.config]["B"], C_full) and not args.recompute else None
+    step_flop = passes * (f_alg * pairs + flops_per_query_tail(cfg) * B * C)
+    roofline = {"bound": bound, "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": frac,
+                "traffic": traffic, "peak_source": peak_src,
+                "pipe_time_ms_at_100pct": {k: 1e3 * v for k, v in pt.items()},
+                "frac_of_bound_pipe_whole_step": (pt[max(pt, key=pt.get)] / (ms / args.steps * 1e-3)) if dom_tc else None,
+                "algorithmic_flop_per_launch": dom_flop, "kernel_ms_avg": dom_ms,
+                "kernel_share_of_step": dom_ms * args.steps / ms if dom_ms == dom_ms else None,
                 "fwd_kernel_ms_avg": fwd_avg, "fwd_achieved": (f_alg * pairs / (fwd_avg * 1e-3) / 1e12) if fwd_ms else None,
-                "whole_step_achieved": 3.0 * (f_alg * pairs + flops_per_query_tail(cfg) * B * C) / (ms / args.steps * 1e-3) / 1e12,
-                "note": ("tcgen05 kind::f16 MMAs (fp16 operands, fp32 accumulate in TMEM)" if tcmode else "arithmetic on this path is fp32 FMA (precision mode fp32)")
-                        + "; FLOP count is SURVEY 8d's contract figure F_pair_alg per (query, latent) pair, x2 for the backward "
-                          "(dgrad + wgrad; recompute and the 3-term split products of the relu layers are not counted)"}
-    total_flop_step = 3.0 * (f_alg * pairs + flops_per_query_tail(cfg) * B * C)
+                "whole_step_achieved": step_flop / (ms / args.steps * 1e-3) / 1e12,
+                "whole_step_frac": step_flop / (ms / args.steps * 1e-3) / 1e12 / peak,
+                "note": ("tcgen05 kind::f16 MMAs (fp16 operands, fp32 accumulate in TMEM)" if dom_tc else "arithmetic of this kernel is fp32 FMA")
+                        + "; FLOP count is SURVEY 8d's contract figure F_pair_alg per (query, latent) pair"
+                        + (", x2 for the backward (dgrad + wgrad; recompute and the 3-term split products of the relu layers are not counted)" if dom_is_bwd else "")}
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not args.forward_only:
         r = cpu_leg(cfg, 40, 1, budget_s=15.0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    q_total = world * B * C * args.steps
-    line = {"metric": METRIC, "value": q_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate (tcgen05) + f32",
-            "data": "synthetic",
-            "config": {**workload, "precision": args.precision, "global_fields": world * B, "parallelism": f"dp{world} over fields",
-                       "l2": "per-step working set (~2.5 GB workspace at ns64) >> 126 MB L2; no explicit flush",
-                       "step": "fwd + bwd incl. all weight grads" + (" + NCCL all-reduce of weight grads" if world > 1 else ""),
-                       "step_tflop_contract": total_flop_step / 1e12},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+    q_step = (B_global * C_full) if args.scaling == "strong" else world * B * C
+    q_total = q_step * args.steps
+    if fwd_tc and (bwd_tc or args.forward_only):
+        dtype = "f16 operands / f32 accumulate (tcgen05) + f32"
+    elif fwd_tc:
+        dtype = "forward: f16 operands / f32 accumulate (tcgen05); backward: f32 (FMA kernels)"
+    else:
+        dtype = "f32"
+    metric = METRIC if not args.forward_only else "coord-queries/sec (ENF cross-attn forward only)"
+    line = {"metric": metric, "value": q_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {**workload, "precision": args.precision, "global_fields": B_global,
+                       "parallelism": f"dp{world} over {partition}",
+                       "dispatch": {"pair_fwd": "tcgen05" if fwd_tc else "fp32-fma", "pair_bwd": None if args.forward_only else ("tcgen05" if bwd_tc else "fp32-fma")},
+                       "mode": "forward-only" if args.forward_only else ("recompute" if args.recompute else "stash"),
+                       "chunk_fields": chunk_used if args.recompute else None,
+                       "workspace_bytes": workspace_bytes,
+                       "l2": f"per-step working set ({workspace_bytes / 2**30:.2f} GiB workspace) >> 126 MB L2; no explicit flush",
+                       "step": ("fwd (no_grad)" if args.forward_only else "fwd + bwd incl. all weight grads")
+                               + ((" + NCCL all-reduce of weight" + (" and latent" if partition == "queries" else "") + " grads") if world > 1 and not args.forward_only else ""),
+                       "step_tflop_contract": step_flop / 1e12},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk_sum,
             "e2e": {"value": q_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches}

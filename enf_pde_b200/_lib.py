@@ -64,7 +64,6 @@ INVARIANT_KINDS = {
 }
 PREC_FP32, PREC_BF16 = 0, 1
 FLAG_FORWARD_ONLY = 1
-FLAG_TC_BACKWARD_D64 = 2
 FLAG_RECOMPUTE = 4
 FLAG_OUT_BF16 = 8
 ABI_VERSION = 2

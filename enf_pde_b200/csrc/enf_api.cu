@@ -71,7 +71,7 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
-  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_TC_BACKWARD_D64 | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16))
+  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16))
     return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
   if ((D->flags & ENF_FLAG_OUT_BF16) && (!(D->flags & ENF_FLAG_FORWARD_ONLY) || !enf_thin_supported(D->d, D->O)))
     return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_OUT_BF16 needs ENF_FLAG_FORWARD_ONLY and num_out <= 4");
@@ -81,10 +81,10 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   return ENF_OK;
 }
 
-// tensor-core backward: d = 128 always, d = 64 on request (ENF_FLAG_TC_BACKWARD_D64, see include/enf_b200.h)
+// tensor-core backward wherever the tensor-core forward runs (d in {64, 128}, H <= 2): a backward on the fp32 kernels behind a
+// 16-bit-operand forward mixes two different roundings of the same activations (measured: 2e-2 on single weight-gradient leaves)
 bool use_tc_bwd(const EnfDesc& D) {
-  return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H) &&
-         (D.d == 128 || (D.flags & ENF_FLAG_TC_BACKWARD_D64));
+  return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H);
 }
 
 // fields per backward chunk: everything O(B*C*Z) that only lives between the pair kernels of one chunk is sized by this.
@@ -652,6 +652,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     tp.dgr = reinterpret_cast<const uint4*>(c.f("dgr")); tp.trstd = c.f("trstd");
     static const bool trace = getenv("ENF_DEBUG_TRACE") != nullptr;
     tp.dbg = trace ? reinterpret_cast<long long*>(c.f("dbg")) : nullptr;
+    { const char* e = getenv("ENF_DEBUG_NOSPLIT"); tp.debug_nosplit = (e && e[0] == '1') ? 1 : 0; }
     tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");
     tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
     tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");

@@ -214,6 +214,7 @@ struct EnfPairTcBwdParams {
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // shared-weight grads (atomics)
   float* g_U; float* g_kappa; float* g_lam; float* g_sigma;                                // per-latent outputs of B
   long long* dbg;                            // optional clock64() trace of one CTA (diagnostics; null in production)
+  int debug_nosplit;                         // diagnostics (ENF_DEBUG_NOSPLIT): kernels B / C drop the low terms of their relu GEMMs
 };
 bool enf_pairs_bwd_tc_supported(int d, int H);
 // prep (once per backward, whole batch): gradient scale, fp16 cotangent of nbar, Dg;  main: kernels A, B, C on p.B fields

@@ -308,8 +308,10 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           if (it == 0) tc::mbar_wait(bar_w, 0);
           tc::tc_fence_after();
           issue_gemm<D>(tT, aGhi, aW, C::ABLK, C::WBLK);
-          issue_gemm<D>(tT, aGlo, aW, C::ABLK, C::WBLK, 1);
-          issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
+          if (!P.debug_nosplit) {
+            issue_gemm<D>(tT, aGlo, aW, C::ABLK, C::WBLK, 1);
+            issue_gemm<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 1);
+          }
           tc::mma_commit(bar_g1);
         }
         __syncwarp();

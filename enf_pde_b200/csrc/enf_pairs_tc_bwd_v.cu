@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
           if (it == 0) tc::mbar_wait(bar_w, 0);
           tc::tc_fence_after();
           issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, 0, KH, 0);
-          issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 0, KH, 1);
-          issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 0, KH, 1);
+          if (!P.debug_nosplit) {
+            issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, 0, KH, 1);
+            issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, 0, KH, 1);
+          }
         }
         __syncwarp();
       } else {
@@ -272,8 +274,10 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       if (tid == MMA_TID) {
         tc::tc_fence_after();
         issue_gemm_ksteps<D>(tT, aGhi, aW, C::ABLK, C::WBLK, KH, 2 * KH, 1);
-        issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, KH, 2 * KH, 1);
-        issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, KH, 2 * KH, 1);
+        if (!P.debug_nosplit) {
+          issue_gemm_ksteps<D>(tT, aX, aW, C::ABLK, C::WBLK, KH, 2 * KH, 1);
+          issue_gemm_ksteps<D>(tT, aGhi, aWlo, C::ABLK, C::WBLK, KH, 2 * KH, 1);
+        }
         tc::mma_commit(bar_g1);
       }
       // ---- in the shadow of the 3-term GEMM: E3 and the next tile's invariants -----------------------------------------

@@ -153,7 +153,7 @@ class EquivariantCrossAttentionNeF:
                  cross_attn_invariant: BaseInvariant, self_attn_invariant: Optional[BaseInvariant] = None,
                  embedding_type: str = "rff", embedding_freq_multiplier=(0.05, 0.1),
                  condition_value_transform: bool = True, use_gaussian_window: bool = True,
-                 precision: str = "fp32", tc_backward_d64: bool = False, recompute: bool = False, chunk_fields: int = 0,
+                 precision: str = "fp32", recompute: bool = False, chunk_fields: int = 0,
                  workspace_cap_bytes: Optional[int] = None, out_bf16: bool = False):
         if num_layers != 0:
             raise NotImplementedError("latent self-attention blocks (num_layers > 0) are not on the accelerated path; "
@@ -173,9 +173,6 @@ class EquivariantCrossAttentionNeF:
         self.condition_value_transform = condition_value_transform
         self.use_gaussian_window = use_gaussian_window
         self.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
-        # num_hidden = 64 in tensor-core mode: backward on the tcgen05 kernels too (ENF_FLAG_TC_BACKWARD_D64; off by default:
-        # 3e-3 on dp for `ponita`, see include/enf_b200.h)
-        self.tc_backward_d64 = bool(tc_backward_d64)
         # bounded-memory training (ENF_FLAG_RECOMPUTE): no per-(query, latent) stash; the backward re-runs the pair forward
         # per chunk of `chunk_fields` fields (0: library default), or of as many fields as fit `workspace_cap_bytes`
         self.recompute = bool(recompute) or workspace_cap_bytes is not None
@@ -250,7 +247,7 @@ class EquivariantCrossAttentionNeF:
             raise ValueError(f"gaussian_window_size must have shape {(B, Z, 1)}")
         desc = dict(B=B, C=C, Z=Z, d=self.num_hidden, H=self.num_heads, L=self.latent_dim, O=self.num_out, Dx=Dx,
                     invariant_kind=_lib.INVARIANT_KINDS[inv.invariant_type], use_window=int(self.use_gaussian_window),
-                    precision=self.precision, flags=_lib.FLAG_TC_BACKWARD_D64 if self.tc_backward_d64 else 0)
+                    precision=self.precision, flags=0)
         leaves = params_to_leaves(variables)
         # forward only (validation roll-outs, pde_trainer.py:389-405): nothing is kept for a backward
         if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p, a, sigma, *leaves))):

@@ -59,11 +59,7 @@ enum EnfFlags {
    * _base_pde_trainer.py:446-457,588-598).  Nothing is saved for a backward (no logits, no operand
    * stash), the workspace is ~10x smaller, enf_xattn_bwd on such a workspace returns ENF_ERR_STATE. */
   ENF_FLAG_FORWARD_ONLY = 1,
-  /* tensor-core precision mode at num_hidden = 64: also run the BACKWARD on the tcgen05 kernels (default: the forward
-   * only, the backward on the fp32 kernels).  Opt-in because the 16-bit operand noise of the logit cotangents is
-   * amplified by the cancelling sum over queries in d(pose) of the non-periodic window: measured 3e-3 on dp for
-   * `ponita`, outside the 2e-3 bucket (other invariants and all other gradients are inside it). */
-  ENF_FLAG_TC_BACKWARD_D64 = 2,
+  /* (bit 2 was ENF_FLAG_TC_BACKWARD_D64 in ABI 1: the tcgen05 backward is now the default at num_hidden = 64 too) */
   /* bounded-memory training (tensor-core precision mode): the forward keeps NO per-(query, latent) tensor for the
    * backward; enf_xattn_bwd walks the fields in chunks of EnfDesc.chunk_fields and re-runs the fused pair forward on each
    * chunk to rebuild that chunk's operand stash before its backward kernels.  The workspace then scales with

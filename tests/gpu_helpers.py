@@ -59,7 +59,7 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
                            ptr(dp), ptr(da), ptr(dsig), ptr(ws), nbytes, st)
     assert rc == 0, lib.enf_last_error()
     torch.cuda.synchronize()
-    names_bwd = ["g_W3", "g_b3", "g_U", "g_kappa", "g_sigma", "gf_A_q", "gf_c_q", "gf_Wp", "gf_bp", "gf_W2g", "gf_b2g",
+    names_bwd = ["g_W3", "g_b3", "g_U", "g_kappa", "g_lam", "g_sigma", "gf_A_q", "gf_c_q", "gf_Wp", "gf_bp", "gf_W2g", "gf_b2g",
                  "gf_M2g", "gf_c2g", "gf_W_A", "gf_b_A"]
     snap.update({n: ws_view(lib, desc, ws, n).clone() for n in names_bwd})
 
@@ -73,7 +73,7 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
                ahat=m.L["ahat"], k=m.L["k"], v0=m.L["v0"], U=m.L["U"], kappa=m.L["kappa"], Weff=m.L["Weff"], beff=m.L["beff"],
                W3=m.L["W3"], b3=m.L["b3"], nbar=m.S["nbar"], lse=m.S["lse"], e1=m.T["e1"],
                e3c=m.T["e3c"], e3=m.T["e3"], fo=m.T["fo"], o1p=m.T["o1p"], o2p=m.T["o2p"],
-               g_W3=m.GL["W3"], g_b3=m.GL["b3"], g_U=m.GL["U"], g_kappa=m.GL["kappa"], g_sigma=m.GL["sigma"],
+               g_W3=m.GL["W3"], g_b3=m.GL["b3"], g_U=m.GL["U"], g_kappa=m.GL["kappa"], g_lam=m.GL["Lam"], g_sigma=m.GL["sigma"],
                gf_A_q=m.Gf["A_q"], gf_c_q=m.Gf["c_q"], gf_Wp=m.Gf["Wp"], gf_bp=m.Gf["bp"], gf_W2g=m.Gf["W2g"],
                gf_b2g=m.Gf["b2g"], gf_M2g=m.Gf["M2g"], gf_c2g=m.Gf["c2g"], gf_W_A=m.Gf["W_A"], gf_b_A=m.Gf["b_A"])
     errs = {}
@@ -86,5 +86,5 @@ def run_stages(cfg, params, x, p, a, sigma, d_out, shared_x=False, precision=0):
     errs["dsigma"] = rel_err(dsig.cpu(), ds_ref) if cfg.use_gaussian_window else 0.0
     for leaf, e in leaf_errs({n: g.cpu() for n, g in zip(_lib.LEAVES, grads)}, {n: G[n] for n in _lib.LEAVES}).items():
         errs["gw_" + leaf] = e            # per leaf, floored (helpers.leaf_errs)
-    res = dict(out=out, dp=dp, da=da, dsigma=dsig, grads=grads, launches=lib.enf_last_launch_count())
+    res = dict(out=out, dp=dp, da=da, dsigma=dsig, grads=grads, launches=lib.enf_last_launch_count(), ws=ws, desc=desc, model=m)
     return res, errs

@@ -7,7 +7,8 @@ coordinate queries are independent.  A cotangent supported on a few random rows 
   * the latent gradients dp, da, dsigma of the checked fields, and
   * ALL 46 weight gradients (a sum over exactly those rows of all fields)
 equal to the oracle evaluated on the sub-sampled problem, while the CUDA path still walks every tile / item / latent of the
-full-size launch.  Tolerances: the bucket of the kernels that run (2e-3 tensor-core, 1e-4 fp32), per leaf for the weights."""
+full-size launch.  Tolerances: the bucket of the kernels that run -- tensor-core: 2e-3 on the decoded field and the latent
+gradients, weight gradients 2e-3 of the largest entry and 1e-2 per leaf; fp32: 1e-4 on everything (helpers.TOL_*)."""
 import types
 
 import numpy as np
@@ -15,7 +16,7 @@ import pytest
 import torch
 
 from oracle import enf_ref as R
-from helpers import rel_err, make_case, leaf_errs
+from helpers import rel_err, make_case, leaf_errs, Checker, compare, TOL_FP32, TOL_TC, TOL_TC_LEAF
 
 pytestmark = pytest.mark.gpu
 
@@ -34,17 +35,41 @@ REAL = {
 }
 
 
-def _oracle_on_rows(cfg, params, x_rows, p, a, sigma, d_rows, chunk):
-    """fwd_bwd of the oracle on the sub-sampled problem, field chunk by field chunk (memory), weight gradients summed."""
-    B = p.shape[0]
-    outs, dps, das, dss, gsum = [], [], [], [], None
-    for b0 in range(0, B, chunk):
-        sl = slice(b0, min(B, b0 + chunk))
-        o, g, dp, da, ds = R.fwd_bwd(cfg, params, x_rows[sl], p[sl], a[sl], sigma[sl], d_rows[sl])
-        outs.append(o); dps.append(dp); das.append(da); dss.append(ds)
-        flat = R.tree_flatten(g["params"])
-        gsum = flat if gsum is None else {k: gsum[k] + flat[k] for k in flat}
-    return torch.cat(outs), gsum, torch.cat(dps), torch.cat(das), torch.cat(dss)
+class _RowsChecker(Checker):
+    """Checker whose reference is the oracle on the sub-sampled problem, evaluated field chunk by field chunk (memory) with
+    the weight gradients summed over chunks."""
+
+    def __init__(self, cfg, case, chunk):
+        self.chunk = chunk
+        super().__init__(cfg, case, ref=self._chunked(cfg, case, chunk))
+
+    @staticmethod
+    def _chunked(cfg, case, chunk):
+        params, x_rows, p, a, sigma, d_rows = case
+        B = p.shape[0]
+        outs, dps, das, dss, gsum = [], [], [], [], None
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, min(B, b0 + chunk))
+            o, g, dp, da, ds = R.fwd_bwd(cfg, params, x_rows[sl], p[sl], a[sl], sigma[sl], d_rows[sl])
+            outs.append(o); dps.append(dp); das.append(da); dss.append(ds)
+            flat = R.tree_flatten(g["params"])
+            gsum = flat if gsum is None else {k: gsum[k] + flat[k] for k in flat}
+        return torch.cat(outs), {"params": R.tree_unflatten(gsum)}, torch.cat(dps), torch.cat(das), torch.cat(dss)
+
+    def allow(self):
+        if self._allow is None:
+            tot = None
+            for shift in (4e-6, -4e-6):
+                R.RELU_KINK_SHIFT[0] = shift
+                try:
+                    g = self._chunked(self.cfg, self.case, self.chunk)
+                finally:
+                    R.RELU_KINK_SHIFT[0] = 0.0
+                fb, fg = R.tree_flatten(self.ref[1]["params"]), R.tree_flatten(g[1]["params"])
+                cur = ({k: (fg[k] - fb[k]).abs() for k in fb}, (g[2] - self.ref[2]).abs(), (g[3] - self.ref[3]).abs(), (g[4] - self.ref[4]).abs())
+                tot = cur if tot is None else ({k: tot[0][k] + cur[0][k] for k in cur[0]}, tot[1] + cur[1], tot[2] + cur[2], tot[3] + cur[3])
+            self._allow = tot
+        return self._allow
 
 
 @pytest.mark.parametrize("name", list(REAL))
@@ -75,16 +100,15 @@ def test_baseline_config_at_real_shape(name):
                         invariant_kind=_lib.INVARIANT_KINDS[cfg.invariant_type], use_window=int(cfg.use_gaussian_window),
                         precision=_lib.PREC_BF16, flags=0)
     fwd_tc, bwd_tc = _lib.dispatch(desc)
-    tol = 2e-3 if fwd_tc else 1e-4
+    tol, tol_leaf = (TOL_TC, TOL_TC_LEAF) if fwd_tc else (TOL_FP32, TOL_FP32)
+    assert fwd_tc == bwd_tc                                              # never a 16-bit forward behind an fp32 backward
 
     x_rows = coords[rows][None].expand(B, -1, -1)
-    out_ref, g_ref, dp_ref, da_ref, ds_ref = _oracle_on_rows(cfg, params, x_rows, p, a, sigma, d_out[:, rows], chunk)
-    errs = dict(out=rel_err(out.detach()[:, rows.cuda()], out_ref), dp=rel_err(pg.grad, dp_ref), da=rel_err(ag.grad, da_ref))
-    if cfg.use_gaussian_window:
-        errs["ds"] = rel_err(sg.grad, ds_ref)
-    le = leaf_errs({k: v.grad for k, v in R.tree_flatten(P["params"]).items()}, g_ref)
-    worst = max(le, key=le.get)
-    errs["dtheta"] = le[worst]
+    chk = _RowsChecker(cfg, (params, x_rows, p, a, sigma, d_out[:, rows]), chunk)
+    gf = {k: v.grad for k, v in R.tree_flatten(P["params"]).items()}
+    errs, worst, ok = compare(chk, out.detach(), pg.grad, ag.grad, sg.grad if sg is not None else None, gf, tol, tol_leaf,
+                              use_window=cfg.use_gaussian_window, rows=rows.cuda())
+    errs["dtheta_global"] = max(leaf_errs(gf, R.tree_flatten(chk.ref[1]["params"]), floor=1.0).values())
     print(name, f"tcgen05 fwd/bwd = {fwd_tc}/{bwd_tc}", {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst,
-          "launches:", E.last_launch_counts())
-    assert all(v < tol for v in errs.values()), (errs, worst)
+          "kink allowance used:", chk.used_allowance, "launches:", E.last_launch_counts())
+    assert ok and errs["dtheta_global"] < tol, (errs, worst)
