@@ -130,15 +130,32 @@ class Checker:
     """Compares a CUDA result with the oracle, quantity by quantity; when a gradient is over its tolerance the relu-kink
     allowance is computed (once, lazily: two more oracle passes) and the comparison repeated with it."""
 
-    def __init__(self, cfg, case, ref=None):
+    def __init__(self, cfg, case, ref=None, fp32_floor=False):
         self.cfg, self.case = cfg, case
         self.ref = ref if ref is not None else R.fwd_bwd(cfg, *case)       # (out, dtheta tree, dp, da, dsigma)
         self._allow = None
         self.used_allowance = []
+        # fp32_floor: also allow twice the distance between the oracle evaluated in float32 (the reference's dtype) and in
+        # float64.  Only for inputs that are ill-conditioned in float32 by construction: `ball_lat` feeds the RAW polar angle of
+        # the latent (up to 1e2 rad with the reference's ball initialiser) into 2 pi u Omega, so the phase itself carries
+        # ~1e-5 rad of float32 rounding whatever the implementation.
+        self.fp32_floor = fp32_floor
+
+    def _floor(self):
+        f = lambda t: t.float()
+        params, x, p, a, sigma, d_out = self.case
+        g = R.fwd_bwd(self.cfg, R.tree_map(f, params), f(x), f(p), f(a), f(sigma), f(d_out))
+        fb, fg = R.tree_flatten(self.ref[1]["params"]), R.tree_flatten(g[1]["params"])
+        return ({k: 2 * (fg[k].double() - fb[k]).abs() for k in fb}, 2 * (g[2].double() - self.ref[2]).abs(),
+                2 * (g[3].double() - self.ref[3]).abs(), 2 * (g[4].double() - self.ref[4]).abs())
 
     def allow(self):
         if self._allow is None:
-            self._allow = kink_allowance(self.cfg, *self.case)
+            al = kink_allowance(self.cfg, *self.case)
+            if self.fp32_floor:
+                fl = self._floor()
+                al = ({k: al[0][k] + fl[0][k] for k in al[0]}, al[1] + fl[1], al[2] + fl[2], al[3] + fl[3])
+            self._allow = al
         return self._allow
 
     def grad(self, name, got, tol):
