@@ -66,6 +66,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 FLAG_FORWARD_ONLY = 1
 FLAG_RECOMPUTE = 4
 FLAG_OUT_BF16 = 8
+FLAG_FROZEN_RELU = 16
 ABI_VERSION = 2
 
 EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_chunk_for_cap",

@@ -71,10 +71,12 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
-  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16))
+  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16 | ENF_FLAG_FROZEN_RELU))
     return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
   if ((D->flags & ENF_FLAG_OUT_BF16) && (!(D->flags & ENF_FLAG_FORWARD_ONLY) || !enf_thin_supported(D->d, D->O)))
     return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_OUT_BF16 needs ENF_FLAG_FORWARD_ONLY and num_out <= 4");
+  if ((D->flags & ENF_FLAG_FROZEN_RELU) && D->precision != ENF_PREC_FP32)
+    return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_FROZEN_RELU is implemented by the fp32 kernels only");
   if (D->chunk_fields < 0 || D->reserved[0] || D->reserved[1] || D->reserved[2])
     return fail(ENF_ERR_BAD_DESC, "chunk_fields must be >= 0 and the reserved fields 0");
   if (rl) *rl = r;
@@ -103,7 +105,9 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   Y.add("A_q", d * Hd); Y.add("c_q", Hd); Y.add("Wp", d2); Y.add("bp", d); Y.add("W2g", d * 2 * Hd); Y.add("b2g", 2 * Hd);
   Y.add("M2g", d2); Y.add("c2g", d); Y.add("P1", Hd * Hd); Y.add("b1", Hd); Y.add("W_A", Hd * Hd); Y.add("b_A", Hd);
   Y.add("dP1", Hd * Hd); Y.add("db1", Hd); Y.add("q_w1T", d2); Y.add("v_w1T", d2); Y.add("WpT", d2);
-  Y.add("lam", BZ * ENF_LAM_SIZE); Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
+  Y.add("lam", BZ * ENF_LAM_SIZE);
+  if (D.flags & ENF_FLAG_FROZEN_RELU) Y.add("lam_mask", BZ * ENF_LAM_SIZE);
+  Y.add("a0", BZ * d); Y.add("acore", BZ * d); Y.add("arstd", BZ); Y.add("ahat", BZ * d);
   Y.add("k", BZ * Hd); Y.add("v0", BZ * Hd); Y.add("U", BZ * Hd); Y.add("kappa", BZ * H);
   Y.add("Weff", BZ * H * d2); Y.add("beff", BZ * Hd); Y.add("W3", BZ * H * d2); Y.add("b3", BZ * Hd);
   {
@@ -247,6 +251,7 @@ EnfPairParams pair_params(const EnfDesc& D, const EnfRecordLayout& rl, const Enf
   p.B = D.B; p.C = D.C; p.Z = D.Z; p.H = D.H; p.I = rl.I;
   p.row_kind = rl.row_kind; p.win_kind = rl.win_kind; p.win_row = rl.win_row; p.nsq = rl.nsq;
   p.xi = c.f("xi"); p.xi_bs = xi_bs; p.lam = c.f("lam"); p.sigma = sigma;
+  p.lam_mask = (D.flags & ENF_FLAG_FROZEN_RELU) ? c.f("lam_mask") : nullptr;
   p.q_omega = w.q_omega; p.v_omega = w.v_omega;
   p.q_w1 = w.q_w1; p.q_b1 = w.q_b1; p.v_w1 = w.v_w1; p.v_b1 = w.v_b1;
   p.Wp = c.f("Wp"); p.bp = c.f("bp");
@@ -463,6 +468,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
 
   // ---- L: per-latent folds ----------------------------------------------------------------------
   c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
+  if (D.flags & ENF_FLAG_FROZEN_RELU)      // second pose set: the relu pattern's expansion point
+    c.launches += enf_launch_latent_record(st, D, p + BZ * rl.P, c.f("lam_mask"));
   c.gemm((int)BZ, d, L, enf_mat(a, L), enf_mat(w->stem_w, d), enf_mat(c.f("a0"), d), opt_bias(w->stem_b));
   c.launches += enf_launch_ln_fwd(st, c.f("a0"), BZ, d, w->ln_attn_g, w->ln_attn_b, c.f("acore"), c.f("ahat"), c.f("arstd"), 0);
   c.begin_group();

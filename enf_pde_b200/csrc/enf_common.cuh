@@ -146,6 +146,7 @@ struct EnfPairParams {
   int row_kind, win_kind, win_row, nsq;
   const float* xi;  int64_t xi_bs;           // [Bx, C, 8]
   const float* lam;                          // [B, Z, 7, 8]
+  const float* lam_mask;                     // frozen-relu mode (ENF_FLAG_FROZEN_RELU): record of the mask poses, else null
   const float* sigma;                        // [B, Z] or null
   const float* q_omega; const float* v_omega;  // [I, d/2]
   const float* q_w1; const float* q_b1;      // [d, d], [d]

@@ -145,6 +145,8 @@ struct Smem {
   float* Uz;      // [MAXH][D]
   float* omq;     // [6][D/2]
   float* omv;     // [6][D/2]
+  float* lam2;    // [56]     frozen-relu mode: record of the mask poses
+  float* u2;      // [TM][8]  frozen-relu mode: invariants against the mask poses
 };
 
 template <int D>
@@ -167,10 +169,12 @@ __device__ __forceinline__ float* carve_small(float* base, Smem& S) {
   S.Uz = p; p += MAXH * D;
   S.omq = p; p += 6 * (D / 2);
   S.omv = p; p += 6 * (D / 2);
+  S.lam2 = p; p += 64;
+  S.u2 = p; p += TM * 8;
   return p;
 }
 template <int D> constexpr int small_floats() {
-  return TM * 8 * 4 + TM * 3 + MAXH * TM * 5 + 64 + 8 + MAXH * D + 12 * (D / 2);
+  return TM * 8 * 4 + TM * 3 + MAXH * TM * 5 + 64 + 8 + MAXH * D + 12 * (D / 2) + 64 + TM * 8;
 }
 
 // invariants u[I] and window w of row t against the staged latent record
@@ -217,14 +221,31 @@ __device__ __forceinline__ void pair_invariants(const EnfPairParams& P, const Sm
   S.w[t] = w;
 }
 
+// invariants only, of row t against record `lam` -> u[t][0..I)   (frozen-relu mode: the mask poses' invariants)
+__device__ __forceinline__ void pair_invariants_only(const EnfPairParams& P, const float* xi_all, const float* lam, float* u, int t) {
+  const float* xi = xi_all + t * 8;
+  for (int r = 0; r < P.I; ++r) {
+    const float* L = lam + r * ENF_F_XI;
+    float v = 0.f;
+    if (P.row_kind == ENF_ROW_DOT) {
+#pragma unroll
+      for (int f = 0; f < ENF_F_XI; ++f) v = fmaf(L[f], xi[f], v);
+    } else {
+      for (int i = 0; i < P.nsq; ++i) { float dlt = L[i] - xi[i]; v = fmaf(dlt, dlt, v); }
+      if (P.row_kind == ENF_ROW_SQDIST_SQRT) v = sqrtf(v);
+    }
+    u[t * 8 + r] = v;
+  }
+}
+
 // gamma(u) = [sin(2 pi u Omega) | cos(2 pi u Omega)]  (rff.py:84-93) into G[TM][D]
 template <int D>
-__device__ __forceinline__ void rff_features(const Smem& S, const float* om, int I, float* G) {
+__device__ __forceinline__ void rff_features(const float* u, const float* om, int I, float* G) {
   constexpr int HD = D / 2;
   for (int e = threadIdx.x; e < TM * HD; e += NT) {
     int row = e / HD, j = e % HD;
     float proj = 0.f;
-    for (int i = 0; i < I; ++i) proj = fmaf(S.u[row * 8 + i], om[i * HD + j], proj);
+    for (int i = 0; i < I; ++i) proj = fmaf(u[row * 8 + i], om[i * HD + j], proj);
     float sn, cs;
     sincospif(2.f * proj, &sn, &cs);
     G[row * Cfg<D>::LD + j] = sn;
@@ -256,20 +277,36 @@ __device__ __forceinline__ void stage_latent(const EnfPairParams& P, const Smem&
 
 // steps shared by forward and backward: invariants, q-path logits, v-path up to that = LN(gelu(tpre)).
 // Buffers: Gq,H1q,Gv,H1v,Tpre,That (forward passes aliases: Gq=Gv=Tpre=That=bufA, H1q=H1v=bufB).
+// Frozen-relu mode (P.lam_mask != null; the Hessian-vector products of the second-order outer gradient): the two relu layers
+// use the activation PATTERN of the mask poses -- h = [pre(mask pose) > 0] * pre(evaluation pose) -- so that a finite difference
+// of gradients along a latent direction differentiates the same piecewise-linear branch everywhere (what reverse-over-reverse
+// autodiff does: relu'' = 0).  MQ / MV receive the mask poses' pre-activations ([TM][LD] each; tmpG is one more scratch tile);
+// without the mode MQ = H1q and MV = H1v (callers test `> 0` on MQ / MV either way).
 template <int D, bool KEEP>
 __device__ __forceinline__ void pair_chain_common(const EnfPairParams& P, const Smem& S, int64_t bz,
                                                   float* Gq, float* H1q, float* Gv, float* H1v, float* Tpre,
-                                                  float* That, float* Ws) {
+                                                  float* That, float* Ws, float* MQ, float* MV, float* tmpG) {
   using C = Cfg<D>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float scale = rsqrtf((float)D);
+  const bool frozen = P.lam_mask != nullptr;
   stage_latent<D>(P, S, bz);
+  if (frozen && tid < ENF_LAM_SIZE) S.lam2[tid] = P.lam_mask[bz * ENF_LAM_SIZE + tid];
   __syncthreads();
-  if (tid < TM) pair_invariants(P, S, tid, P.sigma ? P.sigma[bz] : 1.f);
+  if (tid < TM) {
+    pair_invariants(P, S, tid, P.sigma ? P.sigma[bz] : 1.f);
+    if (frozen) pair_invariants_only(P, S.xi, S.lam2, S.u2, tid);
+  }
   __syncthreads();
-  rff_features<D>(S, S.omq, P.I, Gq);
+  if (frozen) {
+    rff_features<D>(S.u2, S.omq, P.I, tmpG);
+    __syncthreads();
+    tile_gemm<D, 0, false>(tmpG, P.q_w1, MQ, P.q_b1, nullptr, Ws);            // pre-activations at the mask poses
+  }
+  rff_features<D>(S.u, S.omq, P.I, Gq);
   __syncthreads();
-  tile_gemm<D, 1, false>(Gq, P.q_w1, H1q, P.q_b1, nullptr, Ws);
+  if (frozen) tile_gemm<D, 2, false>(Gq, P.q_w1, H1q, P.q_b1, MQ, Ws);
+  else tile_gemm<D, 1, false>(Gq, P.q_w1, H1q, P.q_b1, nullptr, Ws);
   for (int r = warp; r < TM; r += NT / 32) {
     for (int h = 0; h < P.H; ++h) {
       float acc = 0.f;
@@ -279,9 +316,15 @@ __device__ __forceinline__ void pair_chain_common(const EnfPairParams& P, const 
     }
   }
   if (!KEEP) __syncthreads();     // forward aliases Gq/Gv: everyone must be done reading H1q before it is reused
-  rff_features<D>(S, S.omv, P.I, Gv);
+  if (frozen) {
+    rff_features<D>(S.u2, S.omv, P.I, tmpG);
+    __syncthreads();
+    tile_gemm<D, 0, false>(tmpG, P.v_w1, MV, P.v_b1, nullptr, Ws);
+  }
+  rff_features<D>(S.u, S.omv, P.I, Gv);
   __syncthreads();
-  tile_gemm<D, 1, false>(Gv, P.v_w1, H1v, P.v_b1, nullptr, Ws);
+  if (frozen) tile_gemm<D, 2, false>(Gv, P.v_w1, H1v, P.v_b1, MV, Ws);
+  else tile_gemm<D, 1, false>(Gv, P.v_w1, H1v, P.v_b1, nullptr, Ws);
   tile_gemm<D, 0, false>(H1v, P.Wp, Tpre, P.bp, nullptr, Ws);
   for (int r = warp; r < TM; r += NT / 32) {
     float rstd = ln_gelu_row<D>(Tpre + r * C::LD, That + r * C::LD, lane);
@@ -303,7 +346,8 @@ __global__ void __launch_bounds__(NT, 1) pairs_fwd_kernel(EnfPairParams P) {
   float* bufA = p; p += C::BUF;
   float* bufB = p; p += C::BUF;
   float* Ws = p; p += C::KC * D;
-  float* acc = p;                      // [H][TM][LD]
+  float* acc = p; p += P.H * C::BUF;   // [H][TM][LD]
+  float* bufMask = p;                  // frozen-relu mode only: [2][TM][LD] (mask pre-activations, scratch features)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, c0 = blockIdx.x * TM;
@@ -321,7 +365,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_fwd_kernel(EnfPairParams P) {
 
   for (int z = 0; z < P.Z; ++z) {
     const int64_t bz = (int64_t)b * P.Z + z;
-    pair_chain_common<D, false>(P, S, bz, bufA, bufB, bufA, bufB, bufA, bufA, Ws);
+    pair_chain_common<D, false>(P, S, bz, bufA, bufB, bufA, bufB, bufA, bufA, Ws, bufMask, bufMask, bufMask + C::BUF);
     // bufA now holds that = LN(gelu(tpre))
     for (int h = 0; h < H; ++h) {
       const int64_t bzh = bz * H + h;
@@ -372,7 +416,10 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
   float* bufM = p; p += C::BUF;
   float* bufN = p; p += C::BUF;
   float* DT = p; p += C::BUF;
-  float* Ws = p;
+  float* Ws = p; p += C::KC * D;
+  // frozen-relu mode: the mask poses' pre-activations of the two relu layers (otherwise the layers' own outputs serve as masks)
+  float* MQ = P.lam_mask ? p : H1q;
+  float* MV = P.lam_mask ? p + C::BUF : H1v;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, c0 = blockIdx.x * TM;
@@ -405,7 +452,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
 
   for (int z = 0; z < P.Z; ++z) {
     const int64_t bz = (int64_t)b * P.Z + z;
-    pair_chain_common<D, true>(P, S, bz, Gq, H1q, Gv, H1v, Tpre, That, Ws);
+    pair_chain_common<D, true>(P, S, bz, Gq, H1q, Gv, H1v, Tpre, That, Ws, MQ, MV, bufM);
 
     // ---- heads: recompute n, softmax weights, ds, dmpre; wgrad dW3/db3; dgrad into DT ------------
     for (int h = 0; h < H; ++h) {
@@ -455,7 +502,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
     }
     __syncthreads();
     tile_wgrad<D>(H1v, DT, P.g_Wp, P.g_bp);
-    tile_gemm<D, 2, false>(DT, P.WpT, bufM, nullptr, H1v, Ws);                  // dzv = (dtpre Wp^T) * [h1v > 0]
+    tile_gemm<D, 2, false>(DT, P.WpT, bufM, nullptr, MV, Ws);                   // dzv = (dtpre Wp^T) * [h1v > 0]
     tile_wgrad<D>(Gv, bufM, P.g_v_w1, P.g_v_b1);
     tile_gemm<D, 0, false>(bufM, P.v_w1T, bufN, nullptr, nullptr, Ws);          // d gamma_v
     // du from the value embedding
@@ -475,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
       int r = e / D, i = e % D;
       float v = 0.f;
       for (int h = 0; h < H; ++h) v = fmaf(S.aux[h * TM + r], S.Uz[h * D + i], v);
-      bufM[r * C::LD + i] = H1q[r * C::LD + i] > 0.f ? scale * v : 0.f;
+      bufM[r * C::LD + i] = MQ[r * C::LD + i] > 0.f ? scale * v : 0.f;
     }
     for (int e = tid; e < H * D; e += NT) {
       int h = e / D, i = e % D;
@@ -562,16 +609,16 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
   }
 }
 
-template <int D> size_t fwd_smem(int H) {
-  return (size_t)(small_floats<D>() + 4 + 2 * Cfg<D>::BUF + Cfg<D>::KC * D + H * Cfg<D>::BUF) * sizeof(float);
+template <int D> size_t fwd_smem(int H, bool frozen) {
+  return (size_t)(small_floats<D>() + 4 + (2 + (frozen ? 2 : 0)) * Cfg<D>::BUF + Cfg<D>::KC * D + H * Cfg<D>::BUF) * sizeof(float);
 }
-template <int D> size_t bwd_smem() {
-  return (size_t)(small_floats<D>() + 4 + 9 * Cfg<D>::BUF + Cfg<D>::KC * D) * sizeof(float);
+template <int D> size_t bwd_smem(bool frozen) {
+  return (size_t)(small_floats<D>() + 4 + (9 + (frozen ? 2 : 0)) * Cfg<D>::BUF + Cfg<D>::KC * D) * sizeof(float);
 }
 
 template <int D>
 int launch_fwd(cudaStream_t st, const EnfPairParams& p) {
-  size_t smem = fwd_smem<D>(p.H);
+  size_t smem = fwd_smem<D>(p.H, p.lam_mask != nullptr);
   if (cudaFuncSetAttribute(pairs_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   dim3 grid((p.C + TM - 1) / TM, p.B);
   pairs_fwd_kernel<D><<<grid, NT, smem, st>>>(p);
@@ -579,7 +626,7 @@ int launch_fwd(cudaStream_t st, const EnfPairParams& p) {
 }
 template <int D>
 int launch_bwd(cudaStream_t st, const EnfPairParams& p) {
-  size_t smem = bwd_smem<D>();
+  size_t smem = bwd_smem<D>(p.lam_mask != nullptr);
   if (cudaFuncSetAttribute(pairs_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   dim3 grid((p.C + TM - 1) / TM, p.B);
   pairs_bwd_kernel<D><<<grid, NT, smem, st>>>(p);

@@ -82,6 +82,12 @@ class _XAttnFunction(torch.autograd.Function):
         lib = _lib.load()
         desc_kw, x_shared = meta
         desc = _lib.EnfDesc(**desc_kw)
+        ctx.n_extra = 0
+        if desc.flags & _lib.FLAG_FROZEN_RELU:          # trailing argument: the mask poses; the C ABI takes p[2][B,Z,P]
+            *leaves, p_mask = leaves
+            ctx.n_extra = 1
+            ctx.p_shape = tuple(p.shape)
+            p = torch.stack([_as_f32(p, "p"), _as_f32(p_mask, "relu_mask_pose")]).contiguous()
         x = _as_f32(x, "x"); p = _as_f32(p, "p"); a = _as_f32(a, "a")
         sigma = None if sigma is None else _as_f32(sigma, "gaussian_window_size")
         leaves = [_as_f32(t, n) for t, n in zip(leaves, _lib.LEAVES)]
@@ -122,9 +128,10 @@ class _XAttnFunction(torch.autograd.Function):
         leaves = saved[4:] if ctx.has_sigma else saved[3:]
         desc = _lib.EnfDesc(**ctx.desc_kw)
         d_out = _as_f32(d_out, "d_out")
-        need_w = any(ctx.needs_input_grad[5:])
+        need_w = any(ctx.needs_input_grad[5:5 + len(leaves)])
         grads = [torch.empty_like(t) for t in leaves] if need_w else None
-        dp = torch.empty_like(p); da = torch.empty_like(a)
+        dp = torch.empty(ctx.p_shape, dtype=p.dtype, device=p.device) if ctx.n_extra else torch.empty_like(p)
+        da = torch.empty_like(a)
         dsigma = torch.empty_like(sigma) if sigma is not None else None
         w = _weights_struct(leaves)
         gw = _weights_struct(grads) if need_w else None
@@ -135,7 +142,7 @@ class _XAttnFunction(torch.autograd.Function):
                                    _ptr(ctx.ws), ctx.nbytes, stream)
         _lib.check(rc, "enf_xattn_bwd")
         _XAttnFunction.last_launches[1] = lib.enf_last_launch_count()
-        return (None, None, dp, da, dsigma, *(grads if need_w else [None] * len(leaves)))
+        return (None, None, dp, da, dsigma, *(grads if need_w else [None] * len(leaves)), *([None] * ctx.n_extra))
 
 
 _XAttnFunction.last_launches = [0, 0]
@@ -227,7 +234,9 @@ class EquivariantCrossAttentionNeF:
         return {"params": _unflatten(flat)}
 
     # -- nef.apply(params, x, p, a, window) (pde_trainer.py:184,478,537) -----------------------------------
-    def apply(self, variables, x, p, a, gaussian_window_size=None):
+    def apply(self, variables, x, p, a, gaussian_window_size=None, relu_mask_pose=None):
+        """`relu_mask_pose` (B,Z,P), fp32 precision only: evaluate with the relu activation pattern of THOSE poses
+        (ENF_FLAG_FROZEN_RELU; used by enf_pde_b200.meta for Hessian-vector products)."""
         inv = self.cross_attn_invariant
         if self.use_gaussian_window and gaussian_window_size is None:
             raise TypeError("gaussian_window_size is None but use_gaussian_window=True "
@@ -249,6 +258,11 @@ class EquivariantCrossAttentionNeF:
                     invariant_kind=_lib.INVARIANT_KINDS[inv.invariant_type], use_window=int(self.use_gaussian_window),
                     precision=self.precision, flags=0)
         leaves = params_to_leaves(variables)
+        if relu_mask_pose is not None:
+            if tuple(relu_mask_pose.shape) != tuple(p.shape):
+                raise ValueError("relu_mask_pose must have the shape of p")
+            desc["flags"] |= _lib.FLAG_FROZEN_RELU
+            return _XAttnFunction.apply((desc, x_shared), x_arg, p, a, sigma, *leaves, relu_mask_pose.detach())
         # forward only (validation roll-outs, pde_trainer.py:389-405): nothing is kept for a backward
         if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p, a, sigma, *leaves))):
             desc["flags"] |= _lib.FLAG_FORWARD_ONLY

@@ -69,7 +69,15 @@ enum EnfFlags {
   ENF_FLAG_RECOMPUTE = 4,
   /* forward only, num_out <= 4: `out` is written as bfloat16 [B,C,O] instead of float32 (validation / visualisation
    * roll-outs decode B*T fields over the full grid, _base_pde_trainer.py:446-457). */
-  ENF_FLAG_OUT_BF16 = 8
+  ENF_FLAG_OUT_BF16 = 8,
+  /* fp32 precision only.  `p` holds TWO pose sets back to back, p[2][B,Z,P]: p[0] = the poses the path is evaluated at, p[1] =
+   * the poses whose relu ACTIVATION PATTERN the two RFF layers (rff.py:61) use: h = [pre(p[1]) > 0] * pre(p[0]).  With
+   * p[1] = p[0] this is the plain path.  It exists for the second-order outer gradient of the meta-learning step
+   * (jax.value_and_grad at pde_trainer.py:255 through jax.grad at :188): a Hessian-vector product is taken as a finite
+   * difference of enf_xattn_bwd gradients along a latent direction, and freezing the pattern at the expansion point makes that
+   * difference differentiate one linear branch of the relus -- exactly what reverse-over-reverse autodiff computes (relu'' = 0;
+   * a plain finite difference would add the curvature concentrated at the kinks).  dp[B,Z,P] is the gradient w.r.t. p[0]. */
+  ENF_FLAG_FROZEN_RELU = 16
 };
 
 enum EnfError {

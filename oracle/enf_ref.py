@@ -506,6 +506,47 @@ def inner_loop(cfg: EnfConfig, params, coords, img, p, a, sigma, lrs, num_inner_
     return ((out - img[:, m]) ** 2).mean(), (p, a, sigma)
 
 
+def outer_loss_and_grads(cfg: EnfConfig, params, coords, img, p0, a0, sigma0, lrs, num_inner_steps, masks,
+                         optimize_gaussian_window=False, n_pos=None):
+    """The meta-learning OUTER objective and its gradient, second order included: `jax.value_and_grad(self.enf_loss)`
+    (pde_trainer.py:255) through `inner_loop` (:122-235), whose steps take `jax.grad(loss_fn)` (:188-204) and are NOT
+    stop-gradiented.  p0 (1,Z,P), a0 (1,Z,L), sigma0 (1,Z,1): the shared autodecoder latents, repeated over the B fields
+    (:157-159); lrs: dict of tensors p_pos (1,), p_ori (1,), a (L,), gaussian_window (1,).
+    Returns (loss, {"nef": param-tree grads, "p": , "a": , "gaussian_window": , "lrs": {key: grad}}) -- torch double backward
+    (create_graph=True): relu'' = 0, as in JAX."""
+    B = img.shape[0]
+    params = tree_map(lambda t: t.detach().clone().requires_grad_(True), params)
+    p0 = p0.detach().clone().requires_grad_(True)
+    a0 = a0.detach().clone().requires_grad_(True)
+    s0 = sigma0.detach().clone().requires_grad_(True)
+    lr = {k: torch.as_tensor(v, dtype=p0.dtype).detach().clone().requires_grad_(True) for k, v in lrs.items()}
+    n_pos = p0.shape[-1] if n_pos is None else n_pos
+    p, a, sigma = p0.repeat(B, 1, 1), a0.repeat(B, 1, 1), s0.repeat(B, 1, 1)
+    for step in range(num_inner_steps):
+        m = masks[step]
+        out = nef_apply(cfg, params, coords[m][None].expand(B, -1, -1), p, a, sigma)
+        loss = ((out - img[:, m]) ** 2).mean()
+        gp, ga, gs = torch.autograd.grad(loss, (p, a, sigma), create_graph=True, allow_unused=True)
+        lr_p = torch.cat([lr["p_pos"].expand(n_pos)] + ([lr["p_ori"].expand(p.shape[-1] - n_pos)] if p.shape[-1] > n_pos else []))
+        p = p - lr_p * gp * B
+        a = a - lr["a"].reshape(1, 1, -1) * ga * B
+        if optimize_gaussian_window and gs is not None:
+            sigma = sigma - lr["gaussian_window"] * gs * B
+    m = masks[num_inner_steps]
+    out = nef_apply(cfg, params, coords[m][None].expand(B, -1, -1), p, a, sigma)
+    loss = ((out - img[:, m]) ** 2).mean()
+    leaves = list(tree_flatten(params).items())
+    lr_keys = list(lr)
+    inputs = [t for _, t in leaves] + [p0, a0, s0] + [lr[k] for k in lr_keys]
+    grads = torch.autograd.grad(loss, inputs, allow_unused=True)
+    z = lambda g, t: g if g is not None else torch.zeros_like(t)
+    n = len(leaves)
+    gflat = {name: z(g, t) for (name, t), g in zip(leaves, grads[:n])}
+    return loss.detach(), {"nef": tree_unflatten(gflat), "p": z(grads[n], p0), "a": z(grads[n + 1], a0),
+                           "gaussian_window": z(grads[n + 2], s0),
+                           "lrs": {k: z(g, lr[k]) for k, g in zip(lr_keys, grads[n + 3:])}}
+
+
 def fwd_bwd(cfg: EnfConfig, params, x, p, a, sigma, d_out):
     """Forward + reverse pass with cotangent d_out.  Returns out and grads wrt (params, p, a, sigma)."""
     params = tree_map(lambda t: t.detach().clone().requires_grad_(True), params)

@@ -138,3 +138,56 @@ def test_bf16_output_option_forward_only(precision):
         o16 = _nef(cfg, precision, out_bf16=True).apply(P, f32(x), f32(p), f32(a), f32(sigma))
     assert o16.dtype == torch.bfloat16 and o32.dtype == torch.float32
     assert torch.equal(o16, o32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("optimize_window", [False, True])
+def test_second_order_outer_gradient_against_oracle(optimize_window):
+    """enf_pde_b200.outer_step_gradients vs the oracle's double backward through the restated inner loop
+    (jax.value_and_grad at pde_trainer.py:255 through jax.grad at :188-204), K = 3 Meta-SGD steps: gradients w.r.t. the 46 NeF
+    leaves, the shared autodecoder latents (p, a, gaussian_window) and the Meta-SGD learning rates.
+    The Hessian-vector products are 4th-order central differences of the fp32 backward with the relu pattern frozen
+    (ENF_FLAG_FROZEN_RELU); tolerance 2e-3 on every quantity (per leaf for the weights), and the test also shows that the
+    first-order (FOMAML) estimate misses by far more than that, i.e. that the second-order terms are being checked."""
+    import enf_pde_b200 as E
+    from helpers import leaf_errs
+    cfg = R.EnfConfig(num_in=2, num_hidden=64, num_heads=2, num_out=1, latent_dim=16, invariant_type="ponita",
+                      embedding_freq_multiplier=(0.05, 0.05))
+    B, C, Z, K = 3, 256, 9, 3
+    params, _, p, a, sigma, _ = make_case(cfg, 1, 8, Z, seed=13)
+    coords = R.make_coords(cfg, (16, 16)).float().double()
+    g = torch.Generator().manual_seed(17)
+    img = torch.randn(B, C, cfg.num_out, generator=g, dtype=torch.float64).float().double()
+    masks = [torch.randperm(C, generator=g)[:180] for _ in range(K + 1)]
+    lrs = {"p_pos": torch.tensor([0.3]), "p_ori": torch.tensor([0.2]), "a": torch.full((cfg.latent_dim,), 1.5),
+           "gaussian_window": torch.tensor([0.05])}
+    loss_ref, g_ref = R.outer_loss_and_grads(cfg, params, coords, img, p, a, sigma, {k: v.double() for k, v in lrs.items()}, K, masks,
+                                             optimize_gaussian_window=optimize_window, n_pos=2)
+    nef = _nef(cfg, "fp32")
+    P = _cuda(params)
+    loss, grads, _ = E.outer_step_gradients(nef, P, f32(coords), f32(img), f32(p), f32(a), f32(sigma),
+                                            {k: v.cuda() for k, v in lrs.items()}, K, [m.cuda() for m in masks],
+                                            optimize_gaussian_window=optimize_window)
+    from enf_pde_b200 import _lib
+    want = R.tree_flatten(g_ref["nef"])
+    got = {_lib.LEAF_PATHS[n]: t for n, t in zip(_lib.LEAVES, grads["nef"])}
+    le = leaf_errs(got, want)
+    errs = dict(loss=abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)), p=rel_err(grads["p"], g_ref["p"]),
+                a=rel_err(grads["a"], g_ref["a"]), window=rel_err(grads["gaussian_window"], g_ref["gaussian_window"]),
+                dtheta=max(le.values()))
+    for k in lrs:
+        if float(g_ref["lrs"][k].abs().max()) > 0:
+            errs["lr_" + k] = rel_err(grads["lrs"][k], g_ref["lrs"][k])
+        else:
+            assert float(grads["lrs"][k].abs().max()) == 0.0, k
+    print("outer gradient", optimize_window, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", max(le, key=le.get))
+    assert all(v < 2e-3 for v in errs.values()), errs
+    # the second-order terms matter on this problem: the first-order (FOMAML) estimate -- the last apply's own weight gradient
+    # at the adapted latents -- misses the oracle's outer gradient by far more than the tolerance above
+    _, (pK, aK, sK) = R.inner_loop(cfg, params, coords, img, p.repeat(B, 1, 1), a.repeat(B, 1, 1), sigma.repeat(B, 1, 1), lrs, K, masks,
+                                   optimize_gaussian_window=optimize_window, n_pos=2)
+    xs = coords[masks[K]][None].expand(B, -1, -1)
+    out = R.nef_apply(cfg, params, xs, pK, aK, sK)
+    _, g_fo, _, _, _ = R.fwd_bwd(cfg, params, xs, pK, aK, sK, 2 * (out - img[:, masks[K]]) / out.numel())
+    fo_err = max(leaf_errs(R.tree_flatten(g_fo["params"]), want).values())
+    print("first-order estimate misses by", f"{fo_err:.2e}")
+    assert fo_err > 2e-2

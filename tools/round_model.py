@@ -61,6 +61,47 @@ class Rounded(FM.Folded):
                  mpre=mpre, n=n, n_rstd=n_rstd, att=att, nbar=nbar, lse=(m + torch.log(l))[:, :, 0])
         self.S = S
         return nbar
+    # per-query tail with operand roundings: t_act (forward activations), t_w (weights), tb_g (dgrad cotangents), tw_act / tw_g
+    # (wgrad operands).  Cotangents are scaled by a power of two first, as the kernels do.
+    def tail_fwd(self, nbar):
+        cfg, w, f = self.cfg, self.w, self.f
+        H, d = cfg.num_heads, cfg.num_hidden
+        B, C = nbar.shape[:2]; q = self.q
+        T = {}
+        e1 = q(nbar.reshape(B, C, H * d), 't_act') @ q(f["W_A"], 't_w') + f["b_A"]
+        e3c, e_rstd = ln_core(gelu(e1))
+        e3 = e3c * w["fb_g"] + w["fb_beta"]
+        fo = q(e3, 't_act') @ q(w["fb_w2"], 't_w') + w["fb_b2"]
+        o1p = q(gelu(fo), 't_act') @ q(w["m0_w"], 't_w') + w["m0_b"]
+        o2p = q(gelu(o1p), 't_act') @ q(w["m1_w"], 't_w') + w["m1_b"]
+        out = gelu(o2p) @ w["m2_w"] + w["m2_b"]
+        T.update(e1=e1, e3c=e3c, e_rstd=e_rstd, e3=e3, fo=fo, o1p=o1p, o2p=o2p)
+        self.T = T
+        return out
+    def tail_bwd(self, nbar, d_out):
+        cfg, w, f, T = self.cfg, self.w, self.f, self.T
+        H, d = cfg.num_heads, cfg.num_hidden
+        B, C = nbar.shape[:2]; q = self.q
+        G = {}
+        fl = lambda t: t.reshape(-1, t.shape[-1])
+        gsc = 2.0 ** math.floor(math.log2(64.0 / float(d_out.abs().max())))
+        qg = lambda x, site: q(x * gsc, site) / gsc
+        o2 = gelu(T["o2p"])
+        G["m2_w"] = fl(o2).T @ fl(d_out); G["m2_b"] = fl(d_out).sum(0)
+        do2p = (d_out @ w["m2_w"].T) * gelu_grad(T["o2p"])
+        G["m1_w"] = fl(q(gelu(T["o1p"]), 'tw_act')).T @ fl(qg(do2p, 'tw_g')); G["m1_b"] = fl(do2p).sum(0)
+        do1p = (qg(do2p, 'tb_g') @ q(w["m1_w"], 't_w').T) * gelu_grad(T["o1p"])
+        G["m0_w"] = fl(q(gelu(T["fo"]), 'tw_act')).T @ fl(qg(do1p, 'tw_g')); G["m0_b"] = fl(do1p).sum(0)
+        dfo = (qg(do1p, 'tb_g') @ q(w["m0_w"], 't_w').T) * gelu_grad(T["fo"])
+        G["fb_w2"] = fl(q(T["e3"], 'tw_act')).T @ fl(qg(dfo, 'tw_g')); G["fb_b2"] = fl(dfo).sum(0)
+        de3 = qg(dfo, 'tb_g') @ q(w["fb_w2"], 't_w').T
+        G["fb_g"] = fl(de3 * T["e3c"]).sum(0); G["fb_beta"] = fl(de3).sum(0)
+        de2 = ln_core_bwd(de3 * w["fb_g"], T["e3c"], T["e_rstd"])
+        de1 = de2 * gelu_grad(T["e1"])
+        Gf = {}
+        Gf["W_A"] = fl(q(nbar.reshape(B, C, H * d), 'tw_act')).T @ fl(qg(de1, 'tw_g')); Gf["b_A"] = fl(de1).sum(0)
+        dnbar = (qg(de1, 'tb_g') @ q(f["W_A"], 't_w').T).reshape(B, C, H, d)
+        return dnbar, G, Gf
     def pairs_bwd(self, xi, sigma, dnbar):
         cfg, w, f, L, S = self.cfg, self.w, self.f, self.L, self.S
         H, d = cfg.num_heads, cfg.num_hidden
@@ -123,6 +164,15 @@ if __name__ == '__main__':
       'tanh proxy only': {},
       'all + tanh proxy': {s_: 'f16' for s_ in FWD_PAIR + BWD_PAIR},
     }
+    if os.environ.get("TAIL"):
+        exps = {
+          'tail: act fp16 (fwd)': {'t_act': 'f16'},
+          'tail: act + dgrad cot fp16': {'t_act': 'f16', 'tb_g': 'f16'},
+          'tail: act + cot + wgrad ops fp16': {'t_act': 'f16', 'tb_g': 'f16', 'tw_act': 'f16', 'tw_g': 'f16'},
+          'tail: all + weights fp16': {'t_act': 'f16', 'tb_g': 'f16', 'tw_act': 'f16', 'tw_g': 'f16', 't_w': 'f16'},
+          'pair fp16 only': {s_: 'f16' for s_ in FWD_PAIR + BWD_PAIR},
+          'pair + tail(act,cot,wgrad)': {**{s_: 'f16' for s_ in FWD_PAIR + BWD_PAIR}, 't_act': 'f16', 'tb_g': 'f16', 'tw_act': 'f16', 'tw_g': 'f16'},
+        }
     seeds = [int(a_) for a_ in sys.argv[1:]] or [1, 4]
     for seed in seeds:
         kw, B, C, Z = _draw(seed)
