@@ -146,7 +146,8 @@ def test_second_order_outer_gradient_against_oracle(optimize_window):
     (jax.value_and_grad at pde_trainer.py:255 through jax.grad at :188-204), K = 3 Meta-SGD steps: gradients w.r.t. the 46 NeF
     leaves, the shared autodecoder latents (p, a, gaussian_window) and the Meta-SGD learning rates.
     The Hessian-vector products are 4th-order central differences of the fp32 backward with the relu pattern frozen
-    (ENF_FLAG_FROZEN_RELU); tolerance 2e-3 on every quantity (per leaf for the weights), and the test also shows that the
+    (ENF_FLAG_FROZEN_RELU); tolerance 1e-4 -- the fp32 bucket -- on every quantity (per leaf for the weights; measured 3e-6), and
+    the test also shows that the
     first-order (FOMAML) estimate misses by far more than that, i.e. that the second-order terms are being checked."""
     import enf_pde_b200 as E
     from helpers import leaf_errs
@@ -168,7 +169,7 @@ def test_second_order_outer_gradient_against_oracle(optimize_window):
                                             {k: v.cuda() for k, v in lrs.items()}, K, [m.cuda() for m in masks],
                                             optimize_gaussian_window=optimize_window)
     from enf_pde_b200 import _lib
-    want = R.tree_flatten(g_ref["nef"])
+    want = R.tree_flatten(g_ref["nef"]["params"])
     got = {_lib.LEAF_PATHS[n]: t for n, t in zip(_lib.LEAVES, grads["nef"])}
     le = leaf_errs(got, want)
     errs = dict(loss=abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)), p=rel_err(grads["p"], g_ref["p"]),
@@ -180,7 +181,7 @@ def test_second_order_outer_gradient_against_oracle(optimize_window):
         else:
             assert float(grads["lrs"][k].abs().max()) == 0.0, k
     print("outer gradient", optimize_window, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", max(le, key=le.get))
-    assert all(v < 2e-3 for v in errs.values()), errs
+    assert all(v < TOL_FP32 for v in errs.values()), errs
     # the second-order terms matter on this problem: the first-order (FOMAML) estimate -- the last apply's own weight gradient
     # at the adapted latents -- misses the oracle's outer gradient by far more than the tolerance above
     _, (pK, aK, sK) = R.inner_loop(cfg, params, coords, img, p.repeat(B, 1, 1), a.repeat(B, 1, 1), sigma.repeat(B, 1, 1), lrs, K, masks,
