@@ -7,17 +7,22 @@
 // the documented XLA FFI C++ API (jaxlib >= 0.4.31) and guarded so that a build without the headers yields an empty
 // translation unit.  Where JAX exists:
 //
-//   g++ -O2 -std=c++17 -shared -fPIC -I"$(python -c 'import jax.ffi; print(jax.ffi.include_dir())')" \
+//   g++ -O2 -std=c++17 -shared -fPIC -I"$(python -c 'import jax.ffi; print(jax.ffi.include_dir())')"
 //       -I/usr/local/cuda/include -I../../include enf_xla_ffi.cc -L.. -lenf_b200 -o ../libenf_b200_xla.so
 //
 // Python side: enf_pde_b200/jax_binding.py (register_ffi_target + custom_vjp), described in INTEGRATION.md section 3.
 //
-// Operand order (both handlers):  x, p, a, sigma, <46 weight leaves in EnfWeights order>  [bwd: + workspace, d_out]
+// Operands   fwd: x, p, a, sigma, <46 weight leaves in EnfWeights order>
+//            bwd: x, p, a, sigma, workspace, d_out, <46 weight leaves in EnfWeights order>
 //   x      f32[B,C,Dx]  or  f32[C,Dx] (one grid shared by all fields -> x_batch_stride = 0, pde_trainer.py:197)
 //   sigma  f32[B,Z,1]   or  f32[0] when use_window == 0
-// Results:  fwd: out f32[B,C,O], workspace u8[enf_xattn_workspace_bytes]
-//           bwd: 46 weight-gradient leaves, dp f32[B,Z,P], da f32[B,Z,L], dsigma f32[B,Z,1]
-// Attributes: d, H, L, O, invariant_kind, use_window, precision, flags (all i32) = the EnfDesc fields XLA cannot infer.
+// Results    fwd: out f32[B,C,O], workspace u8[enf_xattn_workspace_bytes]
+//            bwd: workspace u8[...] (ALIASED to the workspace operand: jax_binding.py passes input_output_aliases={4: 0}, so
+//                 the library's scratch writes go to a buffer XLA knows is written), then the 46 weight-gradient leaves,
+//                 dp f32[B,Z,P], da f32[B,Z,L], dsigma f32[B,Z,1]
+// Attributes: d, H, L, O, invariant_kind, use_window, precision, flags, chunk_fields (all i32) = the EnfDesc fields XLA cannot
+// infer.  enf_xattn_bwd does not consume the forward state, so a vjp applied to several cotangents stays correct (XLA copies the
+// donated workspace when it is still live).
 #if defined(__has_include)
 #if __has_include("xla/ffi/api/ffi.h")
 #define ENF_HAVE_XLA_FFI 1
@@ -29,6 +34,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <type_traits>
 
@@ -43,7 +49,8 @@ namespace {
 using F32 = ffi::Buffer<ffi::F32>;
 
 ffi::Error describe(const F32& x, const F32& p, const F32& a, int32_t d, int32_t H, int32_t L, int32_t O, int32_t invariant_kind,
-                    int32_t use_window, int32_t precision, int32_t flags, EnfDesc* desc, int64_t* x_batch_stride) {
+                    int32_t use_window, int32_t precision, int32_t flags, int32_t chunk_fields, EnfDesc* desc, int64_t* x_batch_stride) {
+  std::memset(desc, 0, sizeof(*desc));
   auto xd = x.dimensions(), pd = p.dimensions(), ad = a.dimensions();
   if (pd.size() != 3 || ad.size() != 3 || (xd.size() != 2 && xd.size() != 3))
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_xattn: expected x[B,C,Dx] or x[C,Dx], p[B,Z,P], a[B,Z,L]");
@@ -54,6 +61,7 @@ ffi::Error describe(const F32& x, const F32& p, const F32& a, int32_t d, int32_t
   desc->Dx = (int32_t)xd[shared ? 1 : 2];
   desc->d = d; desc->H = H; desc->L = L; desc->O = O;
   desc->invariant_kind = invariant_kind; desc->use_window = use_window; desc->precision = precision; desc->flags = flags;
+  desc->chunk_fields = chunk_fields;
   if (ad[0] != pd[0] || ad[1] != pd[1] || ad[2] != L || (!shared && xd[0] != pd[0]))
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_xattn: x, p, a disagree on B / Z / latent_dim");
   if (pd[2] != enf_pose_dim(invariant_kind, desc->Dx))
@@ -84,10 +92,10 @@ ffi::Error status(int rc, const char* what) {
 
 ffi::Error FwdImpl(cudaStream_t stream, F32 x, F32 p, F32 a, F32 sigma, ffi::RemainingArgs leaves, ffi::ResultBuffer<ffi::F32> out,
                    ffi::ResultBuffer<ffi::U8> workspace, int32_t d, int32_t H, int32_t L, int32_t O, int32_t invariant_kind,
-                   int32_t use_window, int32_t precision, int32_t flags) {
+                   int32_t use_window, int32_t precision, int32_t flags, int32_t chunk_fields) {
   EnfDesc desc;
   int64_t xbs;
-  if (auto e = describe(x, p, a, d, H, L, O, invariant_kind, use_window, precision, flags, &desc, &xbs); e.failure()) return e;
+  if (auto e = describe(x, p, a, d, H, L, O, invariant_kind, use_window, precision, flags, chunk_fields, &desc, &xbs); e.failure()) return e;
   if (leaves.size() != ENF_NUM_WEIGHT_LEAVES) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_xattn_fwd: expected 46 weight leaves");
   EnfWeights w;
   if (auto e = collect_leaves(leaves, 0, &w, false); e.failure()) return e;
@@ -100,17 +108,22 @@ ffi::Error FwdImpl(cudaStream_t stream, F32 x, F32 p, F32 a, F32 sigma, ffi::Rem
                 "enf_xattn_fwd");
 }
 
-// operands: x, p, a, sigma, workspace (the forward's result, donated: input_output_aliases is not needed because the
-// library only requires the SAME device buffer, and XLA passes the forward's result buffer through unchanged), d_out,
-// then the 46 leaves.  results: 46 leaf gradients, dp, da, dsigma.
+// operands: x, p, a, sigma, workspace (the forward's result), d_out, then the 46 leaves.
+// results:  workspace_out (aliased to the workspace operand by the caller: same device buffer, but declared as WRITTEN, which
+//           an input operand is not), then 46 leaf gradients, dp, da, dsigma.
 ffi::Error BwdImpl(cudaStream_t stream, F32 x, F32 p, F32 a, F32 sigma, ffi::Buffer<ffi::U8> workspace, F32 d_out,
-                   ffi::RemainingArgs leaves, ffi::RemainingRets grads, int32_t d, int32_t H, int32_t L, int32_t O,
-                   int32_t invariant_kind, int32_t use_window, int32_t precision, int32_t flags) {
+                   ffi::RemainingArgs leaves, ffi::ResultBuffer<ffi::U8> workspace_out, ffi::RemainingRets grads, int32_t d,
+                   int32_t H, int32_t L, int32_t O, int32_t invariant_kind, int32_t use_window, int32_t precision, int32_t flags,
+                   int32_t chunk_fields) {
   EnfDesc desc;
   int64_t xbs;
-  if (auto e = describe(x, p, a, d, H, L, O, invariant_kind, use_window, precision, flags, &desc, &xbs); e.failure()) return e;
+  if (auto e = describe(x, p, a, d, H, L, O, invariant_kind, use_window, precision, flags, chunk_fields, &desc, &xbs); e.failure()) return e;
   if (leaves.size() != ENF_NUM_WEIGHT_LEAVES || grads.size() != ENF_NUM_WEIGHT_LEAVES + 3)
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_xattn_bwd: expected 46 leaves in, 46 + 3 gradients out");
+  if (workspace_out->typed_data() != workspace.typed_data())
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument,
+                      "enf_xattn_bwd: the workspace result must alias the workspace operand (input_output_aliases={4: 0}): the "
+                      "library keys the forward state on the buffer address");
   EnfWeights w;
   EnfWeightGrads gw;
   if (auto e = collect_leaves(leaves, 0, &w, false); e.failure()) return e;
@@ -120,8 +133,8 @@ ffi::Error BwdImpl(cudaStream_t stream, F32 x, F32 p, F32 a, F32 sigma, ffi::Buf
   const float* sg = (use_window && sigma.element_count() > 0) ? sigma.typed_data() : nullptr;
   float* dsg = (use_window && (*ds)->element_count() > 0) ? (*ds)->typed_data() : nullptr;
   return status(enf_xattn_bwd(&desc, &w, x.typed_data(), xbs, p.typed_data(), a.typed_data(), sg, d_out.typed_data(), &gw,
-                              (*dp)->typed_data(), (*da)->typed_data(), dsg, const_cast<uint8_t*>(workspace.typed_data()),
-                              (size_t)workspace.element_count(), (enf_stream_t)stream),
+                              (*dp)->typed_data(), (*da)->typed_data(), dsg, workspace_out->typed_data(),
+                              (size_t)workspace_out->element_count(), (enf_stream_t)stream),
                 "enf_xattn_bwd");
 }
 
@@ -144,7 +157,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnFwd, FwdImpl,
                                   .Attr<int32_t>("invariant_kind")
                                   .Attr<int32_t>("use_window")
                                   .Attr<int32_t>("precision")
-                                  .Attr<int32_t>("flags"));
+                                  .Attr<int32_t>("flags")
+                                  .Attr<int32_t>("chunk_fields"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnBwd, BwdImpl,
                               ffi::Ffi::Bind()
@@ -156,6 +170,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnBwd, BwdImpl,
                                   .Arg<ffi::Buffer<ffi::U8>>()   // workspace of the matching forward
                                   .Arg<F32>()                    // d_out
                                   .RemainingArgs()
+                                  .Ret<ffi::Buffer<ffi::U8>>()   // workspace, aliased to operand 4
                                   .RemainingRets()
                                   .Attr<int32_t>("d")
                                   .Attr<int32_t>("H")
@@ -164,7 +179,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnBwd, BwdImpl,
                                   .Attr<int32_t>("invariant_kind")
                                   .Attr<int32_t>("use_window")
                                   .Attr<int32_t>("precision")
-                                  .Attr<int32_t>("flags"));
+                                  .Attr<int32_t>("flags")
+                                  .Attr<int32_t>("chunk_fields"));
 
 #else   // no jaxlib headers: nothing to build (see the header comment)
 

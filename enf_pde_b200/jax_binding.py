@@ -46,19 +46,22 @@ def _register():
 
 
 def make_enf_apply(num_hidden, num_heads, num_out, latent_dim, invariant_type, num_in, use_gaussian_window=True,
-                   precision="bf16"):
-    """Returns enf_apply(leaves, x, p, a, sigma) -> (B, C, num_out), differentiable once in leaves, p, a, sigma."""
+                   precision="bf16", recompute=False, chunk_fields=0):
+    """Returns enf_apply(leaves, x, p, a, sigma) -> (B, C, num_out), differentiable once in leaves, p, a, sigma.
+    recompute: ENF_FLAG_RECOMPUTE (the workspace -- a custom_vjp residual, several of which are live inside inner_loop -- then
+    scales with chunk_fields fields instead of the batch)."""
     _register()
     lib = _lib.load()
     kind = _lib.INVARIANT_KINDS[invariant_type]
     prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+    flags = _lib.FLAG_RECOMPUTE if recompute else 0
     attrs = dict(d=np.int32(num_hidden), H=np.int32(num_heads), L=np.int32(latent_dim), O=np.int32(num_out),
                  invariant_kind=np.int32(kind), use_window=np.int32(int(use_gaussian_window)), precision=np.int32(prec),
-                 flags=np.int32(0))
+                 flags=np.int32(flags), chunk_fields=np.int32(chunk_fields))
 
     def ws_bytes(B, C, Z):
         desc = _lib.EnfDesc(B=B, C=C, Z=Z, d=num_hidden, H=num_heads, L=latent_dim, O=num_out, Dx=num_in, invariant_kind=kind,
-                            use_window=int(use_gaussian_window), precision=prec, flags=0)
+                            use_window=int(use_gaussian_window), precision=prec, flags=flags, chunk_fields=chunk_fields)
         n = lib.enf_xattn_workspace_bytes(ctypes.byref(desc))
         if n == 0:
             raise ValueError(lib.enf_last_error().decode())
@@ -84,10 +87,14 @@ def make_enf_apply(num_hidden, num_heads, num_out, latent_dim, invariant_type, n
     def vjp_bwd(res, d_out):
         ws, leaves, x, p, a, sigma = res
         sig = sigma if use_gaussian_window else jnp.zeros((0,), jnp.float32)
-        shapes = [jax.ShapeDtypeStruct(l.shape, jnp.float32) for l in leaves]
+        # result 0 = the workspace again, aliased to operand 4: the backward's scratch writes then go to a buffer XLA knows
+        # is written (an input operand may be aliased / CSE'd); XLA copies the donated residual if it is still live
+        shapes = [jax.ShapeDtypeStruct(ws.shape, jnp.uint8)]
+        shapes += [jax.ShapeDtypeStruct(l.shape, jnp.float32) for l in leaves]
         shapes += [jax.ShapeDtypeStruct(p.shape, jnp.float32), jax.ShapeDtypeStruct(a.shape, jnp.float32),
                    jax.ShapeDtypeStruct(sig.shape, jnp.float32)]
-        outs = jax.ffi.ffi_call("enf_xattn_bwd", tuple(shapes))(x, p, a, sig, ws, d_out, *leaves, **attrs)
+        outs = jax.ffi.ffi_call("enf_xattn_bwd", tuple(shapes), input_output_aliases={4: 0})(x, p, a, sig, ws, d_out, *leaves, **attrs)
+        outs = outs[1:]
         n = len(leaves)
         dsigma = outs[n + 2] if use_gaussian_window else None
         return (list(outs[:n]), jnp.zeros_like(x), outs[n], outs[n + 1], dsigma)

@@ -47,7 +47,7 @@ def test_bad_descriptions_are_rejected_without_a_gpu():
     lib = E.load_library()
     ok = dict(B=2, C=10, Z=4, d=32, H=2, L=8, O=1, Dx=2, invariant_kind=3, use_window=1, precision=0, flags=0)
     assert lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**ok))) > 0
-    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=16),
+    for bad in (dict(d=48), dict(H=5), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(precision=7), dict(flags=32), dict(flags=_lib.FLAG_FROZEN_RELU, precision=1),
                 dict(flags=_lib.FLAG_OUT_BF16), dict(chunk_fields=-1), dict(B=400, Z=64, H=4)):
         d = _lib.EnfDesc(**{**ok, **bad})
         assert lib.enf_xattn_workspace_bytes(ctypes.byref(d)) == 0, bad
@@ -100,6 +100,24 @@ def test_jax_binding_module_is_importable_and_refuses_without_jax():
     src = open(os.path.join(os.path.dirname(J.__file__), "csrc", "enf_xla_ffi.cc")).read()
     for sym in ("EnfXattnFwd", "EnfXattnBwd", "enf_xattn_fwd(", "enf_xattn_bwd(", "XLA_FFI_DEFINE_HANDLER_SYMBOL"):
         assert sym in src
+
+
+def test_xla_ffi_shim_type_checks():
+    """csrc/enf_xla_ffi.cc cannot be built against jaxlib in this image; it is at least type-checked on every run against a
+    minimal stand-in for xla/ffi/api/ffi.h (tests/mock_xla) that declares the part of the typed FFI API the shim uses."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "enf_pde_b200", "csrc", "enf_xla_ffi.cc")
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "mock_xla"),
+           "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "include"), src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    assert "const_cast<uint8_t*>" not in text            # the backward writes through an aliased RESULT, not an input operand
+    assert "workspace_out" in text and "chunk_fields" in text
 
 
 def test_forward_only_workspace_is_smaller():
