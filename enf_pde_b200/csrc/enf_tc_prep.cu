@@ -141,6 +141,82 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(int mode, const float
   if (warp == 0) tc::tmem_dealloc<128>(tm);
 }
 
+// ---- bring-up of num_hidden = 32 (K = N = 32 < the 64-element swizzle row): which MMA shapes read a half-used 128-byte row?
+// Tiles keep the 128-byte row pitch of the D >= 64 kernels; features 32..63 of every row are zero.
+//   mode 0: out[r][n] = sum_k X[r][k] Wt[n][k]     K-major A and B, N = 32, two K-steps
+//   mode 1: out[r][k] = sum_n X[r][n] Wt[n][k]     B = the image read MN-major with N = 32 (half a swizzle row)
+//   mode 3: same with N = 64 (reads the zero half too; output columns 32..63 are zeros)
+//   mode 2: out[i][j] = sum_r X[r][i] Y[r][j]      A MN-major with M = 64 (rows 32..63 of the result are zeros), B MN-major N = 32
+//   mode 4: same with N = 64
+__global__ void __launch_bounds__(128) tc_gemm_test32_kernel(int mode, const float* __restrict__ X, const float* __restrict__ Y,
+                                                             const uint8_t* __restrict__ img, float* __restrict__ out) {
+  constexpr int D = 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr uint32_t BLK = 128 * 128;
+  uint8_t* tA = base;
+  uint8_t* tB = base + BLK;
+  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { tc::mbar_init(&bar_w, 1); tc::mbar_init(&bar_mma, 1); tc::mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc<128>(&tmem_base);
+  for (int e = tid; e < 2 * (int)BLK / 16; e += 128) reinterpret_cast<uint4*>(base)[e] = make_uint4(0u, 0u, 0u, 0u);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  const bool wgrad = mode == 2 || mode == 4;
+  for (int c0 = 0; c0 < D; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = X[tid * D + c0 + i];
+    tc::st_row8_bf16(tA, BLK, tid, c0, v);
+    if (wgrad) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = Y[tid * D + c0 + i];
+      tc::st_row8_bf16(tB, BLK, tid, c0, v);
+    }
+  }
+  if (!wgrad && tid == 0) {
+    tc::mbar_expect_tx(&bar_w, (uint32_t)(D * 128));
+    tc::bulk_g2s(tB, img, (uint32_t)(D * 128), &bar_w);          // image = [32 rows][128 bytes], 64 of them used
+  }
+  tc::fence_proxy_async();
+  __syncthreads();
+  const int NN = (mode == 3 || mode == 4) ? 64 : 32;
+  if (tid == 0) {
+    if (!wgrad) tc::mbar_wait(&bar_w, 0);
+    tc::tc_fence_after();
+    const uint32_t a0 = tc::smem_u32(tA), b0 = tc::smem_u32(tB);
+    const uint32_t WBLK = D * 128;
+    if (mode == 0) {
+      const uint32_t idesc = tc::make_idesc(128, 32, tc::kOperandFmt, 0, 0);
+      for (int kk = 0; kk < 2; ++kk) tc::mma_f16(tm, tc::desc_kmajor(a0 + kk * 32), tc::desc_kmajor(b0 + kk * 32), idesc, kk > 0);
+    } else if (!wgrad) {
+      const uint32_t idesc = tc::make_idesc(128, NN, tc::kOperandFmt, 0, 1);
+      for (int kk = 0; kk < 2; ++kk) tc::mma_f16(tm, tc::desc_kmajor(a0 + kk * 32), tc::desc_mnmajor(b0 + kk * 2048, WBLK), idesc, kk > 0);
+    } else {
+      const uint32_t idesc = tc::make_idesc(64, NN, tc::kOperandFmt, 1, 1);
+      for (int kk = 0; kk < 128 / 16; ++kk) tc::mma_f16(tm, tc::desc_mnmajor(a0 + kk * 2048, BLK), tc::desc_mnmajor(b0 + kk * 2048, BLK), idesc, kk > 0);
+    }
+    tc::mma_commit(&bar_mma);
+  }
+  tc::mbar_wait(&bar_mma, 0);
+  tc::tc_fence_after();
+  const int out_row = wgrad ? (lane < 16 ? warp * 16 + lane : -1) : tid;       // M = 64: row r in lane 32 (r / 16) + r % 16
+  for (int c0 = 0; c0 < NN; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc::tmem_ld_wait();
+    if (out_row >= 0)
+      for (int i = 0; i < 32; ++i) out[out_row * 64 + c0 + i] = v[i];            // out: [128][64]
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<128>(tm);
+}
+
 }  // namespace
 
 int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual) {
@@ -157,6 +233,15 @@ int enf_launch_weight_image_T(cudaStream_t st, const float* W, void* img, int N,
 
 extern "C" int enf_debug_tc_gemm(int mode, int D, const float* X, const float* Y, float* out, void* scratch, enf_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (D == 32) {       // bring-up shapes of num_hidden = 32; out is [128][64]; scratch >= 4096 bytes
+    if (mode != 2 && mode != 4) {
+      if (cudaMemsetAsync(scratch, 0, 32 * 128, st) != cudaSuccess) return ENF_ERR_CUDA;
+      enf_launch_weight_image(st, Y, scratch, nullptr, 32, 32, 1, 0);
+    }
+    const size_t smem32 = 2 * 128 * 128 + 1024;
+    tc_gemm_test32_kernel<<<1, 128, smem32, st>>>(mode, X, Y, (const uint8_t*)scratch, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : ENF_ERR_CUDA;
+  }
   if (D != 64 && D != 128) return ENF_ERR_UNSUPPORTED;
   if (mode != 2) enf_launch_weight_image(st, Y, scratch, nullptr, D, D, 1, 0);
   size_t smem = 2 * (size_t)(D / 64) * 128 * 128 + 1024;

@@ -166,6 +166,7 @@ if __name__ == '__main__':
     }
     if os.environ.get("TAIL"):
         exps = {
+          'tail: weights fp16 only': {'t_w': 'f16'},
           'tail: act fp16 (fwd)': {'t_act': 'f16'},
           'tail: act + dgrad cot fp16': {'t_act': 'f16', 'tb_g': 'f16'},
           'tail: act + cot + wgrad ops fp16': {'t_act': 'f16', 'tb_g': 'f16', 'tw_act': 'f16', 'tw_g': 'f16'},
