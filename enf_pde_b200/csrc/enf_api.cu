@@ -118,7 +118,9 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     if (train && !tc_both) { Y.add("W3T", BZ * H * d2); Y.add("dWeff", BZ * H * d2); }
   }
   if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
-    Y.add("img_q_w1", d2 / 2); Y.add("img_v_w1", d2 / 2); Y.add("img_Wp", d2 / 2); Y.add("img_W3", BZ * H * d2 / 2);
+    // operand images: rows of max(d, 64) 16-bit features (d = 32 keeps the 128-byte row pitch), counted in floats
+    const size_t dimg = d * (d < 64 ? 64 : d) / 2;
+    Y.add("img_q_w1", dimg); Y.add("img_v_w1", dimg); Y.add("img_Wp", dimg); Y.add("img_W3", BZ * H * dimg);
     if (train) Y.add("slog", BC * (size_t)D.Z * H);
     Y.add("dbg_fwd", 8192);
     // tf32 stage GEMMs: activated copies of the decode-MLP pre-activations (their A operands arrive by TMA) and the
@@ -126,7 +128,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     Y.add("fo_act", BC * Hd); Y.add("o1_act", BC * d); Y.add("o2_act", BC * d);
     Y.add("lo_W_A", Hd * Hd); Y.add("lo_fb_w2", Hd * Hd); Y.add("lo_m0_w", Hd * d); Y.add("lo_m1_w", d2); Y.add("lo_mx_w1", d2);
     if (train && use_tc_bwd(D)) {
-      Y.add("img_q_w1_lo", d2 / 2); Y.add("img_v_w1_lo", d2 / 2);
+      Y.add("img_q_w1_lo", dimg); Y.add("img_v_w1_lo", dimg);
       const size_t Cpad = (size_t)((D.C + 127) / 128) * 128;      // kernels A / B work on whole 128-query tiles
       // per-(query, latent) tensors that live between the pair kernels of ONE backward chunk: all fields in the default
       // (stash) mode, chunk_fields fields with ENF_FLAG_RECOMPUTE
@@ -136,7 +138,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
       Y.add("duv", cC * (size_t)D.Z * 8);
       Y.add("dbg", 8192);
       // fp16 operand images of `that` per (field, latent, 128-query tile), stashed by the forward for backward kernel A
-      Y.add("that_img", cZ * Cpad * d / 2);
+      Y.add("that_img", cZ * Cpad * (d < 64 ? 64 : d) / 2);
       // rstd * gelu' of the same layer (fp16), stashed for backward kernel B: with `that` it is all the LayerNorm / gelu backward needs
       Y.add("dgr", cZ * Cpad * d / 2); Y.add("trstd", cZ * Cpad);
     }
@@ -285,7 +287,7 @@ void shift_fields(EnfPairTcParams& tp, const EnfDesc& D, int b0, int nb) {
   const int64_t bz = (int64_t)b0 * D.Z, bc = (int64_t)b0 * D.C, Hd = (int64_t)D.H * D.d;
   tp.B = nb;
   tp.xi += b0 * tp.xi_bs; tp.lam += bz * ENF_LAM_SIZE; if (tp.sigma) tp.sigma += bz;
-  tp.img_W3 += bz * D.H * (int64_t)D.d * D.d * 2;
+  tp.img_W3 += bz * D.H * (int64_t)D.d * (D.d < 64 ? 64 : D.d) * 2;
   tp.U += bz * Hd; tp.kappa += bz * D.H; tp.b3 += bz * Hd; tp.nbar += bc * Hd; tp.lse += bc * D.H;
   if (tp.slog) tp.slog += bz * D.C * D.H;
 }
@@ -295,7 +297,7 @@ void shift_fields(EnfPairTcBwdParams& tp, const EnfDesc& D, int b0, int nb) {
   const int64_t ntiles = (D.C + 127) / 128;
   tp.B = nb;
   tp.xi += b0 * tp.xi_bs; tp.lam += bz * ENF_LAM_SIZE; if (tp.sigma) tp.sigma += bz;
-  tp.img_W3 += bz * D.H * (int64_t)D.d * D.d * 2;
+  tp.img_W3 += bz * D.H * (int64_t)D.d * (D.d < 64 ? 64 : D.d) * 2;
   tp.U += bz * Hd; tp.b3 += bz * Hd; tp.slog += bz * D.C * D.H; tp.lse += bc * D.H; tp.nbar += bc * Hd;
   tp.dnbar += bc * Hd; tp.Dg += bc * D.H; tp.dnb16 += (int64_t)b0 * ntiles * 128 * Hd / 8;
   tp.g_W3 += bz * D.H * (int64_t)D.d * D.d; tp.g_b3 += bz * Hd;

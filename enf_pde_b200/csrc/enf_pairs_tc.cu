@@ -27,26 +27,35 @@ using namespace tcp;
 template <int D, int H> struct TcCfg {
   static constexpr int NQ = D / 32;                    // threads per query row (32 columns each)
   static constexpr int NT = ROWS * NQ;                 // threads per CTA
-  static constexpr uint32_t WIMG = D * D * 2;          // bytes of one weight image
+  static constexpr uint32_t WIMG = wimg_bytes<D>();    // bytes of one weight image
   static constexpr uint32_t WBLK = D * 128;            // bytes of one 64-feature block of a weight image
   static constexpr uint32_t ABLK = ROWS * 128;         // bytes of one 64-feature block of an activation tile
-  static constexpr uint32_t ATILE = (D / 64) * ABLK;
-  static constexpr int TMEM_COLS = (2 + H) * D <= 256 ? 256 : 512;   // T0 (also the RFF phases of the next latent) | T1 | H softmax accumulators
+  static constexpr uint32_t ATILE = atile_bytes<D>();
+  static constexpr uint32_t DTILE = ROWS * D * 2;      // bytes of one tile of the gelu' stash (fp16, chunked order)
+  // d = 32: the images are small, so ALL heads' W3[z,h] are staged together one latent ahead (d >= 64 streams W3[z,1] into the
+  // A0 tile once GEMM3 has released it), and with H = 3 the third head's GEMM4 reuses T0 after E4_0, which moves the next
+  // latent's RFF phases to a region of their own
+  static constexpr bool kStageAll = D == 32;
+  static constexpr uint32_t SBYTES = kStageAll ? H * WIMG : WIMG;
+  static constexpr bool kOwnPhaseRegion = H == 3;
+  static constexpr int TMEM_NEED = (2 + H) * D + (kOwnPhaseRegion ? D : 0);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;   // T0 (also the RFF phases of the next latent) | T1 | H softmax accumulators
   // byte offsets inside the 1024-aligned dynamic shared memory
   static constexpr uint32_t OFF_W = 0;                 // W1_q, W1_v, W' images
-  static constexpr uint32_t OFF_S = 3 * WIMG;          // W3[z,0] stage
-  static constexpr uint32_t OFF_A0 = OFF_S + WIMG;
+  static constexpr uint32_t OFF_S = 3 * WIMG;          // W3[z,0] stage (d = 32: W3[z,0..H-1])
+  static constexpr uint32_t OFF_A0 = OFF_S + SBYTES;
   static constexpr uint32_t OFF_A1 = OFF_A0 + ATILE;
   static constexpr uint32_t OFF_U = OFF_A1 + ATILE;    // projection operand: invariants of the 128 rows (2 atoms)
   static constexpr uint32_t OFF_OM = OFF_U + 2 * kProjAtom;   // projection operand: [Omega_q | Omega_v] (D / 64 atoms)
   // staging of the backward's stash rstd * gelu' (one activation tile): the W3 stage buffer where that is large enough (d = 128)
-  static constexpr uint32_t OFF_G = OFF_OM + (D / 64) * kProjAtom;
+  static constexpr uint32_t OFF_G = OFF_OM + nblk<D>() * kProjAtom;
   static constexpr uint32_t OFF_F = OFF_G + (WIMG >= ATILE ? 0 : ATILE);    // float arrays start here
   // float arrays (counts)
   // per-latent vectors are double buffered (cp.async prefetch of the next latent): [2] x { Lam 64 | U H*D | b3 H*D | kappa, sigma 8 }
   static constexpr int F_LAT = 64 + 2 * H * D + 8;
-  static constexpr int F_WIN = 2 * ROWS, F_BIAS = 3 * D, F_EXCH = 2 * NQ * ROWS * 2;
-  static_assert(H <= 2, "the logit partials [NQ][ROWS][H] share exchange buffer 1");
+  static constexpr int F_WIN = 2 * ROWS, F_BIAS = 3 * D, F_EXCH = NQ * ROWS * 2 + NQ * ROWS * (H > 2 ? H : 2);
+  static_assert(H <= 2 || D == 32, "three heads: num_hidden = 32 only (TMEM: T0 | T1 | H accumulators | phases)");
+  static_assert(H <= 3, "the logit partials [NQ][ROWS][H] share exchange buffer 1");
   static constexpr int F_TOTAL = 2 * F_LAT + F_WIN + F_BIAS + F_EXCH;
   static constexpr uint32_t SMEM_BYTES = OFF_F + F_TOTAL * 4 + 128 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -61,7 +70,7 @@ template <int D, int H> struct TcCfg {
 #endif
 
 template <int D, int H>
-__global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
+__global__ void __launch_bounds__(TcCfg<D, H>::NT, D <= 64 ? 2 : 1) pairs_fwd_tc_kernel(EnfPairTcParams P) {
   using C = TcCfg<D, H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer stays in the shared address space (LDS/STS, not generic LD/ST)
@@ -83,10 +92,10 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
   uint64_t* bar_g1 = bars + 1;
   uint64_t* bar_g2 = bars + 2;
   uint64_t* bar_g3 = bars + 3;
-  uint64_t* bar_g4 = bars + 4;                // [2]
-  uint64_t* bar_w3 = bars + 6;                // [2]
-  uint64_t* bar_p = bars + 8;                 // RFF phases of the next latent are in TMEM
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_g4 = bars + 4;                // [3]
+  uint64_t* bar_w3 = bars + 7;                // [2]
+  uint64_t* bar_p = bars + 9;                 // RFF phases of the next latent are in TMEM
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = warp & 3, cq = warp >> 2;
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
   constexpr int HD = D / 2;
 
   if (tid == 0) {
-    for (int i = 0; i < 9; ++i) tc::mbar_init(bars + i, 1);
+    for (int i = 0; i < 10; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
   if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
@@ -111,13 +120,20 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
     if (tid < NU) tc::cp_async<16>(dst + 64 + 4 * tid, P.U + q * H * D + 4 * tid);
     else if (tid < 2 * NU) tc::cp_async<16>(dst + 64 + H * D + 4 * (tid - NU), P.b3 + q * H * D + 4 * (tid - NU));
     else if (tid < 2 * NU + ENF_LAM_SIZE / 4) tc::cp_async<16>(dst + 4 * (tid - 2 * NU), P.lam + q * ENF_LAM_SIZE + 4 * (tid - 2 * NU));
-    else if (tid == 2 * NU + ENF_LAM_SIZE / 4) tc::cp_async<4 * H>(dst + 64 + 2 * H * D, P.kappa + q * H);
+    else if (tid == 2 * NU + ENF_LAM_SIZE / 4) {
+      if (H == 3) {          // 12 bytes is not a cp.async size (and q * 12 bytes is only 4-byte aligned)
+#pragma unroll
+        for (int h = 0; h < H; ++h) tc::cp_async<4>(dst + 64 + 2 * H * D + h, P.kappa + q * H + h);
+      } else {
+        tc::cp_async<4 * (H == 3 ? 1 : H)>(dst + 64 + 2 * H * D, P.kappa + q * H);
+      }
+    }
     else if (tid == 2 * NU + ENF_LAM_SIZE / 4 + 1 && P.sigma) tc::cp_async<4>(dst + 64 + 2 * H * D + 4, P.sigma + q);
   };
   prefetch_latent(0);
   tc::cp_async_wait_all();
   proj_zero(sU, 2, tid, C::NT);
-  proj_zero(sOm, D / 64, tid, C::NT);
+  proj_zero(sOm, nblk<D>(), tid, C::NT);
   // every thread keeps its row's query features in registers for the whole kernel (the NQ threads of a row share the
   // invariant rows of the next latent between them)
   float xi_r[8];
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
   // thread of the row also the window value
   auto write_invariants = [&](const float* lat, int wbuf) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < (6 + C::NQ - 1) / C::NQ; ++k) {
       const int i = cq + k * C::NQ;
       if (i < P.I && i < 6) proj_store_pair(sU, i, row, inv_row(P, lat, xi_r, i), true);
     }
@@ -151,7 +167,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
   // T0 doubles as the landing zone of the next latent's RFF phases (issued once E4_0 has read it), which leaves H x D columns
   // for the softmax-weighted accumulators: they live in TMEM (tcgen05.ld / st once per latent and head), not in 64 registers
   // per thread, so that the epilogues have registers for more than one dependent chain in flight.
-  const uint32_t t0 = tm, t1 = tm + D, tp = tm, tacc = tm + 2 * D;
+  const uint32_t t0 = tm, t1 = tm + D, tacc = tm + 2 * D, tp = C::kOwnPhaseRegion ? tm + (2 + H) * D : tm;
   const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
   const uint32_t my_t = lane_off + col0;      // lane-quadrant / column offset of this warp
 
@@ -160,8 +176,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
     tc::bulk_g2s(sW, P.img_q_w1, C::WIMG, bar_w);
     tc::bulk_g2s(sW + C::WIMG, P.img_v_w1, C::WIMG, bar_w);
     tc::bulk_g2s(sW + 2 * C::WIMG, P.img_Wp, C::WIMG, bar_w);
-    tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
-    tc::bulk_g2s(sS, P.img_W3 + ((int64_t)b * P.Z * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+    tc::mbar_expect_tx(&bar_w3[0], C::SBYTES);
+    tc::bulk_g2s(sS, P.img_W3 + ((int64_t)b * P.Z * H) * C::WIMG, C::SBYTES, &bar_w3[0]);
   }
   const uint32_t aA0 = tc::smem_u32(sA0), aA1 = tc::smem_u32(sA1), aS = tc::smem_u32(sS), aW = tc::smem_u32(sW);
   const uint32_t aU = tc::smem_u32(sU), aOm = tc::smem_u32(sOm);
@@ -314,7 +330,7 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
     tc::mbar_wait(bar_g3, par);
     tc::tc_fence_after();
     F_STAMP(11);
-    if (H > 1 && tid == 0) {          // A0 is free again: stream W3[z,1] into it
+    if (H > 1 && !C::kStageAll && tid == 0) {          // A0 is free again: stream W3[z,1] into it
       tc::mbar_expect_tx(&bar_w3[1], C::WIMG);
       tc::bulk_g2s(sA0, P.img_W3 + (bz * H + 1) * C::WIMG, C::WIMG, &bar_w3[1]);
     }
@@ -356,8 +372,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
       issue_gemm<D>(t0, aA1, aS, C::ABLK, C::WBLK);
       tc::mma_commit(&bar_g4[0]);
       if (H > 1) {
-        tc::mbar_wait(&bar_w3[1], par);
-        issue_gemm<D>(t1, aA1, aA0, C::ABLK, C::WBLK);
+        if (!C::kStageAll) tc::mbar_wait(&bar_w3[1], par);
+        issue_gemm<D>(t1, aA1, C::kStageAll ? aS + C::WIMG : aA0, C::ABLK, C::WBLK);
         tc::mma_commit(&bar_g4[1]);
       }
     }
@@ -373,9 +389,9 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
       tc::mbar_wait(&bar_g4[h], par);
       tc::tc_fence_after();
       F_STAMP(16 + 2 * h);
-      tc::tmem_ld32((h == 0 ? t0 : t1) + my_t, v);
+      tc::tmem_ld32(((h & 1) ? t1 : t0) + my_t, v);
       tc::tmem_ld_wait();
-      if (h == 0 && (more || P.dgr)) {
+      if (h == 0 && (more || P.dgr || H == 3)) {
         // GEMM4_0 is complete, so the W3 stage buffer is free: it stages the backward's stash rstd * gelu' (in kernel B's load
         // order [column quarter][chunk][row] x 16 bytes), which then leaves by ONE bulk store -- 64 STG.128 per CTA in a burst
         // stalled every warp on the SM's store path instead.  T0 has been read by this thread: when everybody has, the next
@@ -395,8 +411,12 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
               issue_proj(tp, aU, aOm, D);
               tc::mma_commit(bar_p);
             }
+            if (H == 3) {      // T0 has been read by everybody: the third head's GEMM4 goes there
+              issue_gemm<D>(t0, aA1, aS + 2 * C::WIMG, C::ABLK, C::WBLK);
+              tc::mma_commit(&bar_g4[2]);
+            }
             if (P.dgr) {
-              tc::bulk_s2g(P.dgr + ((size_t)bz * gridDim.x + blockIdx.x) * (C::ATILE / 16), sG, C::ATILE);
+              tc::bulk_s2g(P.dgr + ((size_t)bz * gridDim.x + blockIdx.x) * (C::DTILE / 16), sG, C::DTILE);
               tc::bulk_commit();
             }
           }
@@ -424,8 +444,8 @@ __global__ void __launch_bounds__(TcCfg<D, H>::NT, D == 64 ? 2 : 1) pairs_fwd_tc
     if (tid == 0) {
       if (P.that_img) tc::bulk_wait_read0();   // the stashes have been read out of A1 / the stage buffer before they are overwritten
       if (more) {                              // stage buffer: next latent's W3[.,0] (needed by its GEMM4_0, most of a latent away)
-        tc::mbar_expect_tx(&bar_w3[0], C::WIMG);
-        tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::WIMG, &bar_w3[0]);
+        tc::mbar_expect_tx(&bar_w3[0], C::SBYTES);
+        tc::bulk_g2s(sS, P.img_W3 + ((bz + 1) * H) * C::WIMG, C::SBYTES, &bar_w3[0]);
       }
     }
     tc::tmem_st_wait();
@@ -465,9 +485,12 @@ int launch_tc(cudaStream_t st, const EnfPairTcParams& p) {
 
 }  // namespace
 
-bool enf_pairs_fwd_tc_supported(int d, int H) { return (d == 128 || d == 64) && (H == 1 || H == 2); }
+bool enf_pairs_fwd_tc_supported(int d, int H) { return ((d == 128 || d == 64) && (H == 1 || H == 2)) || (d == 32 && H >= 1 && H <= 3); }
 
 int enf_launch_pairs_fwd_tc(cudaStream_t st, int d, int H, const EnfPairTcParams& p) {
+  if (d == 32 && H == 3) return launch_tc<32, 3>(st, p);
+  if (d == 32 && H == 2) return launch_tc<32, 2>(st, p);
+  if (d == 32 && H == 1) return launch_tc<32, 1>(st, p);
   if (d == 128 && H == 2) return launch_tc<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_tc<128, 1>(st, p);
   if (d == 64 && H == 2) return launch_tc<64, 2>(st, p);

@@ -25,11 +25,12 @@ using namespace tcp;
 template <int D, int H> struct BwdCfg {
   static constexpr int NQ = D / 32;
   static constexpr int NT = ROWS * NQ;
-  static constexpr uint32_t WIMG = D * D * 2;
+  static constexpr uint32_t WIMG = wimg_bytes<D>();
   static constexpr uint32_t WBLK = D * 128;
   static constexpr uint32_t ABLK = ROWS * 128;
-  static constexpr uint32_t ATILE = (D / 64) * ABLK;
+  static constexpr uint32_t ATILE = atile_bytes<D>();
   static constexpr int HD = D / 2;
+  static_assert(H <= 2 || D == 32, "three heads: num_hidden = 32 only");
 };
 
 __device__ __forceinline__ void load_scale(const float* gmax, float& gs, float& inv_gs) {
@@ -122,8 +123,8 @@ template <int D, int H> struct ACfg {
 // Warp roles: warps 0..15 are the epilogue warps (thread layout of enf_pairs_tc_common.cuh); warp 16 only issues --
 // bulk copies, tcgen05.mma, commits.  Epilogue warps never block on each other: when their part of an operand tile is
 // written they ARRIVE on a named barrier the issue warp SYNCs on, and go on with whatever does not need that MMA.
-constexpr int kABarHead = 5;      // + h: dm_h tile written                      (named barriers 1..4 belong to row_exchange)
-constexpr int kABarDth = 7;       // dthat of the tile has been read out of TMEM
+constexpr int kABarHead = 5;      // + h (h < 3): dm_h tile written              (named barriers 1..4 belong to row_exchange)
+constexpr int kABarDth = 8;       // dthat of the tile has been read out of TMEM
 using tc::named_arrive;
 using tc::named_sync;
 
@@ -138,7 +139,7 @@ using tc::named_sync;
 // SEP = true: a 17th warp issues (96 registers per thread: the register file is granted in units of 4 warps);
 // SEP = false: warp 0 issues between its own epilogue phases (it SYNCs on the named barriers, the others ARRIVE), 128 registers.
 template <int D, int H, bool SEP>
-__global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2 : 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D <= 64 ? 2 : 1) pairs_bwd_tc_a_kernel(EnfPairTcBwdParams P) {
   using C = BwdCfg<D, H>;
   using A = ACfg<D, H>;
   constexpr int NTA = C::NT + (SEP ? 32 : 0);         // epilogue threads (+ the issue warp)
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
   float* s_db3 = f; f += H * D;
   float* s_rs = f; f += 2 * 3 * ROWS * H;             // [2 tiles][logit | lse | Dg][ROWS][H], filled one tile ahead by cp.async
   uint64_t* bars = reinterpret_cast<uint64_t*>(f);
-  uint64_t *bar_w = bars, *bar_t = bars + 1 /*[2]*/, *bar_g4 = bars + 3 /*[2]*/, *bar_d = bars + 5, *bar_gb = bars + 6;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t *bar_w = bars, *bar_t = bars + 1 /*[2]*/, *bar_g4 = bars + 3 /*[3]*/, *bar_d = bars + 6, *bar_gb = bars + 7;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool issuer = SEP && warp == 16;
@@ -166,12 +167,15 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
   const uint8_t* timg = P.that_img + (size_t)bz * ntiles * C::ATILE;
 
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
-  // two working regions + H weight-gradient accumulators; at d = 64 that is half of TMEM (and of shared memory, and 128
-  // registers per thread for 256 threads): two CTAs per SM, each filling the other's MMA / barrier waits
-  constexpr int kTmemCols = (2 + H) * D <= 256 ? 256 : 512;
+  // two working regions (three with three heads: the third head's m has a region of its own) + H weight-gradient
+  // accumulators; at d <= 64 that is at most half of TMEM (and of shared memory, and 128 registers per thread for <= 256
+  // threads): two CTAs per SM, each filling the other's MMA / barrier waits
+  constexpr int kWork = H == 3 ? 3 : 2;
+  constexpr int kTmemNeed = (kWork + H) * D;
+  constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   if (warp == 0) tc::tmem_alloc<kTmemCols>(s_tmem);
   for (int e = tid; e < H * D; e += NTA) { s_b3[e] = P.b3[bz * H * D + e]; s_db3[e] = 0.f; }
   float gs, inv_gs;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = *s_tmem;
-  const uint32_t tW3 = tm + 2 * D;
+  const uint32_t tW3 = tm + kWork * D, tR2 = tm + 2 * D;      // tR2: working region of the third head (H = 3)
   const uint32_t lane_off = (uint32_t)(lq * 32) << 16;
   const uint32_t my_t = lane_off + col0;
   const uint32_t aW3 = tc::smem_u32(sW3), aT = tc::smem_u32(sT), aDm = tc::smem_u32(sDm);
@@ -203,6 +207,10 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
     if (H > 1) {
       issue_gemm<D>(tm + (e ^ 1) * D, aT + e * C::ATILE, aW3 + C::WIMG, C::ABLK, C::WBLK);
       tc::mma_commit(&bar_g4[1]);
+    }
+    if (H > 2) {                                      // every head's epilogue of the previous tile is behind the barrier too
+      issue_gemm<D>(tR2, aT + e * C::ATILE, aW3 + 2 * C::WIMG, C::ABLK, C::WBLK);
+      tc::mma_commit(&bar_g4[2]);
     }
     if (ct + 1 < ntiles) {                            // next that tile -> the other buffer, once the previous tile's wgrad has read it
       if (ct > 0) tc::mbar_wait(bar_gb, (ct - 1) & 1);
@@ -256,9 +264,19 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
       if (cq == 0 && c < P.C) {
         const int64_t q = (int64_t)b * P.C + c;
         float* dst = s_rs + (ct & 1) * 3 * ROWS * H + row * H;
-        tc::cp_async<4 * H>(dst, P.slog + (bz * P.C + c) * H);
-        tc::cp_async<4 * H>(dst + ROWS * H, P.lse + q * H);
-        tc::cp_async<4 * H>(dst + 2 * ROWS * H, P.Dg + q * H);
+        if (H == 3) {        // 12 bytes is not a cp.async size
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            tc::cp_async<4>(dst + h, P.slog + (bz * P.C + c) * H + h);
+            tc::cp_async<4>(dst + ROWS * H + h, P.lse + q * H + h);
+            tc::cp_async<4>(dst + 2 * ROWS * H + h, P.Dg + q * H + h);
+          }
+        } else {
+          constexpr int kB = 4 * (H == 3 ? 1 : H);
+          tc::cp_async<kB>(dst, P.slog + (bz * P.C + c) * H);
+          tc::cp_async<kB>(dst + ROWS * H, P.lse + q * H);
+          tc::cp_async<kB>(dst + 2 * ROWS * H, P.Dg + q * H);
+        }
       }
     };
     if (!SEP && warp == 0) {
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
         tc::mbar_wait(&bar_g4[h], par);
         tc::tc_fence_after();
         A_STAMP(32, 2 + 8 * h);
-        tc::tmem_ld32((h == 0 ? tF : tS) + my_t, v);
+        tc::tmem_ld32((h == 0 ? tF : h == 1 ? tS : tR2) + my_t, v);
         tc::tmem_ld_wait();
         A_STAMP(32, 3 + 8 * h);
         // one pass, one exchange: with g = gelu(m), n = (g - mu) rstd the row sums the LayerNorm backward needs are
@@ -410,9 +428,8 @@ __global__ void __launch_bounds__(BwdCfg<D, H>::NT + (SEP ? 32 : 0), D == 64 ? 2
   __syncthreads();
   tc::tc_fence_after();
   if (!issuer) {
-    // accumulator row (input feature) of this thread: M = 128 keeps row r in TMEM lane r, M = 64 (d = 64) in lane
-    // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
-    const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
+    // accumulator row (input feature) of this thread (enf_pairs_tc_common.cuh: wgrad_row)
+    const int wrow = wgrad_row<D>(row, lq, lane);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       float w[32];
@@ -458,9 +475,12 @@ int launch_main(cudaStream_t st, const EnfPairTcBwdParams& p) {
 
 }  // namespace
 
-bool enf_pairs_bwd_tc_supported(int d, int H) { return (d == 128 || d == 64) && (H == 1 || H == 2); }
+bool enf_pairs_bwd_tc_supported(int d, int H) { return ((d == 128 || d == 64) && (H == 1 || H == 2)) || (d == 32 && H >= 1 && H <= 3); }
 
 int enf_launch_pairs_bwd_tc_prep(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
+  if (d == 32 && H == 3) return launch_prep<32, 3>(st, p);
+  if (d == 32 && H == 2) return launch_prep<32, 2>(st, p);
+  if (d == 32 && H == 1) return launch_prep<32, 1>(st, p);
   if (d == 128 && H == 2) return launch_prep<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_prep<128, 1>(st, p);
   if (d == 64 && H == 2) return launch_prep<64, 2>(st, p);
@@ -469,6 +489,9 @@ int enf_launch_pairs_bwd_tc_prep(cudaStream_t st, int d, int H, const EnfPairTcB
 }
 
 int enf_launch_pairs_bwd_tc_main(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
+  if (d == 32 && H == 3) return launch_main<32, 3>(st, p);
+  if (d == 32 && H == 2) return launch_main<32, 2>(st, p);
+  if (d == 32 && H == 1) return launch_main<32, 1>(st, p);
   if (d == 128 && H == 2) return launch_main<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_main<128, 1>(st, p);
   if (d == 64 && H == 2) return launch_main<64, 2>(st, p);

@@ -24,10 +24,13 @@ template <int D, int H> struct QCfg {
   static constexpr int NQ = D / 32;
   static constexpr int NT = ROWS * NQ;
   static constexpr int HD = D / 2;
-  static constexpr uint32_t WIMG = D * D * 2;
+  static constexpr uint32_t WIMG = wimg_bytes<D>();
   static constexpr uint32_t WBLK = D * 128;
   static constexpr uint32_t ABLK = ROWS * 128;
-  static constexpr uint32_t ATILE = (D / 64) * ABLK;
+  static constexpr uint32_t ATILE = atile_bytes<D>();
+  static constexpr int TMEM_NEED = 2 * D + 64 + 48;           // T | dW1_q | phases (64) | db1q | dU | du (16 each)
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(1 + 2 * H <= 8, "side operand row: [1 | ds_hi (H) | ds_lo (H)] in 8 halves");
   static constexpr uint32_t OFF_W = 0;                         // W1_q image, W1_q low image
   static constexpr uint32_t OFF_GHI = 2 * WIMG;                // gamma_q hi
   static constexpr uint32_t OFF_GLO = OFF_GHI + ATILE;         // gamma_q lo -> h1q -> dproj
@@ -55,7 +58,7 @@ __device__ __forceinline__ void load_scale_q(const float* gmax, float& gs, float
 // D[D x 16] (+)= Act^T S : Act = [128 rows][D] activation tile read MN-major (M = feature), S = [128 rows][16] side operand
 template <int D>
 __device__ __forceinline__ void issue_rowsum(uint32_t d_tmem, uint32_t act_addr, uint32_t s_addr, uint32_t ablk, uint32_t accumulate) {
-  constexpr uint32_t idesc = tc::make_idesc(D, 16, tc::kOperandFmt, 1, 1);
+  constexpr uint32_t idesc = tc::make_idesc(wgrad_m<D>(), 16, tc::kOperandFmt, 1, 1);
 #pragma unroll
   for (int kk = 0; kk < ROWS / 16; ++kk)
     tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_mnmajor(s_addr + kk * 2048, ROWS * 128), idesc,
@@ -78,13 +81,14 @@ __device__ __forceinline__ void issue_du(uint32_t d_tmem, uint32_t a_addr, uint3
 #endif
 
 template <int D, int H>
-__global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
   using C = QCfg<D, H>;
   constexpr int HD = C::HD;
   constexpr int MMA_TID = C::NT - 128;                // lane 0 of the first warp of the last column quarter
   // per-row side work by column quarter: 0 = next tile's invariants, kPart0 / kPart1 = the two halves of the previous
-  // tile's window / invariant backward (at d = 64 a row has two threads: quarter 0 also takes the second half)
-  constexpr int kPart0 = 1, kPart1 = C::NQ > 2 ? 2 : 0;
+  // tile's window / invariant backward (at d = 64 a row has two threads: quarter 0 also takes the second half; at d = 32 it
+  // has one, which takes everything)
+  constexpr int kPart0 = C::NQ > 1 ? 1 : 0, kPart1 = C::NQ > 2 ? 2 : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = base + C::OFF_W;
@@ -113,13 +117,13 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
   const float scale = rsqrtf((float)D);
   // row (feature) of an M = D accumulator held by my TMEM lane: M = 128 keeps row r in lane r, M = 64 (d = 64) in lane
   // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
-  const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
+  const int wrow = wgrad_row<D>(row, lq, lane);
 
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 0) tc::tmem_alloc<512>(s_tmem);
+  if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
   for (int e = tid; e < D; e += C::NT) s_b1q[e] = P.q_b1[e];
   {
     uint4* z4 = reinterpret_cast<uint4*>(sS);          // S, U, Om, OmT are contiguous
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
       rx[2] = make_float4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]);
       rx[3] = make_float4(rec.u[4], rec.u[5], rec.w, rec.c);
     };
-    float lam_acc = 0.f, kap_acc[H];                   // lam_acc: cq == 1 threads hold dLam[0..31], cq == 2 threads dLam[32..55] | dsigma
+    float lam_acc0 = 0.f, lam_acc1 = 0.f, kap_acc[H];         // lam_acc<part> of the thread that owns `part`: 0: dLam[0..31], 1: dLam[32..55] | dsigma
 #pragma unroll
     for (int h = 0; h < H; ++h) kap_acc[h] = 0.f;
     // du (tile ct) + du_v -> window backward -> dq -> my half of dLam / dsigma partial sums (lane l keeps column l).
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
           vv[e] = e1 < ENF_LAM_SIZE ? dq[e1 >> 3] * xi_r[e1 & 7] : (e1 == ENF_LAM_SIZE ? dsg : 0.f);
         }
       }
-      lam_acc += warp_colsum32(vv, lane);
+      const float cs = warp_colsum32(vv, lane);
+      if (part == 0) lam_acc0 += cs; else lam_acc1 += cs;
     };
 
     if (cq == 0) {
@@ -335,9 +340,10 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
         for (int h = 0; h < H; ++h) { kap_acc[h] += dsv[h]; dw += dsv[h]; }
         s_rx[(((it0 + ct) % 3) * ROWS + row) * C::RX + 16] = dw;
         if (ct + 1 < ntiles) write_invariants(ct + 1, pre8);
-        if (kPart1 == 0 && ct > 0) {                       // d = 64: this thread also owns the second half of the row backward
-          float duv[8];
+        if (kPart1 == 0 && ct > 0) {                       // d <= 64: this thread also owns the second half of the row backward
+          float duv[8];                                    //          (d = 32: both halves)
           load_duv(ct - 1, duv);
+          if (kPart0 == 0) row_backward(ct - 1, (it - 1) & 1, 0, duv);
           row_backward(ct - 1, (it - 1) & 1, 1, duv);
         }
       } else if ((cq == kPart0 || cq == kPart1) && ct > 0) {
@@ -439,11 +445,14 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
     }
     // ---- item flush --------------------------------------------------------------------------------------------------
     if (cq == kPart0 || cq == kPart1) {
-      const int part = cq == kPart0 ? 0 : 1;
       float duv[8];
       load_duv(ntiles - 1, duv);
-      row_backward(ntiles - 1, (it - 1) & 1, part, duv);
-      atomicAdd(&s_dlam[part * 32 + lane], lam_acc);
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        if (cq != (part == 0 ? kPart0 : kPart1)) continue;
+        row_backward(ntiles - 1, (it - 1) & 1, part, duv);
+        atomicAdd(&s_dlam[part * 32 + lane], part == 0 ? lam_acc0 : lam_acc1);
+      }
     }
     {
       tc::mbar_wait(bar_u, (it - 1) & 1);
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, 1) pairs_bwd_tc_q_kernel(EnfPa
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<512>(tm);
+  if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tm);
 }
 
 template <int D, int H>
@@ -500,7 +509,8 @@ int launch_q(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = QCfg<D, H>;
   if (cudaFuncSetAttribute(pairs_bwd_tc_q_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess) return -1;
   int nitems = p.B * p.Z;
-  int grid = nitems < 148 ? nitems : 148;
+  const int ctas = (D == 32 ? 2 : 1) * 148;                 // d = 32: two CTAs per SM (half of TMEM each)
+  int grid = nitems < ctas ? nitems : ctas;
   pairs_bwd_tc_q_kernel<D, H><<<grid, C::NT, C::SMEM_BYTES, st>>>(p);
   return 1;
 }
@@ -508,6 +518,9 @@ int launch_q(cudaStream_t st, const EnfPairTcBwdParams& p) {
 }  // namespace
 
 int enf_launch_pairs_bwd_tc_q(cudaStream_t st, int d, int H, const EnfPairTcBwdParams& p) {
+  if (d == 32 && H == 3) return launch_q<32, 3>(st, p);
+  if (d == 32 && H == 2) return launch_q<32, 2>(st, p);
+  if (d == 32 && H == 1) return launch_q<32, 1>(st, p);
   if (d == 128 && H == 2) return launch_q<128, 2>(st, p);
   if (d == 128 && H == 1) return launch_q<128, 1>(st, p);
   if (d == 64 && H == 2) return launch_q<64, 2>(st, p);

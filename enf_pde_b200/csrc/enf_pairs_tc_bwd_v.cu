@@ -29,10 +29,13 @@ template <int D> struct VCfg {
   static constexpr int NQ = D / 32;
   static constexpr int NT = ROWS * NQ;
   static constexpr int HD = D / 2;
-  static constexpr uint32_t WIMG = D * D * 2;
+  static constexpr uint32_t WIMG = wimg_bytes<D>();
   static constexpr uint32_t WBLK = D * 128;
   static constexpr uint32_t ABLK = ROWS * 128;
-  static constexpr uint32_t ATILE = (D / 64) * ABLK;
+  static constexpr uint32_t ATILE = atile_bytes<D>();
+  static constexpr int TMEM_NEED = 3 * D + 64 + 48;           // T | dW' | dW1_v | phases (64) | db' | db1v | du (16 each)
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int kDuCq = NQ > 1 ? 1 : 0;                // the row's thread that hands du to kernel C
   static constexpr uint32_t OFF_W = 0;                         // W1_v image, W1_v low image, W' image
   static constexpr uint32_t OFF_GHI = 3 * WIMG;                // gamma_v hi
   static constexpr uint32_t OFF_X = OFF_GHI + ATILE;           // gamma_v lo -> h1v -> dproj
@@ -59,7 +62,7 @@ __device__ __forceinline__ void load_scale_v(const float* gmax, float& gs, float
 // D[D x 16] (+)= Act^T S : Act = [128 rows][D] activation tile read MN-major (M = feature), S = K-major [16][128 rows]
 template <int D>
 __device__ __forceinline__ void issue_colsum(uint32_t d_tmem, uint32_t act_addr, uint32_t one_addr, uint32_t ablk, uint32_t accumulate) {
-  constexpr uint32_t idesc = tc::make_idesc(D, 16, tc::kOperandFmt, 1, 0);
+  constexpr uint32_t idesc = tc::make_idesc(wgrad_m<D>(), 16, tc::kOperandFmt, 1, 0);
 #pragma unroll
   for (int kk = 0; kk < ROWS / 16; ++kk)
     tc::mma_f16(d_tmem, tc::desc_mnmajor(act_addr + kk * 2048, ablk), tc::desc_kmajor(one_addr + (kk >> 2) * 2048 + (kk & 3) * 32), idesc,
@@ -82,7 +85,7 @@ __device__ __forceinline__ void issue_du_v(uint32_t d_tmem, uint32_t a_addr, uin
 #endif
 
 template <int D>
-__global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(VCfg<D>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_v_kernel(EnfPairTcBwdParams P) {
   using C = VCfg<D>;
   constexpr int HD = C::HD;
   constexpr int MMA_TID = C::NT - 128;                // lane 0 of the first warp of the last column quarter
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
     for (int i = 0; i < 8; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 0) tc::tmem_alloc<512>(s_tmem);
+  if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
   for (int e = tid; e < D; e += C::NT) { s_bias[e] = P.v_b1[e]; s_bias[D + e] = P.bp[e]; }
   {
     uint4* z4 = reinterpret_cast<uint4*>(sOne);       // One, U, Om, OmT are contiguous
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
         tc::mbar_expect_tx(bar_t, C::ATILE);               // its own chunks from there and overwrites them in place
         tc::bulk_g2s(sDt, P.that_img + (size_t)(bz * ntiles + ct) * C::ATILE, C::ATILE, bar_t);
       }
-      if (cq == 1 && ct > 0) store_du(ct - 1, (it - 1) & 1);      // previous tile's du -> duv (the item's last tile: at its flush)
+      if (cq == C::kDuCq && ct > 0) store_du(ct - 1, (it - 1) & 1);      // previous tile's du -> duv (the item's last tile: at its flush)
       // ---- S1: gamma_v hi / lo ---------------------------------------------------------------------------------
       V_STAMP(1);
       tc::mbar_wait(bar_p, par);
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
       }
     }
     // ---- item flush: the last tile's du ----------------------------------------------------------------------------
-    if (cq == 1) store_du(ntiles - 1, (it - 1) & 1);
+    if (cq == C::kDuCq) store_du(ntiles - 1, (it - 1) & 1);
   }
   // ---- CTA flush: shared-weight gradients ------------------------------------------------------------------------------
   if (it > 0) {
@@ -440,9 +443,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
   __syncthreads();
   tc::tc_fence_after();
   if (it > 0) {
-    // accumulator row (input feature) of this thread: M = 128 keeps row r in TMEM lane r, M = 64 (d = 64) in lane
-    // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
-    const int wrow = D == 128 ? row : (lane < 16 ? 16 * lq + lane : -1);
+    const int wrow = wgrad_row<D>(row, lq, lane);      // accumulator row (input feature) of this thread
     float* dst[2] = {P.g_Wp, P.g_v_w1};
     const uint32_t src[2] = {tWp, tW1};
 #pragma unroll
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, 1) pairs_bwd_tc_v_kernel(EnfPairT
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<512>(tm);
+  if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tm);
 }
 
 template <int D>
@@ -476,7 +477,8 @@ int launch_v(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = VCfg<D>;
   if (cudaFuncSetAttribute(pairs_bwd_tc_v_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess) return -1;
   int nitems = p.B * p.Z;
-  int grid = nitems < 148 ? nitems : 148;
+  const int ctas = (D == 32 ? 2 : 1) * 148;                 // d = 32: two CTAs per SM (half of TMEM each)
+  int grid = nitems < ctas ? nitems : ctas;
   pairs_bwd_tc_v_kernel<D><<<grid, C::NT, C::SMEM_BYTES, st>>>(p);
   return 1;
 }
@@ -484,6 +486,7 @@ int launch_v(cudaStream_t st, const EnfPairTcBwdParams& p) {
 }  // namespace
 
 int enf_launch_pairs_bwd_tc_v(cudaStream_t st, int d, const EnfPairTcBwdParams& p) {
+  if (d == 32) return launch_v<32>(st, p);
   if (d == 128) return launch_v<128>(st, p);
   if (d == 64) return launch_v<64>(st, p);
   return -1;

@@ -12,6 +12,22 @@ namespace tcp {
 
 constexpr int ROWS = 128;
 
+// Operand geometry.  An operand row holds the features in 64-element (128-byte, swizzled) blocks.  num_hidden = 32 keeps
+// that row pitch and uses the first half of its single block (tests/test_gpu_tc_primitives.py pins that K-major reads with two
+// K-steps, MN-major reads with N = 32 and the M = 64 weight-gradient shape all work on such rows); whatever a kernel leaves in
+// the unused half only ever reaches accumulator rows / columns that are never read back.
+template <int D> __host__ __device__ constexpr int nblk() { return D >= 64 ? D / 64 : 1; }
+template <int D> __host__ __device__ constexpr uint32_t wimg_bytes() { return (uint32_t)nblk<D>() * D * 128; }      // weight image [nblk][D rows][128 B]
+template <int D> __host__ __device__ constexpr uint32_t atile_bytes() { return (uint32_t)nblk<D>() * ROWS * 128; }  // activation tile [nblk][128 rows][128 B]
+template <int D> __host__ __device__ constexpr int wgrad_m() { return D >= 64 ? D : 64; }                            // M of the weight-gradient MMAs
+// weight-gradient accumulator row (input feature) held by a thread's TMEM lane: M = 128 keeps row r in lane r, M = 64 in lane
+// 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py); -1: this lane holds no valid row
+template <int D> __device__ __forceinline__ int wgrad_row(int row, int lq, int lane) {
+  if (D == 128) return row;
+  const int r = lane < 16 ? 16 * lq + lane : -1;
+  return r < D ? r : -1;
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -422,7 +438,7 @@ __device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, uint32_t g_addr, ui
 // wgrad: dW[D x D] (+)= Act[128 x D]^T * G[128 x D]; both activation tiles read MN-major (rows = reduction index)
 template <int D>
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t act_addr, uint32_t g_addr, uint32_t ablk, uint32_t accumulate) {
-  constexpr uint32_t idesc = tc::make_idesc(D, D, tc::kOperandFmt, 1, 1);
+  constexpr uint32_t idesc = tc::make_idesc(wgrad_m<D>(), D, tc::kOperandFmt, 1, 1);
   const uint32_t a = tc::desc_lo_mn(act_addr, ablk), b = tc::desc_lo_mn(g_addr, ablk);
 #pragma unroll
   for (int kk = 0; kk < ROWS / 16; ++kk) tc::mma_f16_lo(d_tmem, a + kk * (2048 >> 4), b + kk * (2048 >> 4), idesc, (kk > 0) | accumulate);

@@ -12,8 +12,9 @@ __global__ void __launch_bounds__(256) weight_image_kernel(const float* __restri
                                                            float* __restrict__ cw, int N, int K, int residual) {
   const int64_t b = blockIdx.x;
   const float* src = Wt + b * (int64_t)N * K;
-  uint8_t* dst = img + b * (int64_t)N * K * 2;
-  const int cpr = K / 8;                       // 16-byte chunks per row (8 or 16: divides the warp)
+  // image bytes: [max(K / 64, 1)][N rows][128 B]; K = 32 keeps the 128-byte row pitch and fills half of it
+  uint8_t* dst = img + b * (int64_t)N * (K < 64 ? 64 : K) * 2;
+  const int cpr = K / 8;                       // 16-byte chunks per row (4, 8 or 16: divides the warp)
   for (int e = threadIdx.x; e < N * cpr; e += blockDim.x) {
     int n = e / cpr, ch = e % cpr;
     int k0 = ch * 8;
@@ -44,6 +45,9 @@ __global__ void __launch_bounds__(256) weight_image_T_kernel(const float* __rest
   extern __shared__ uint4 s_img[];
   const int64_t b = blockIdx.x;
   const float* src = W + b * (int64_t)N * K;
+  const int KP = K < 64 ? 64 : K;              // K = 32: rows keep the 128-byte pitch (half used; the rest is zeroed)
+  if (K < 64) for (int e = threadIdx.x; e < N * KP / 8; e += blockDim.x) s_img[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (K < 64) __syncthreads();
   const int cpr = K / 8;
   for (int e = threadIdx.x; e < N * cpr; e += blockDim.x) {
     const int n = e % N, k0 = (e / N) * 8;
@@ -55,8 +59,8 @@ __global__ void __launch_bounds__(256) weight_image_T_kernel(const float* __rest
     s_img[((size_t)(k0 >> 6) * N * 128 + tc::swz_chunk_off(n, (k0 & 63) >> 3)) >> 4] = q;
   }
   __syncthreads();
-  uint4* dst = reinterpret_cast<uint4*>(img + b * (int64_t)N * K * 2);
-  for (int e = threadIdx.x; e < N * K / 8; e += blockDim.x) dst[e] = s_img[e];
+  uint4* dst = reinterpret_cast<uint4*>(img + b * (int64_t)N * KP * 2);
+  for (int e = threadIdx.x; e < N * KP / 8; e += blockDim.x) dst[e] = s_img[e];
 }
 
 // ---- single-tile test GEMM: 128 rows, D features (D = 64 or 128) ---------------------------------------
@@ -225,7 +229,7 @@ int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* 
 }
 
 int enf_launch_weight_image_T(cudaStream_t st, const float* W, void* img, int N, int K, int batch) {
-  const size_t smem = (size_t)N * K * 2;
+  const size_t smem = (size_t)N * (K < 64 ? 64 : K) * 2;
   if (smem > 48 * 1024) return -1;
   weight_image_T_kernel<<<batch, 256, smem, st>>>(W, (uint8_t*)img, N, K);
   return 1;

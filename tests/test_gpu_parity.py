@@ -173,7 +173,7 @@ def test_error_paths():
 TOL_BF16 = TOL_TC     # BASELINE.json's bf16/tf32 bucket
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if c[1]["num_hidden"] in (64, 128)], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [c for c in CASES if c[1]["num_hidden"] in (64, 128) or c[0] == "ihc_d32_h3"], ids=lambda c: c[0])
 def test_tensor_core_path_against_oracle(case):
     """precision='bf16': tcgen05 pair kernels (fp16 operands, fp32 accumulate), forward AND backward at d in {64, 128}.
     Decoded field and latent gradients: 2e-3 (BASELINE.json's bf16/tf32 bucket); weight gradients: 2e-3 of the largest entry
@@ -187,6 +187,9 @@ def test_tensor_core_path_against_oracle(case):
     # d = 64 on these small problems: K = 64 dot products average less operand noise (dp of `ponita` reaches 3e-3 here); the
     # d = 64 BASELINE shape (plane64) is held to 2e-3 at full size in tests/test_gpu_real_shapes.py
     tol = TOL_TC if cfg.num_hidden == 128 else TOL_TC_SMALL
+    from enf_pde_b200 import _lib
+    from gpu_helpers import desc_for
+    assert _lib.dispatch(desc_for(cfg, B, C, Z, precision=1)) == (True, True)      # the tcgen05 kernels, not a fallback
     errs, worst, ok = compare(chk, out, dp, da, ds, gf, tol, TOL_TC_LEAF, use_window=cfg.use_gaussian_window)
     ok = ok and errs["out"] < TOL_TC
     errs["dtheta_global"] = worst_leaf(gf, R.tree_flatten(chk.ref[1]["params"]), floor=1.0)[0]
@@ -220,6 +223,9 @@ def test_tensor_core_multi_tile_against_oracle(case):
     # d = 64 on these small problems: K = 64 dot products average less operand noise (dp of `ponita` reaches 3e-3 here); the
     # d = 64 BASELINE shape (plane64) is held to 2e-3 at full size in tests/test_gpu_real_shapes.py
     tol = TOL_TC if cfg.num_hidden == 128 else TOL_TC_SMALL
+    from enf_pde_b200 import _lib
+    from gpu_helpers import desc_for
+    assert _lib.dispatch(desc_for(cfg, B, C, Z, precision=1)) == (True, True)      # the tcgen05 kernels, not a fallback
     errs, worst, ok = compare(chk, out, dp, da, ds, gf, tol, TOL_TC_LEAF, use_window=cfg.use_gaussian_window)
     ok = ok and errs["out"] < TOL_TC
     errs["dtheta_global"] = worst_leaf(gf, R.tree_flatten(chk.ref[1]["params"]), floor=1.0)[0]
