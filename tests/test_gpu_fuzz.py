@@ -38,7 +38,7 @@ def _draw32(seed):
     inv = rng.choice(["ball", "rel_pos_periodic", "ponita", "ball"])
     B = rng.randint(1, 3)
     C = rng.choice([1, 37, 128, 129, 300, 513])
-    Z = rng.choice([1, 5, 16, 40])
+    Z = rng.choice([1, 5, 16, 40]) if inv == "ball" else rng.choice([1, 4, 16, 36])
     kw = dict(num_in=3 if inv == "ball" else 2, num_hidden=32, num_heads=H, num_out=rng.choice([1, 2]), latent_dim=rng.choice([8, 32]),
               invariant_type=inv, embedding_freq_multiplier=(0.2, 0.5) if inv == "ball" else (0.05, 0.1))
     return kw, B, C, Z
