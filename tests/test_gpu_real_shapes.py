@@ -31,7 +31,7 @@ REAL = {
     "sw192": (dict(num_in=2, num_hidden=128, num_heads=2, num_out=3, latent_dim=32, invariant_type="latitude_periodic",
                    embedding_freq_multiplier=(0.05, 0.2)), 4, (192, 96), 144, (16, 9), 32, 2),
     "ihc": (dict(num_in=3, num_hidden=32, num_heads=3, num_out=1, latent_dim=32, invariant_type="ball",
-                 embedding_freq_multiplier=(0.2, 0.5)), 1, (64, 40, 40), 256, None, 48, 1),
+                 embedding_freq_multiplier=(0.2, 0.5)), 1, (64, 40, 40), 256, None, 256, 1),
 }
 
 
