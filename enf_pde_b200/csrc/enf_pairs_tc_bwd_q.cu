@@ -28,6 +28,10 @@ template <int D, int H> struct QCfg {
   static constexpr uint32_t WBLK = D * 128;
   static constexpr uint32_t ABLK = ROWS * 128;
   static constexpr uint32_t ATILE = atile_bytes<D>();
+  // d = 32 has ONE thread per query row, which would leave it all of the per-row side work (next tile's invariants AND both
+  // halves of the previous tile's window / invariant backward): four SIDE warps (column quarter NQ) take the row backward
+  static constexpr int NSIDE = D == 32 ? ROWS : 0;
+  static constexpr int NTALL = NT + NSIDE;
   static constexpr int TMEM_NEED = 2 * D + 64 + 48;           // T | dW1_q | phases (64) | db1q | dU | du (16 each)
   static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   static_assert(1 + 2 * H <= 8, "side operand row: [1 | ds_hi (H) | ds_lo (H)] in 8 halves");
@@ -81,14 +85,15 @@ __device__ __forceinline__ void issue_du(uint32_t d_tmem, uint32_t a_addr, uint3
 #endif
 
 template <int D, int H>
-__global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
+__global__ void __launch_bounds__(QCfg<D, H>::NTALL, D <= 64 ? 2 : 1) pairs_bwd_tc_q_kernel(EnfPairTcBwdParams P) {
   using C = QCfg<D, H>;
   constexpr int HD = C::HD;
   constexpr int MMA_TID = C::NT - 128;                // lane 0 of the first warp of the last column quarter
   // per-row side work by column quarter: 0 = next tile's invariants, kPart0 / kPart1 = the two halves of the previous
   // tile's window / invariant backward (at d = 64 a row has two threads: quarter 0 also takes the second half; at d = 32 it
   // has one, which takes everything)
-  constexpr int kPart0 = C::NQ > 1 ? 1 : 0, kPart1 = C::NQ > 2 ? 2 : 0;
+  constexpr bool kSide = C::NSIDE > 0;                // side warps: column quarter NQ does BOTH halves of the row backward
+  constexpr int kPart0 = (C::NQ > 1 || kSide) ? 1 : 0, kPart1 = C::NQ > 2 ? 2 : (kSide ? 1 : 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = base + C::OFF_W;
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = warp & 3, cq = warp >> 2;
   const int row = lq * 32 + lane, col0 = cq * 32;
+  const bool main_thr = cq < C::NQ;                   // owns 32 accumulator columns (false: a side warp, d = 32 only)
   const float scale = rsqrtf((float)D);
   // row (feature) of an M = D accumulator held by my TMEM lane: M = 128 keeps row r in lane r, M = 64 (d = 64) in lane
   // 32 (r / 16) + r % 16 (tests/test_gpu_tc_primitives.py)
@@ -124,10 +130,10 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
     tc::mbar_fence_init();
   }
   if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(s_tmem);
-  for (int e = tid; e < D; e += C::NT) s_b1q[e] = P.q_b1[e];
+  for (int e = tid; e < D; e += C::NTALL) s_b1q[e] = P.q_b1[e];
   {
     uint4* z4 = reinterpret_cast<uint4*>(sS);          // S, U, Om, OmT are contiguous
-    for (int e = tid; e < (int)(C::OFF_F - C::OFF_S) / 16; e += C::NT) z4[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < (int)(C::OFF_F - C::OFF_S) / 16; e += C::NTALL) z4[e] = make_uint4(0u, 0u, 0u, 0u);
   }
   float gs, inv_gs;
   load_scale_q(P.gmax, gs, inv_gs);
@@ -147,8 +153,8 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
                  aDz = tc::smem_u32(sDz), aS = tc::smem_u32(sS), aU = tc::smem_u32(sU), aOm = tc::smem_u32(sOm),
                  aOmT = tc::smem_u32(sOmT);
   // Omega images: projection operand (phases) and its transpose for du, both as a two-term fp16 split of 2 pi Omega
-  proj_build_omega(sOm, 0, P.q_omega, P.I, HD, tid, C::NT);
-  for (int e = tid; e < P.I * HD; e += C::NT) {
+  proj_build_omega(sOm, 0, P.q_omega, P.I, HD, tid, C::NTALL);
+  for (int e = tid; e < P.I * HD; e += C::NTALL) {
     const int i = e / HD, j = e % HD;
     const float val = 6.283185307179586f * P.q_omega[e];
     const __half hi = __float2half_rn(val);
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
     if (tid < ENF_LAM_SIZE) s_lam[tid] = P.lam[bz * ENF_LAM_SIZE + tid];
     if (tid < 64) s_dlam[tid] = 0.f;
     if (tid < 8) s_dkap[tid] = 0.f;
-    for (int e = tid; e < H * D; e += C::NT) s_us[e] = scale * P.U[bz * H * D + e];
+    for (int e = tid; e < H * D; e += C::NTALL) s_us[e] = scale * P.U[bz * H * D + e];
     const float sigma = P.sigma ? P.sigma[bz] : 1.f;
     __syncthreads();
 
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
     }
     float dsv_next[H];                                  // logit cotangents of the tile about to start (fetched a tile ahead)
 #pragma unroll
-    for (int h = 0; h < H; ++h) dsv_next[h] = row < P.C ? __ldg(P.ds + (bz * P.C + row) * H + h) : 0.f;
+    for (int h = 0; h < H; ++h) dsv_next[h] = (main_thr && row < P.C) ? __ldg(P.ds + (bz * P.C + row) * H + h) : 0.f;
     tc::fence_proxy_async();
     __syncthreads();
     if (warp == (MMA_TID >> 5)) {
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
       tc::mbar_wait(bar_p, par);
       tc::tc_fence_after();
       Q_STAMP(32, 2); Q_STAMP(160, 2);
-      rff_from_proj<D, true>(tP + lane_off + 16 * cq, sGhi, sGlo, C::ABLK, row, 16 * cq);
+      if (main_thr) rff_from_proj<D, true>(tP + lane_off + 16 * cq, sGhi, sGlo, C::ABLK, row, 16 * cq);
       Q_STAMP(32, 3); Q_STAMP(160, 3);
       tc::tc_fence_before();
       tc::fence_proxy_async();
@@ -340,16 +346,19 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
         for (int h = 0; h < H; ++h) { kap_acc[h] += dsv[h]; dw += dsv[h]; }
         s_rx[(((it0 + ct) % 3) * ROWS + row) * C::RX + 16] = dw;
         if (ct + 1 < ntiles) write_invariants(ct + 1, pre8);
-        if (kPart1 == 0 && ct > 0) {                       // d <= 64: this thread also owns the second half of the row backward
+        if (kPart1 == 0 && !kSide && ct > 0) {             // d = 64: this thread also owns the second half of the row backward
           float duv[8];                                    //          (d = 32: both halves)
           load_duv(ct - 1, duv);
           if (kPart0 == 0) row_backward(ct - 1, (it - 1) & 1, 0, duv);
           row_backward(ct - 1, (it - 1) & 1, 1, duv);
         }
+      } else if (kSide) {
+        if (ct > 0) { row_backward(ct - 1, (it - 1) & 1, 0, pre8); row_backward(ct - 1, (it - 1) & 1, 1, pre8); }
       } else if ((cq == kPart0 || cq == kPart1) && ct > 0) {
         row_backward(ct - 1, (it - 1) & 1, cq == kPart0 ? 0 : 1, pre8);
       }
       // ---- E: h1q, dzq ---------------------------------------------------------------------------------------------
+      if (main_thr) {
       float v[32];
       Q_STAMP(32, 5); Q_STAMP(160, 5);
       tc::mbar_wait(bar_g1, par);
@@ -385,6 +394,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
 #pragma unroll
         for (int h = 0; h < H; ++h) dsv_next[h] = (c0 + ROWS + row < P.C) ? __ldg(P.ds + (pr + ROWS) * H + h) : 0.f;
       }
+      }   // main_thr
       tc::tc_fence_before();
       tc::fence_proxy_async();
       __syncthreads();
@@ -405,6 +415,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
         __syncwarp();
       }
       // ---- S3: d gamma_q -> dproj (my 16 frequencies: sin columns j, cos columns HD + j) ---------------------------
+      if (main_thr) {
       tc::mbar_wait(bar_d, par);
       tc::tc_fence_after();
       Q_STAMP(32, 9); Q_STAMP(160, 9);
@@ -429,6 +440,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
           tc::st_row8_bf16(sGlo, C::ABLK, row, col, o);             // h1q's MMA was issued before the dgrad: it is complete
         }
       }
+      }   // main_thr
       Q_STAMP(32, 10); Q_STAMP(160, 10);
       tc::tc_fence_before();
       tc::fence_proxy_async();
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_
   // ---- CTA flush: shared-weight gradients --------------------------------------------------------------------------------
   __syncthreads();
   tc::tc_fence_after();
-  if (it > 0) {
+  if (it > 0 && main_thr) {
     float v[32];
     tc::tmem_ld32(tW + my_t, v);
     tc::tmem_ld_wait();
@@ -509,9 +521,13 @@ int launch_q(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = QCfg<D, H>;
   if (cudaFuncSetAttribute(pairs_bwd_tc_q_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess) return -1;
   int nitems = p.B * p.Z;
-  const int ctas = (D == 32 ? 2 : 1) * 148;                 // d = 32: two CTAs per SM (half of TMEM each)
+  int occ = 1;                                              // persistent CTAs: as many as are resident at once
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairs_bwd_tc_q_kernel<D, H>, C::NTALL, C::SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+  int nsm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+  const int ctas = occ * nsm;
   int grid = nitems < ctas ? nitems : ctas;
-  pairs_bwd_tc_q_kernel<D, H><<<grid, C::NT, C::SMEM_BYTES, st>>>(p);
+  pairs_bwd_tc_q_kernel<D, H><<<grid, C::NTALL, C::SMEM_BYTES, st>>>(p);
   return 1;
 }
 

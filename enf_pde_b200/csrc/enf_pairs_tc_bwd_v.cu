@@ -477,7 +477,11 @@ int launch_v(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = VCfg<D>;
   if (cudaFuncSetAttribute(pairs_bwd_tc_v_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess) return -1;
   int nitems = p.B * p.Z;
-  const int ctas = (D == 32 ? 2 : 1) * 148;                 // d = 32: two CTAs per SM (half of TMEM each)
+  int occ = 1;                                              // persistent CTAs: as many as are resident at once
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairs_bwd_tc_v_kernel<D>, C::NT, C::SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+  int nsm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+  const int ctas = occ * nsm;
   int grid = nitems < ctas ? nitems : ctas;
   pairs_bwd_tc_v_kernel<D><<<grid, C::NT, C::SMEM_BYTES, st>>>(p);
   return 1;
