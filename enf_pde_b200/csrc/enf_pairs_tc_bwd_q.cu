@@ -402,9 +402,11 @@ __global__ void __launch_bounds__(QCfg<D, H>::NTALL, D <= 64 ? 2 : 1) pairs_bwd_
       if (warp == (MMA_TID >> 5)) {
         if (tc::elect_one()) {
           tc::tc_fence_after();
-          issue_dgrad<D>(tT, aDz, aW, C::ABLK, C::WBLK, 0);          // d gamma_q (first: S3 waits for it)
-          tc::mma_commit(bar_d);
+          // dU first: it is the only MMA that reads the h1q tile, which S3 overwrites with dproj as soon as bar_d fires (MMAs
+          // complete in issue order, so the dgrad's commit covers it; eight N = 16 MMAs: nothing next to the dgrad)
           issue_rowsum<D>(tS2, aGlo, aS, C::ABLK, ct > 0);           // dU (per item)
+          issue_dgrad<D>(tT, aDz, aW, C::ABLK, C::WBLK, 0);          // d gamma_q (S3 waits for it)
+          tc::mma_commit(bar_d);
           issue_wgrad<D>(tW, aGhi, aDz, C::ABLK, it > 0);            // dW1_q (per CTA)
           issue_rowsum<D>(tS1, aDz, aS, C::ABLK, it > 0);            // db1q (per CTA)
           if (ct + 1 < ntiles) {
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NTALL, D <= 64 ? 2 : 1) pairs_bwd_
             const float2 nsn = __half22float2(__hneg2(hs[t])), cs = __half22float2(hc[t]);       // d sin = cos, d cos = -sin
             tc::st2(o + 2 * t, tc::fma2(nsn, tc::ld2(dcs + c8 + 2 * t), tc::mul2(cs, tc::ld2(dsn + c8 + 2 * t))));
           }
-          tc::st_row8_bf16(sGlo, C::ABLK, row, col, o);             // h1q's MMA was issued before the dgrad: it is complete
+          tc::st_row8_bf16(sGlo, C::ABLK, row, col, o);             // h1q's only reader (dU) was issued before the dgrad: it is complete
         }
       }
       }   // main_thr
