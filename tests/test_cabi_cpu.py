@@ -60,7 +60,8 @@ def test_limits_and_dispatch_are_reported():
     ok = dict(B=32, C=4096, Z=64, d=128, H=2, L=16, O=1, Dx=2, invariant_kind=3, use_window=1, precision=1, flags=0)
     assert _lib.dispatch(_lib.EnfDesc(**ok)) == (True, True)
     assert _lib.dispatch(_lib.EnfDesc(**{**ok, "precision": 0})) == (False, False)
-    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "d": 32, "H": 3})) == (False, False)          # fp32 kernels in either mode
+    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "d": 32, "H": 3})) == (True, True)            # config 5 (ihc): tcgen05 kernels
+    assert _lib.dispatch(_lib.EnfDesc(**{**ok, "d": 16, "H": 2})) == (False, False)          # d = 16: fp32 kernels in either mode
     assert _lib.dispatch(_lib.EnfDesc(**{**ok, "flags": _lib.FLAG_FORWARD_ONLY})) == (True, False)
     big = _lib.EnfDesc(**{**ok, "B": 512})                                                      # 512 * 64 * 2 = 65536
     assert lib.enf_xattn_workspace_bytes(ctypes.byref(big)) == 0 and b"65535" in lib.enf_last_error()
