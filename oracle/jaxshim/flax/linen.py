@@ -13,7 +13,7 @@ import dataclasses
 import math
 import numpy as np
 
-from jax.nn import relu  # noqa: F401  (nn.relu)
+from jax.nn import relu, gelu  # noqa: F401  (nn.relu, nn.gelu: flax re-exports jax.nn's, approximate=True default)
 from jax import random as _random
 
 _STACK = []          # modules whose __call__ is executing (innermost last)

@@ -218,3 +218,24 @@ def make_case(cfg, B, C, Z, seed=0, dtype=torch.float64, polar_grid=None, pertur
     params = R.tree_map(r32, params)
     x, p, a, sigma, d_out = (r32(t) for t in (x, p, a, sigma, d_out))
     return params, x, p, a, sigma, d_out
+
+
+# ---- latent ODE model: fixtures written by tests/golden/make_golden_ode.py ------------------------------------
+def ode_golden_names():
+    return sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "ode_*.npz")))
+
+
+def load_ode_golden(name, dtype=torch.float64):
+    from oracle import ode_ref as O
+    z = np.load(os.path.join(GOLDEN_DIR, f"ode_{name}.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    cfg = O.OdeConfig(invariant_type=meta["invariant_type"], num_in=meta["num_in"], num_hidden=meta["hidden"],
+                      num_layers=meta["layers"], latent_dim=meta["L"], basis_dim=meta["basis"], degree=meta["degree"],
+                      widening_factor=meta["widen"])
+    t = lambda k: torch.tensor(z[k], dtype=dtype)
+    params = R.tree_unflatten({k[6:]: t(k) for k in z.files if k.startswith("param:")})
+    direction = R.tree_unflatten({k[4:]: t(k) for k in z.files if k.startswith("dir:")})
+    rec = {k: t(k) for k in z.files if not k.startswith(("param:", "dir:")) and k not in ("meta", "dtheta_dir", "h")}
+    rec["dtheta_dir"] = float(z["dtheta_dir"])
+    rec["h"] = float(z["h"])
+    return cfg, params, direction, rec
