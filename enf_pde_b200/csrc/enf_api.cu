@@ -357,6 +357,10 @@ int enf_profile_collect(int which, float* ms_out, int max_out) {
 }
 
 int enf_last_launch_count(void) { return g_launches; }
+}  // extern "C"
+// shared by the other translation units behind the same ABI (enf_ode.cu): thread-local message of enf_last_error()
+int enf_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+extern "C" {
 
 int enf_debug_gemm(int use_tc, int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
                    int64_t b_cs, const float* B_lo, float* C, int64_t c_rs, const float* bias, const float* aux, float* gelu_out,

@@ -126,6 +126,11 @@ int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const
 int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi);
 int enf_launch_latent_record(cudaStream_t st, const EnfDesc& d, const float* p, float* lam);
 int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float* p, const float* dlam, float* dp);
+// poses used as queries (latent ODE model: invariant(p, p)); self-attention variants of the invariants (ENF_INV_PONITA = Ponita2D, I = 3)
+int enf_launch_pose_features(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, float* xi);
+int enf_launch_pose_features_bwd(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, const float* dxi, float* dp);   // dp +=
+int enf_launch_pose_record(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, float* lam);
+int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, const float* dlam, float* dp);   // dp =
 int enf_launch_weff(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
                     float* Weff, float* beff, int round_weff = 0);
 int enf_launch_weff_bwd(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,

@@ -477,8 +477,9 @@ int launch_v(cudaStream_t st, const EnfPairTcBwdParams& p) {
   using C = VCfg<D>;
   if (cudaFuncSetAttribute(pairs_bwd_tc_v_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess) return -1;
   int nitems = p.B * p.Z;
-  int occ = 1;                                              // persistent CTAs: as many as are resident at once
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairs_bwd_tc_v_kernel<D>, C::NT, C::SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+  // persistent CTAs: as many as are resident at once.  TMEM (not visible to the occupancy API, which also under-reports
+  // kernels with > 48 KB of dynamic shared memory: it answered 1 for d = 32 and halved the grid) allows 512 / TMEM_COLS
+  const int occ = D == 32 ? 512 / C::TMEM_COLS : 1;
   int nsm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
   const int ctas = occ * nsm;

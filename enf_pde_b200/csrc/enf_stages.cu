@@ -22,12 +22,15 @@ __device__ __forceinline__ void sph_unit_grad(float phi, float th, float* dphi, 
 }
 
 // ---- X: per-query feature record xi (one record serves every latent) ----------------
+// `xrs`: floats between consecutive rows of x (Dx for coordinate grids; the raw pose width when the "queries" are the latent
+// poses themselves: latent ODE model / self-attention).  `sa`: self-attention variant of the invariant (get_sa_invariant:
+// only `ponita` differs, Ponita2D reads the query's orientation angle xr[2] too).
 __global__ void query_features_kernel(int kind, int Dx, int C, int64_t total, const float* __restrict__ x,
-                                      int64_t xbs, float* __restrict__ xi) {
+                                      int64_t xbs, float* __restrict__ xi, int xrs, int sa) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   int64_t b = t / C, c = t % C;
-  const float* xr = x + b * xbs + c * Dx;
+  const float* xr = x + b * xbs + c * xrs;
   float o[ENF_F_XI];
 #pragma unroll
   for (int f = 0; f < ENF_F_XI; ++f) o[f] = 0.f;
@@ -42,6 +45,7 @@ __global__ void query_features_kernel(int kind, int Dx, int C, int64_t total, co
       break;
     case ENF_INV_PONITA:
       o[0] = xr[0]; o[1] = xr[1]; o[2] = 1.f;
+      if (sa) sincosf(xr[2], &o[4], &o[3]);         // Ponita2D (ponita.py:84): x_ori . p_ori
       break;
     case ENF_INV_POLAR_PERIODIC:
       sph_unit(xr[0], xr[1], o);
@@ -65,7 +69,7 @@ __global__ void query_features_kernel(int kind, int Dx, int C, int64_t total, co
 
 // ---- L: per-latent pose record Lam (raw poses; the ponita cos/sin embed of nef.py:214-217 is folded in)
 __global__ void latent_record_kernel(int kind, int Dx, int P, int I, int64_t total, const float* __restrict__ p,
-                                     float* __restrict__ lam) {
+                                     float* __restrict__ lam, int sa) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const float* pr = p + t * P;
@@ -96,7 +100,8 @@ __global__ void latent_record_kernel(int kind, int Dx, int P, int I, int64_t tot
       float o0, o1; sincosf(pr[2], &o1, &o0);
       L[0][0] = o0; L[0][1] = o1; L[0][2] = -(pr[0] * o0 + pr[1] * o1);
       L[1][0] = -o1; L[1][1] = o0; L[1][2] = pr[0] * o1 - pr[1] * o0;
-      L[W][0] = pr[0]; L[W][1] = pr[1];
+      if (sa) { L[2][3] = o0; L[2][4] = o1; }        // Ponita2D's third invariant (no window row: I = 3 fills the slot)
+      else { L[W][0] = pr[0]; L[W][1] = pr[1]; }
     } break;
     case ENF_INV_POLAR_PERIODIC:
       sph_unit(pr[0], pr[1], L[0]);
@@ -131,7 +136,7 @@ __global__ void latent_record_kernel(int kind, int Dx, int P, int I, int64_t tot
 // acc[r][f] = sum over queries of dq_r * xi_f (what the pair backward accumulates) -> d(raw pose)
 __global__ void latent_record_bwd_kernel(int kind, int Dx, int P, int I, int win_kind, int64_t total,
                                          const float* __restrict__ p, const float* __restrict__ acc_all,
-                                         float* __restrict__ dp) {
+                                         float* __restrict__ dp, int sa) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const float* pr = p + t * P;
@@ -170,6 +175,7 @@ __global__ void latent_record_bwd_kernel(int kind, int Dx, int P, int I, int win
       g[1] = -a02 * o1 - a12 * o0;
       float do0 = a00 - a02 * pr[0] + a11 - a12 * pr[1];
       float do1 = a01 - a02 * pr[1] - a10 + a12 * pr[0];
+      if (sa) { do0 += ACC(2, 3); do1 += ACC(2, 4); }
       g[2] = -o1 * do0 + o0 * do1;
       if (np) {
         g[0] += 2.f * (pr[0] * ACC(W, 2) - ACC(W, 0));
@@ -215,6 +221,49 @@ __global__ void latent_record_bwd_kernel(int kind, int Dx, int P, int I, int win
   }
 #undef ACC
   for (int i = 0; i < P; ++i) dp[t * P + i] = g[i];
+}
+
+// d(xi record) -> d(raw pose) ACCUMULATED into dp, for poses used as queries (self-attention variant; rows of width P)
+__global__ void query_features_bwd_kernel(int kind, int Dx, int P, int64_t total, const float* __restrict__ p,
+                                          const float* __restrict__ dxi, float* __restrict__ dp) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const float* xr = p + t * P;
+  const float* d = dxi + t * ENF_F_XI;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  switch (kind) {
+    case ENF_INV_REL_POS: case ENF_INV_NORM_REL_POS: case ENF_INV_ABS_POS:
+      for (int i = 0; i < Dx; ++i) g[i] = d[i];
+      break;
+    case ENF_INV_REL_POS_PERIODIC:
+      for (int i = 0; i < 2; ++i) {
+        float s, c; sincospif(xr[i], &s, &c);
+        g[i] = 3.14159265358979323846f * (-s * d[2 * i] + c * d[2 * i + 1]);
+      }
+      break;
+    case ENF_INV_PONITA: {
+      float s, c; sincosf(xr[2], &s, &c);
+      g[0] = d[0]; g[1] = d[1]; g[2] = -s * d[3] + c * d[4];
+    } break;
+    case ENF_INV_POLAR_PERIODIC: {
+      float dphi[3], dth[3]; sph_unit_grad(xr[0], xr[1], dphi, dth);
+      for (int j = 0; j < 3; ++j) { g[0] += d[j] * dphi[j]; g[1] += d[j] * dth[j]; }
+    } break;
+    case ENF_INV_LATITUDE_PERIODIC: case ENF_INV_BALL_LAT: {
+      float s, c; sincosf(xr[0], &s, &c);
+      float dphi[3], dth[3]; sph_unit_grad(xr[0], xr[1], dphi, dth);
+      g[1] = d[0];
+      g[0] = -s * d[1] + c * d[2];
+      for (int j = 0; j < 3; ++j) { g[0] += d[4 + j] * dphi[j]; g[1] += d[4 + j] * dth[j]; }
+      if (kind == ENF_INV_BALL_LAT) g[2] = d[7];
+    } break;
+    case ENF_INV_BALL: {
+      float dphi[3], dth[3]; sph_unit_grad(xr[0], xr[1], dphi, dth);
+      for (int j = 0; j < 3; ++j) { g[0] += d[j] * dphi[j]; g[1] += d[j] * dth[j]; }
+      g[2] = d[3];
+    } break;
+  }
+  for (int i = 0; i < P; ++i) dp[t * P + i] += g[i];
 }
 
 // ---- LayerNorm rows (flax: eps 1e-6, var = E[x^2]-E[x]^2), optional gelu on the input --------------
@@ -660,14 +709,33 @@ int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const
 
 int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi) {
   int64_t total = (int64_t)Bx * d.C;
-  query_features_kernel<<<blocks_for(total, 256), 256, 0, st>>>(d.invariant_kind, d.Dx, d.C, total, x, xbs, xi);
+  query_features_kernel<<<blocks_for(total, 256), 256, 0, st>>>(d.invariant_kind, d.Dx, d.C, total, x, xbs, xi, d.Dx, 0);
+  return 1;
+}
+
+// the "queries" are the latent poses themselves (latent ODE model, ponita_ode_g.py:154 `self.invariant(p, p)`): rows of raw
+// poses [total][P] -> xi records; self-attention variant of the invariant
+int enf_launch_pose_features(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, float* xi) {
+  query_features_kernel<<<blocks_for(total, 256), 256, 0, st>>>(kind, Dx, 1, total, p, (int64_t)P, xi, P, 1);
+  return 1;
+}
+int enf_launch_pose_features_bwd(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, const float* dxi, float* dp) {
+  query_features_bwd_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, total, p, dxi, dp);
+  return 1;
+}
+int enf_launch_pose_record(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, float* lam) {
+  latent_record_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, I, total, p, lam, 1);
+  return 1;
+}
+int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, const float* dlam, float* dp) {
+  latent_record_bwd_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, I, ENF_WIN_NONE, total, p, dlam, dp, 1);
   return 1;
 }
 
 int enf_launch_latent_record(cudaStream_t st, const EnfDesc& d, const float* p, float* lam) {
   EnfRecordLayout r = enf_record_layout(d.invariant_kind, d.Dx, d.use_window);
   int64_t total = (int64_t)d.B * d.Z;
-  latent_record_kernel<<<blocks_for(total, 128), 128, 0, st>>>(d.invariant_kind, d.Dx, r.P, r.I, total, p, lam);
+  latent_record_kernel<<<blocks_for(total, 128), 128, 0, st>>>(d.invariant_kind, d.Dx, r.P, r.I, total, p, lam, 0);
   return 1;
 }
 
@@ -675,7 +743,7 @@ int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float*
   EnfRecordLayout r = enf_record_layout(d.invariant_kind, d.Dx, d.use_window);
   int64_t total = (int64_t)d.B * d.Z;
   latent_record_bwd_kernel<<<blocks_for(total, 128), 128, 0, st>>>(d.invariant_kind, d.Dx, r.P, r.I, r.win_kind, total,
-                                                                   p, dlam, dp);
+                                                                   p, dlam, dp, 0);
   return 1;
 }
 

@@ -46,6 +46,10 @@ def PonitaPos2D():                           # ponita.py:6-18
     return BaseInvariant("ponita", 2, 2, 0, 2, 1)
 
 
+def Ponita2D():                              # ponita.py:46-61 (self-attention variant: the queries carry an orientation too)
+    return BaseInvariant("ponita", 3, 2, 1, 2, 1)
+
+
 def RelativePositionPolarPeriodic():         # polar_periodic.py:6-33
     return BaseInvariant("polar_periodic", 1, 2, 0, 2, 0, True)
 
@@ -86,3 +90,11 @@ def get_ca_invariant(cfg) -> BaseInvariant:
     if t == "ball_lat":
         return BallLatInvariant()
     raise ValueError(f"Unknown invariant type: {t}.")
+
+
+def get_sa_invariant(cfg) -> BaseInvariant:
+    """enf/steerable_attention/invariant/__init__.py:13-45: the self-attention variants (only `ponita` differs: Ponita2D)."""
+    if cfg.invariant_type == "ponita":
+        assert cfg.num_in == 2, "Ponita2D currently only supports 2D input."
+        return Ponita2D()
+    return get_ca_invariant(cfg)

@@ -166,3 +166,49 @@ def test_init_tree_matches_reference_names_and_shapes():
     leaves = E.params_to_leaves({"params": R.tree_unflatten(ours)})
     back = R.tree_flatten(E.leaves_to_params(leaves)["params"])
     assert all(back[k] is ours[k] for k in ours)
+
+
+def test_ode_abi_exports_and_layouts():
+    """include/enf_ode_b200.h (latent ODE model): every declared entry point is exported, the ctypes mirrors have the
+    header's layout, bad descriptions are rejected without a GPU."""
+    from enf_pde_b200 import ode
+    lib = ode._load()
+    header = open(os.path.join(ROOT, "include", "enf_ode_b200.h")).read()
+    declared = set(re.findall(r"\b(enf_ode_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(ode.EXPORTS), declared ^ set(ode.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    body = re.sub(r"/\*.*?\*/", "", header.split("typedef struct EnfOdeLayer {")[1].split("} EnfOdeLayer;")[0], flags=re.S)
+    assert tuple(re.findall(r"\*\s*([a-z0-9_]+)", body)) == ode._LAYER_LEAVES
+    assert int(re.search(r"#define ENF_ODE_MAX_LAYERS (\d+)", header).group(1)) == ode.MAX_LAYERS
+    assert ctypes.sizeof(ode.EnfOdeDesc) == 64 and ctypes.sizeof(ode.EnfOdeLayer) == 64
+    assert ctypes.sizeof(ode.EnfOdeWeights) == 8 * (5 + 8 * ode.MAX_LAYERS + 3)
+    ok = dict(B=2, Z=8, L=16, hidden=128, basis=64, layers=3, widen=2, degree=3, Dx=2, invariant_kind=3)
+    assert lib.enf_ode_workspace_bytes(ctypes.byref(ode.EnfOdeDesc(**ok))) > 0
+    for bad in (dict(layers=0), dict(layers=9), dict(degree=6), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(hidden=0)):
+        assert lib.enf_ode_workspace_bytes(ctypes.byref(ode.EnfOdeDesc(**{**ok, **bad}))) == 0, bad
+        assert lib.enf_last_error()
+    # compute entry points refuse NULL arguments before touching the device
+    d = ode.EnfOdeDesc(**ok)
+    assert lib.enf_ode_fwd(ctypes.byref(d), None, None, None, None, None, None, 0, None) == -3
+
+
+def test_ode_host_mirror_matches_reference_structure():
+    """PonitaODEGen.init builds the reference's parameter tree (names / shapes from tests/golden/ode_ponita.npz, written by the
+    reference's own module); get_sa_invariant mirrors invariant/__init__.py:13-45."""
+    import types
+    from helpers import load_ode_golden
+    from oracle import enf_ref as R
+    cfg, params, _, rec = load_ode_golden("ponita")
+    inv = E.get_sa_invariant(types.SimpleNamespace(invariant_type="ponita", num_in=2))
+    assert (inv.dim, inv.num_x_ori_dims, inv.pose_dim) == (3, 1, 3)
+    assert E.get_sa_invariant(types.SimpleNamespace(invariant_type="rel_pos_periodic", num_in=2)).dim == 4
+    m = E.PonitaODEGen(cfg.num_hidden, cfg.num_layers, cfg.latent_dim, 1, inv, cfg.basis_dim, cfg.degree, cfg.widening_factor)
+    ours = R.tree_flatten(m.init(0, (rec["p"], rec["a"], rec["sigma"]), device="cpu")["params"])
+    theirs = R.tree_flatten(params)
+    assert sorted(ours) == sorted(theirs)
+    for k in ours:
+        assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
+    assert float(ours["ponita/readout_vec_rel/kernel"].abs().max()) < 1e-2        # variance_scaling(1e-6)
+    with pytest.raises(NotImplementedError):
+        E.PonitaODEGen(16, 2, 4, 1, inv, 8, 3, 2, kernel_size=0.5)

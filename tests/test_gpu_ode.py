@@ -1,0 +1,159 @@
+"""Latent ODE model + solver on the GPU through the C ABI (include/enf_ode_b200.h) against the fixtures produced by
+the reference's own source (tests/golden/ode_*.npz) and against the oracle (oracle/ode_ref.py) at the Navier-Stokes config's real
+shape.  fp32 arithmetic: the <= 1e-4 bucket of north_star (max-norm relative, helpers.rel_err), measured ~1e-6.  `-m gpu`."""
+import types
+
+import pytest
+import torch
+
+from oracle import enf_ref as R
+from oracle import ode_ref as O
+from helpers import load_ode_golden, ode_golden_names, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # fp32 bucket
+TOL_LEAF = 2e-4     # per weight-gradient leaf (sums over B*Z*Z pair rows in fp32, atomics)
+
+
+def _model(cfg):
+    import enf_pde_b200 as E
+    inv = E.get_sa_invariant(types.SimpleNamespace(invariant_type=cfg.invariant_type, num_in=cfg.num_in))
+    return E.PonitaODEGen(cfg.num_hidden, cfg.num_layers, cfg.latent_dim, 1, inv, cfg.basis_dim, cfg.degree, cfg.widening_factor,
+                          global_pool=False, kernel_size="global")
+
+
+def _cuda(params):
+    return R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous().requires_grad_(True), params)
+
+
+f32 = lambda t: t.to("cuda", torch.float32)
+
+
+def _oracle_grads(cfg, params, p, a, cot_p, cot_a):
+    P = R.tree_map(lambda t: t.clone().requires_grad_(True), params)
+    pp, aa = p.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    dp, da = O.ponita_ode(cfg, P, pp, aa)
+    ((dp * cot_p).sum() + (da * cot_a).sum()).backward()
+    return dp.detach(), da.detach(), pp.grad, aa.grad, {k: v.grad for k, v in R.tree_flatten(P).items()}
+
+
+def _check(cfg, params, p, a, cot_p, cot_a, want=None):
+    dp_o, da_o, gp_o, ga_o, gth_o = _oracle_grads(cfg, params, p, a, cot_p, cot_a)
+    model = _model(cfg)
+    P = _cuda({"params": params})
+    pg, ag = f32(p).requires_grad_(True), f32(a).requires_grad_(True)
+    dp, da, dw = model.apply(P, (pg, ag, torch.ones(p.shape[0], p.shape[1], 1, device="cuda")))
+    assert dw.shape == (p.shape[0], p.shape[1], 1) and float(dw.abs().max()) == 0.0
+    ((dp * f32(cot_p)).sum() + (da * f32(cot_a)).sum()).backward()
+    errs = dict(dp=rel_err(dp.detach(), dp_o), da=rel_err(da.detach(), da_o), gp=rel_err(pg.grad, gp_o), ga=rel_err(ag.grad, ga_o))
+    if want is not None:        # the reference's own outputs
+        errs["dp_ref"], errs["da_ref"] = rel_err(dp.detach(), want["dp"]), rel_err(da.detach(), want["da"])
+    leaves = R.tree_flatten(P["params"])
+    scale = max(float(g.abs().max()) for g in gth_o.values())
+    leaf_errs = {}
+    for k, g in gth_o.items():
+        got = leaves[k].grad
+        assert got is not None, k
+        # per leaf, with a floor at 1e-3 of the largest leaf (a leaf whose gradient is ~0 is compared absolutely)
+        leaf_errs[k] = float((got.double().cpu() - g).abs().max()) / max(float(g.abs().max()), 1e-3 * scale)
+    worst = max(leaf_errs, key=leaf_errs.get)
+    print(cfg.invariant_type, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf", worst, f"{leaf_errs[worst]:.2e}")
+    assert all(v < TOL for v in errs.values()), errs
+    assert leaf_errs[worst] < TOL_LEAF, (worst, leaf_errs[worst])
+
+
+@pytest.mark.parametrize("name", ode_golden_names())
+def test_ode_fwd_bwd_against_reference_fixtures(name):
+    cfg, params, _, rec = load_ode_golden(name)
+    _check(cfg, params, rec["p"], rec["a"], rec["cot_p"], rec["cot_a"], want=rec)
+
+
+def _ns_case(B=4, Z=64, seed=0):
+    """config_navier_stokes.yaml `node:` block at its real sizes (hidden 128, 3 layers, basis 64, degree 3, widening 2), 64 latents."""
+    cfg = O.OdeConfig(invariant_type="rel_pos_periodic", num_in=2, num_hidden=128, num_layers=3, latent_dim=16, basis_dim=64, degree=3,
+                      widening_factor=2)
+    params = O.ode_init(cfg, seed=seed, readout_scale=1e6)
+    g = torch.Generator().manual_seed(seed)
+    p = torch.as_tensor(R.init_positions_grid(B, Z, 2), dtype=torch.float64) + 0.02 * torch.randn(B, Z, 2, generator=g, dtype=torch.float64)
+    a = 1.0 + 0.3 * torch.randn(B, Z, 16, generator=g, dtype=torch.float64)
+    for k, v in R.tree_flatten(params).items():
+        if k.endswith("bias") or k.endswith("scale"):
+            v += 0.1 * torch.randn(v.shape, generator=g, dtype=torch.float64)
+    return cfg, params, p, a, g
+
+
+def test_ode_real_shape_navier_stokes():
+    cfg, params, p, a, g = _ns_case()
+    cot_p = torch.randn(p.shape, generator=g, dtype=torch.float64)
+    cot_a = torch.randn(a.shape, generator=g, dtype=torch.float64)
+    _check(cfg, params, p, a, cot_p, cot_a)
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_fused_rollout_matches_oracle_solver(method):
+    """enf_ode_solve (forward-only roll-out in the library) vs solvers.py's loop restated in the oracle; also against the
+    reference's own single step (fixtures)."""
+    for name in ("ponita", "rel_pos_periodic", "latitude_periodic"):
+        cfg, params, _, rec = load_ode_golden(name)
+        model = _model(cfg)
+        P = _cuda({"params": params})
+        h, T = rec["h"], 3
+        pt, at, st = model.solve(P, (f32(rec["p"]), f32(rec["a"]), f32(rec["sigma"])), 0.0, T * h, h, method)
+        po, ao, so = O.solve_latent_ode(cfg, params, (rec["p"], rec["a"], rec["sigma"]), 0.0, T * h, h, method)
+        assert pt.shape == po.shape and at.shape == ao.shape and st.shape == so.shape
+        e = dict(p=rel_err(pt, po), a=rel_err(at, ao), s=rel_err(st, so), p1=rel_err(pt[:, 1], rec[f"{method}_p"]),
+                 a1=rel_err(at[:, 1], rec[f"{method}_a"]))
+        print(name, method, {k: f"{v:.2e}" for k, v in e.items()})
+        assert all(v < TOL for v in e.values()), e
+
+
+@pytest.mark.parametrize("method,stop", [("euler", False), ("rk4", False), ("rk4", True)])
+def test_differentiable_solver_gradients(method, stop):
+    """solve_latent_ode (the training path: torch tape across steps, enf_ode_bwd per model call) vs autograd through the oracle's
+    unrolled solver: gradients of a trajectory functional w.r.t. the ODE parameters and the initial latents."""
+    import enf_pde_b200 as E
+    cfg, params, _, rec = load_ode_golden("ponita")
+    g = torch.Generator().manual_seed(3)
+    h, T = 0.2, 2
+    cp = torch.randn(rec["p"].shape[0], T + 1, *rec["p"].shape[1:], generator=g, dtype=torch.float64)
+    ca = torch.randn(rec["a"].shape[0], T + 1, *rec["a"].shape[1:], generator=g, dtype=torch.float64)
+    # oracle
+    Po = R.tree_map(lambda t: t.clone().requires_grad_(True), params)
+    p0, a0 = rec["p"].clone().requires_grad_(True), rec["a"].clone().requires_grad_(True)
+    pt, at, _ = O.solve_latent_ode(cfg, Po, (p0, a0, rec["sigma"]), 0.0, T * h, h, method, stop_gradient=stop)
+    ((pt * cp).sum() + (at * ca).sum()).backward()
+    # CUDA
+    model = _model(cfg)
+    P = _cuda({"params": params})
+    pg, ag = f32(rec["p"]).requires_grad_(True), f32(rec["a"]).requires_grad_(True)
+    ptc, atc, stc = E.solve_latent_ode(lambda z, t: model.apply(P, z), (pg, ag, f32(rec["sigma"])), 0.0, T * h, h, method, stop_gradient=stop)
+    ((ptc * f32(cp)).sum() + (atc * f32(ca)).sum()).backward()
+    errs = dict(p_traj=rel_err(ptc.detach(), pt.detach()), a_traj=rel_err(atc.detach(), at.detach()),
+                gp=rel_err(pg.grad, p0.grad), ga=rel_err(ag.grad, a0.grad))
+    go, gc = R.tree_flatten(Po), R.tree_flatten(P["params"])
+    scale = max(float(v.grad.abs().max()) for v in go.values())
+    leaf = {k: float((gc[k].grad.double().cpu() - go[k].grad).abs().max()) / max(float(go[k].grad.abs().max()), 1e-3 * scale) for k in go}
+    worst = max(leaf, key=leaf.get)
+    print(method, stop, {k: f"{v:.2e}" for k, v in errs.items()}, worst, f"{leaf[worst]:.2e}")
+    assert all(v < TOL for v in errs.values()), errs
+    assert leaf[worst] < TOL_LEAF, (worst, leaf[worst])
+    assert float(stc[:, -1].sub(f32(rec["sigma"])).abs().max()) == 0.0
+
+
+def test_ode_latents_only_backward_and_errors():
+    """dW = NULL skips the weight gradients (frozen ODE parameters); bad descriptions fail loudly."""
+    import ctypes
+    from enf_pde_b200 import ode, _lib
+    cfg, params, _, rec = load_ode_golden("rel_pos_periodic")
+    _, _, gp_o, ga_o, _ = _oracle_grads(cfg, params, rec["p"], rec["a"], rec["cot_p"], rec["cot_a"])
+    model = _model(cfg)
+    P = R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous(), {"params": params})      # no requires_grad
+    pg, ag = f32(rec["p"]).requires_grad_(True), f32(rec["a"]).requires_grad_(True)
+    dp, da, _ = model.apply(P, (pg, ag, None))
+    ((dp * f32(rec["cot_p"])).sum() + (da * f32(rec["cot_a"])).sum()).backward()
+    assert rel_err(pg.grad, gp_o) < TOL and rel_err(ag.grad, ga_o) < TOL
+    lib = ode._load()
+    bad = ode.EnfOdeDesc(B=1, Z=4, L=4, hidden=16, basis=8, layers=9, widen=2, degree=3, Dx=2, invariant_kind=3)
+    assert lib.enf_ode_workspace_bytes(ctypes.byref(bad)) == 0 and b"layers" in lib.enf_last_error()
+    with pytest.raises(RuntimeError):
+        model.apply(P, (rec["p"].float(), rec["a"].float(), None))          # CPU tensors: no fallback
