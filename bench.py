@@ -207,6 +207,110 @@ def reference_probe():
     return "reference", "jax importable: the reference modules could be timed on JAX_PLATFORMS=cpu"
 
 
+def ode_line(args):
+    """`--ode`: one call of the latent ODE model (PonitaODEGen, ponita_ode_g.py) forward + vector-Jacobian product with all weight
+    gradients -- the model evaluation the ODE phase takes per solver stage (pde_trainer.py:299,328) -- at the Navier-Stokes
+    experiment's sizes: 64 latents, hidden 128, 3 layers, basis 64, degree 3 (340 tensor-power features of the 4 periodic
+    invariants), 32 latent sets (= 8 signals x 4 time steps).  Not the headline metric: a row of SURVEY 8f."""
+    import torch
+    import enf_pde_b200 as E
+    from oracle import enf_ref as R
+    from oracle import ode_ref as O
+    assert torch.cuda.is_available(), "bench.py --ode needs a CUDA device"
+    dev = torch.device("cuda", 0)
+    B, Z, L = args.fields or 32, 64, 16
+    ocfg = O.OdeConfig(invariant_type="rel_pos_periodic", num_in=2, num_hidden=128, num_layers=3, latent_dim=L, basis_dim=64, degree=3,
+                       widening_factor=2)
+    inv = E.get_sa_invariant(types.SimpleNamespace(invariant_type="rel_pos_periodic", num_in=2))
+    model = E.PonitaODEGen(128, 3, L, 1, inv, 64, 3, 2)
+    gen = torch.Generator().manual_seed(7)
+    p_h = torch.as_tensor(R.init_positions_grid(B, Z, 2), dtype=torch.float32) + 0.02 * torch.randn(B, Z, 2, generator=gen)
+    a_h = 1.0 + 0.3 * torch.randn(B, Z, L, generator=gen)
+    cp_h, ca_h = torch.randn(B, Z, 2, generator=gen), torch.randn(B, Z, L, generator=gen)
+    variables = model.init(0, (p_h,), device=dev)
+    leaves = R.tree_flatten(variables["params"])
+    for t in leaves.values():
+        t.requires_grad_(True)
+    pin = lambda t: t.pin_memory()
+    p_pin, a_pin, cp_pin, ca_pin = map(pin, (p_h, a_h, cp_h, ca_h))
+    out_pin = torch.empty(B, Z, 2 + L).pin_memory()
+    p_d, a_d, cp_d, ca_d = (t.to(dev) for t in (p_h, a_h, cp_h, ca_h))
+
+    def step(e2e):
+        if e2e:
+            pp, aa = p_pin.to(dev, non_blocking=True).requires_grad_(True), a_pin.to(dev, non_blocking=True).requires_grad_(True)
+            cp, ca = cp_pin.to(dev, non_blocking=True), ca_pin.to(dev, non_blocking=True)
+        else:
+            pp, aa, cp, ca = p_d.detach().requires_grad_(True), a_d.detach().requires_grad_(True), cp_d, ca_d
+        for t in leaves.values():
+            t.grad = None
+        dp, da, _ = model.apply(variables, (pp, aa, None))
+        ((dp * cp).sum() + (da * ca).sum()).backward()
+        if e2e:
+            out_pin.copy_(torch.cat([pp.grad, aa.grad], -1), non_blocking=True)
+
+    def timed(e2e):
+        for _ in range(max(3, args.warmup)):
+            step(e2e)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    with ClockSampler(0) as sampler:
+        ms = timed(False)
+        ms_e2e = timed(True)
+    clocks = sampler.summary()
+    n, m, F, Hd, Bd, NL, W = B * Z * Z, B * Z, ocfg.poly_dim, 128, 64, 3, 256
+    flop_fwd = 2.0 * n * (F * Hd + Hd * Bd + NL * (Bd * Hd + Hd)) + 2.0 * m * (L * Hd + NL * 2 * Hd * W + Hd * (L + 2))
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12            # fp32 FMA peak of one B200, TFLOP/s (no measured figure in MEASURED_PEAKS.json)
+    ach = 3 * flop_fwd / (ms * 1e-3) / 1e12
+    # CPU baseline: the oracle restatement in fp32 on the host cores, same sizes, bounded sample
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(B, 4)
+    params32 = O.ode_init(ocfg, seed=0, dtype=torch.float32, readout_scale=1e6)
+
+    def cpu_step():
+        P = R.tree_map(lambda t: t.detach().requires_grad_(True), params32)
+        pp, aa = p_h[:Bs].clone().requires_grad_(True), a_h[:Bs].clone().requires_grad_(True)
+        dp, da = O.ponita_ode(ocfg, P, pp, aa)
+        ((dp * cp_h[:Bs]).sum() + (da * ca_h[:Bs]).sum()).backward()
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu_step()
+        t0, k = time.perf_counter(), 0
+        while k < 3 or (time.perf_counter() - t0 < 10.0 and k < 50):
+            cpu_step(); k += 1
+        cpu = {"value": Bs * k / (time.perf_counter() - t0), "unit": "latent sets/s", "cores": cores, "kind": "port",
+               "sample": f"{Bs} latent sets x 64 latents per step, {k} steps, PyTorch-CPU fp32 restatement (oracle/ode_ref.py) with autograd"}
+    line = {"metric": "latent-ODE model evaluations/sec (PonitaODEGen fwd+bwd)", "value": B / (ms * 1e-3), "unit": "latent sets/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "latent ODE model at config_navier_stokes.yaml `node:` sizes", "B": B, "Z": Z, "hidden": Hd, "layers": NL,
+                       "basis": Bd, "degree": 3, "poly_features": F, "invariant": "rel_pos_periodic (self-attention variant)",
+                       "l2": "working set (pair-row activations, %.0f MB) > 126 MB L2" % (model_ws_mb(model, p_d, a_d))},
+            "roofline": {"bound": "fp32-fma", "kernel": "enf_gemm_kernel (pair-row Dense layers) + ode_* kernels", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": "nominal fp32 FMA rate (148 SMs x 128 lanes x 2 x 1.965 GHz)",
+                         "algorithmic_flop_per_step": 3 * flop_fwd},
+            "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "latent sets/s", "h2d_bytes_per_step": 4 * 2 * (p_h.numel() + a_h.numel()),
+                    "d2h_bytes_per_step": 4 * out_pin.numel(), "ms_per_step": ms_e2e}}
+    print(json.dumps(line))
+
+
+def model_ws_mb(model, p, a):
+    import ctypes
+    from enf_pde_b200 import ode
+    d = ode.EnfOdeDesc(**model._desc_kw(p, a))
+    return ode._load().enf_ode_workspace_bytes(ctypes.byref(d)) / 1e6
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,7 +330,11 @@ def main():
     ap.add_argument("--out-bf16", action="store_true", help="forward-only: bfloat16 decoded field (ENF_FLAG_OUT_BF16)")
     ap.add_argument("--recompute", action="store_true", help="bounded-memory training: ENF_FLAG_RECOMPUTE")
     ap.add_argument("--chunk-fields", type=int, default=0)
+    ap.add_argument("--ode", action="store_true",
+                    help="latent ODE model line (SURVEY 8f-3): PonitaODEGen fwd + bwd at config_navier_stokes.yaml's `node:` sizes")
     args = ap.parse_args()
+    if args.ode:
+        return ode_line(args)
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

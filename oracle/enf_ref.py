@@ -63,6 +63,7 @@ class EnfConfig:
     invariant_type: str = "rel_pos_periodic"
     embedding_freq_multiplier: Tuple[float, float] = (0.05, 0.1)
     use_gaussian_window: bool = True
+    num_layers: int = 0          # latent self-attention blocks before the cross-attention block
 
     # derived -------------------------------------------------------------------------------
     @property
@@ -71,6 +72,11 @@ class EnfConfig:
         return {"rel_pos": n, "norm_rel_pos": 1, "abs_pos": n, "rel_pos_periodic": 2 * n,
                 "ponita": 2, "polar_periodic": 1, "latitude_periodic": 4, "ball": 5,
                 "ball_lat": 6}[t]
+
+    @property
+    def sa_inv_dim(self) -> int:
+        """dim of get_sa_invariant's class (invariant/__init__.py:13-45): only `ponita` differs (Ponita2D, ponita.py:46-61)."""
+        return 3 if self.invariant_type == "ponita" else self.inv_dim
 
     @property
     def num_z_pos_dims(self) -> int:
@@ -162,10 +168,17 @@ def _cos_angle(x, p):
     return num / den
 
 
-def invariant(cfg: EnfConfig, x, p):
-    """x (B,C,Dx), p (B,Z,P) already cos/sin-embedded for 'ponita'. Returns (B,C,Z,I)."""
+def invariant(cfg: EnfConfig, x, p, sa: bool = False):
+    """x (B,C,Dx), p (B,Z,P) already cos/sin-embedded for 'ponita'. Returns (B,C,Z,I).  sa: the self-attention variant
+    (get_sa_invariant; x is then a set of embedded poses too): only `ponita` differs (Ponita2D, ponita.py:63-86)."""
     t = cfg.invariant_type
     n = cfg.num_in
+    if sa and t == "ponita":
+        rel = x[:, :, None, :2] - p[:, None, :, :2]
+        xo, po = x[:, :, None, 2:], p[:, None, :, 2:]
+        i1 = rel[..., 0] * po[..., 0] + rel[..., 1] * po[..., 1]
+        i2 = -rel[..., 0] * po[..., 1] + rel[..., 1] * po[..., 0]
+        return torch.stack([i1, i2, (xo * po).sum(dim=-1)], dim=-1)
     if t == "rel_pos":
         return x[:, :, None, :n] - p[:, None, :, :n]
     if t == "norm_rel_pos":
@@ -176,7 +189,7 @@ def invariant(cfg: EnfConfig, x, p):
         rel = p[:, None, :, :] - x[:, :, None, :]
         return torch.cat([torch.cos(math.pi * rel), torch.sin(math.pi * rel)], dim=-1)
     if t == "ponita":
-        rel = x[:, :, None, :] - p[:, None, :, :2]
+        rel = x[:, :, None, :2] - p[:, None, :, :2]
         ori = p[:, None, :, 2:]
         i1 = rel[..., 0] * ori[..., 0] + rel[..., 1] * ori[..., 1]
         i2 = -rel[..., 0] * ori[..., 1] + rel[..., 1] * ori[..., 0]
@@ -236,11 +249,12 @@ def gaussian_window(cfg: EnfConfig, x, p, sigma):
 # the operator and the model
 # --------------------------------------------------------------------------------------------
 
-def cross_attention(cfg: EnfConfig, ap, x, p, a, sigma):
+def cross_attention(cfg: EnfConfig, ap, x, p, a, sigma, sa: bool = False):
     """EquivariantCrossAttention.__call__ (equivariant_cross_attention.py:74-151) with
-    condition_value_transform=True, condition_invariant_embedding=False, project_heads=False."""
+    condition_value_transform=True, condition_invariant_embedding=False; project_heads only changes the width of
+    out_proj (:68-72), which the parameter shapes carry.  sa: built on the self-attention invariant (x = embedded poses)."""
     H, d = cfg.num_heads, cfg.num_hidden
-    inv = invariant(cfg, x, p)                                   # :86
+    inv = invariant(cfg, x, p, sa)                               # :86
     inv_emb_q = rff_net(inv, ap["invariant_embedding_query"])    # :89
     q = dense(inv_emb_q, ap["inv_emb_to_q"])                     # :92
     k = dense(a, ap["a_to_k"])                                   # :93
@@ -263,12 +277,17 @@ def cross_attention(cfg: EnfConfig, ap, x, p, a, sigma):
 
 
 def nef_apply(cfg: EnfConfig, params: Dict, x, p, a, sigma, return_att: bool = False):
-    """EquivariantCrossAttentionNeF.__call__ (equivariant_cross_attention_nef.py:204-235), num_layers=0."""
+    """EquivariantCrossAttentionNeF.__call__ (equivariant_cross_attention_nef.py:204-235)."""
     P = params["params"] if "params" in params else params
     if cfg.num_z_ori_dims > 0:                                   # :214-217
         n = cfg.num_z_pos_dims
         p = torch.cat([p[:, :, :n], torch.cos(p[:, :, n:]), torch.sin(p[:, :, n:])], dim=-1)
     a = dense(a, P["latent_stem"])                               # :220
+    for i in range(cfg.num_layers):                              # :223-226 latent self-attention (x = p, residual, project_heads)
+        sb = P[f"self_attention_blocks_{i}"]
+        y, _ = cross_attention(cfg, sb["attn"], p, p, layer_norm(a, sb["layer_norm_attn"]), sigma, sa=True)   # :56-59
+        a = a + pointwise_ffn(a + y, sb["pointwise_ffn"])        # :62-64 (block) and :225
+        a = gelu_tanh(a)                                         # :226
     blk = P["cross_attention_blocks_0"]
     a_norm = layer_norm(a, blk["layer_norm_attn"])               # :56
     y, att = cross_attention(cfg, blk["attn"], x, p, a_norm, sigma)   # :59
@@ -335,8 +354,19 @@ def nef_init(cfg: EnfConfig, seed: int = 0, dtype=torch.float64, perturb: float 
         "inv_emb_cond_mixer": _ffn_params(rng, d, d, d),
         "out_proj": _dense_default(rng, H * d, H * d),
     }
+    def sa_block():
+        Is = cfg.sa_inv_dim
+        return {"layer_norm_attn": {"scale": np.ones(d), "bias": np.zeros(d)},
+                "attn": {"invariant_embedding_query": _rff_params(rng, Is, d, fq),
+                         "invariant_embedding_value": _rff_params(rng, Is, d, fv),
+                         "inv_emb_to_q": _dense_default(rng, d, H * d), "a_to_k": _dense_default(rng, d, H * d),
+                         "a_to_v": _dense_default(rng, d, H * d), "inv_emb_to_v": _ffn_params(rng, d, d, 2 * H * d),
+                         "inv_emb_cond_mixer": _ffn_params(rng, d, d, d), "out_proj": _dense_default(rng, H * d, d)},
+                "pointwise_ffn": _ffn_params(rng, d, d, d)}
+
     tree = {
         "latent_stem": _dense_default(rng, L, d),
+        **{f"self_attention_blocks_{i}": sa_block() for i in range(cfg.num_layers)},
         "cross_attention_blocks_0": {
             "layer_norm_attn": {"scale": np.ones(d), "bias": np.zeros(d)},
             "attn": attn,

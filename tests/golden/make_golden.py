@@ -64,6 +64,16 @@ CASES = {
     # -- what ball.py:90-92 does for the same quantities (BallLatFixed below).
     "ball_lat": dict(invariant_type="ball_lat", num_in=3, d=16, H=2, L=4, O=2, B=2, C=14, Z=5,
                      freq=(0.2, 0.5), window=True),
+    # latent self-attention blocks before the cross-attention block (num_layers > 0, equivariant_cross_attention_nef.py:159-167,
+    # 223-226): x = p, residual, project_heads; `ponita` switches to Ponita2D (get_sa_invariant)
+    "sa1_rel_pos_periodic": dict(invariant_type="rel_pos_periodic", num_in=2, d=16, H=2, L=6, O=1, B=2, C=12, Z=5,
+                                 freq=(0.05, 0.1), window=True, layers=1),
+    "sa2_ponita": dict(invariant_type="ponita", num_in=2, d=16, H=2, L=5, O=1, B=2, C=10, Z=4,
+                       freq=(0.05, 0.2), window=True, layers=2),
+    "sa1_latitude_periodic": dict(invariant_type="latitude_periodic", num_in=2, d=16, H=1, L=4, O=2, B=1, C=9, Z=8,
+                                  freq=(0.05, 0.2), window=True, layers=1),
+    "sa1_rel_pos_nowin": dict(invariant_type="rel_pos", num_in=2, d=16, H=2, L=4, O=1, B=2, C=8, Z=3,
+                              freq=(0.2, 0.3), window=False, layers=1),
 }
 
 
@@ -115,7 +125,7 @@ def build_case(name, c, rng):
     cfg = types.SimpleNamespace(invariant_type=c["invariant_type"], num_in=c["num_in"])
     ca_inv = ball_lat_fixed() if c["invariant_type"] == "ball_lat" else get_ca_invariant(cfg)
     nef = EquivariantCrossAttentionNeF(
-        num_hidden=c["d"], num_heads=c["H"], num_layers=0, num_out=c["O"], latent_dim=c["L"],
+        num_hidden=c["d"], num_heads=c["H"], num_layers=c.get("layers", 0), num_out=c["O"], latent_dim=c["L"],
         self_attn_invariant=ca_inv if c["invariant_type"] == "ball_lat" else get_sa_invariant(cfg), cross_attn_invariant=ca_inv,
         embedding_type="rff", embedding_freq_multiplier=list(c["freq"]),
         condition_value_transform=True, use_gaussian_window=c["window"])

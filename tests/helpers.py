@@ -20,7 +20,8 @@ def load_golden(name, dtype=torch.float64):
     meta = ast.literal_eval(str(z["meta"]))
     cfg = R.EnfConfig(num_in=meta["num_in"], num_hidden=meta["d"], num_heads=meta["H"], num_out=meta["O"],
                       latent_dim=meta["L"], invariant_type=meta["invariant_type"],
-                      embedding_freq_multiplier=tuple(meta["freq"]), use_gaussian_window=meta["window"])
+                      embedding_freq_multiplier=tuple(meta["freq"]), use_gaussian_window=meta["window"],
+                      num_layers=meta.get("layers", 0))
     t = lambda k: torch.tensor(z[k], dtype=dtype)
     params = {"params": R.tree_unflatten({k[6:]: t(k) for k in z.files if k.startswith("param:")})}
     direction = R.tree_unflatten({k[4:]: t(k) for k in z.files if k.startswith("dir:")})
