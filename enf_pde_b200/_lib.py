@@ -58,6 +58,22 @@ LEAF_PATHS = {
     "m2_w": "out_proj/layers_4/kernel", "m2_b": "out_proj/layers_4/bias",
 }
 
+# leaves a latent self-attention step does not use (no decode MLP) / a call with ENF_FLAG_NO_STEM does not use
+_MLP_LEAVES = ("m0_w", "m0_b", "m1_w", "m1_b", "m2_w", "m2_b")
+_STEM_LEAVES = ("stem_w", "stem_b")
+
+
+def leaf_paths(block: str, with_stem: bool, with_mlp: bool):
+    """leaf -> path (or None: unused by the call) for the block named `block` ('cross_attention_blocks_0', 'self_attention_blocks_<i>')."""
+    out = {}
+    for n, path in LEAF_PATHS.items():
+        if (n in _STEM_LEAVES and not with_stem) or (n in _MLP_LEAVES and not with_mlp):
+            out[n] = None
+        else:
+            out[n] = path.replace("cross_attention_blocks_0", block)
+    return out
+
+
 INVARIANT_KINDS = {
     "rel_pos": 0, "norm_rel_pos": 1, "abs_pos": 2, "rel_pos_periodic": 3, "ponita": 4,
     "polar_periodic": 5, "latitude_periodic": 6, "ball": 7, "ball_lat": 8,
@@ -67,6 +83,8 @@ FLAG_FORWARD_ONLY = 1
 FLAG_RECOMPUTE = 4
 FLAG_OUT_BF16 = 8
 FLAG_FROZEN_RELU = 16
+FLAG_SELF_BLOCK = 32
+FLAG_NO_STEM = 64
 ABI_VERSION = 2
 
 EXPORTS = ("enf_abi_version", "enf_invariant_dim", "enf_pose_dim", "enf_xattn_workspace_bytes", "enf_xattn_chunk_for_cap",

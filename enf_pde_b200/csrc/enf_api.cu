@@ -54,7 +54,26 @@ void leaf_sizes(const EnfDesc& D, int I, size_t* n) {
       L * d, d, d, d, I * (d / 2), d * d, d, d * d, d, I * (d / 2), d * d, d, d * d, d, d * Hd, Hd, d * Hd, Hd, d * Hd, Hd,
       d * d, d, d, d, d * 2 * Hd, 2 * Hd, d * d, d, d, d, d * d, d, Hd * Hd, Hd, Hd * Hd, Hd, Hd, Hd, Hd * Hd, Hd,
       Hd * d, d, d * d, d, d * O, O};
+  if (D.flags & ENF_FLAG_NO_STEM) v[0] = v[1] = 0;
+  if (D.flags & ENF_FLAG_SELF_BLOCK) {         // project_heads: out_proj (Hd, d); pointwise FFN d -> d -> d; no decode MLP
+    v[32] = Hd * d; v[33] = d; v[34] = d * d; v[35] = d; v[36] = d; v[37] = d; v[38] = d * d; v[39] = d;
+    for (int i = 40; i < ENF_NUM_WEIGHT_LEAVES; ++i) v[i] = 0;
+  }
   memcpy(n, v, sizeof(v));
+}
+
+// the pair kernels' record layout; self-attention steps use get_sa_invariant's variant (Ponita2D: a third invariant)
+EnfRecordLayout record_layout(const EnfDesc& D) {
+  EnfRecordLayout r = enf_record_layout(D.invariant_kind, D.Dx, D.use_window);
+  if ((D.flags & ENF_FLAG_SELF_BLOCK) && D.invariant_kind == ENF_INV_PONITA) {
+    r.I = 3;
+    if (r.win_kind == ENF_WIN_NP) r.win_row = r.I;
+  }
+  return r;
+}
+// tcgen05 pair kernels: tensor-core precision mode, a supported shape, and not a latent self-attention step
+bool tc_fwd_on(const EnfDesc& D) {
+  return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && !(D.flags & ENF_FLAG_SELF_BLOCK);
 }
 
 int validate(const EnfDesc* D, EnfRecordLayout* rl) {
@@ -62,7 +81,7 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if (D->B <= 0 || D->C <= 0 || D->Z <= 0 || D->L <= 0 || D->O <= 0) return fail(ENF_ERR_BAD_DESC, "B, C, Z, L, O must be positive");
   if (!(D->d == 16 || D->d == 32 || D->d == 64 || D->d == 128)) return fail(ENF_ERR_UNSUPPORTED, "num_hidden must be 16, 32, 64 or 128");
   if (D->H < 1 || D->H > 4) return fail(ENF_ERR_UNSUPPORTED, "num_heads must be 1..4");
-  EnfRecordLayout r = enf_record_layout(D->invariant_kind, D->Dx, D->use_window);
+  EnfRecordLayout r = record_layout(*D);
   if (r.I < 0) return fail(ENF_ERR_BAD_DESC, "unknown invariant_kind");
   int k = D->invariant_kind;
   bool dx_ok = (k <= ENF_INV_ABS_POS) ? (D->Dx >= 1 && D->Dx <= 3)
@@ -71,8 +90,14 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
   if ((int64_t)D->B * D->Z * D->H > 65535) return fail(ENF_ERR_UNSUPPORTED, "B*Z*H must be <= 65535 per call (shard the fields)");
   if (D->B > 65535) return fail(ENF_ERR_UNSUPPORTED, "B must be <= 65535");
   if (D->precision != ENF_PREC_FP32 && D->precision != ENF_PREC_BF16) return fail(ENF_ERR_BAD_DESC, "unknown precision");
-  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16 | ENF_FLAG_FROZEN_RELU))
+  if (D->flags & ~(ENF_FLAG_FORWARD_ONLY | ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16 | ENF_FLAG_FROZEN_RELU | ENF_FLAG_SELF_BLOCK | ENF_FLAG_NO_STEM))
     return fail(ENF_ERR_BAD_DESC, "unknown bits in flags");
+  if ((D->flags & ENF_FLAG_NO_STEM) && D->L != D->d) return fail(ENF_ERR_BAD_DESC, "ENF_FLAG_NO_STEM: a is the hidden state, L must equal d");
+  if (D->flags & ENF_FLAG_SELF_BLOCK) {
+    if (D->C != D->Z || D->O != D->d) return fail(ENF_ERR_BAD_DESC, "ENF_FLAG_SELF_BLOCK: the queries are the latents (C == Z) and out is the hidden state (O == d)");
+    if (D->flags & (ENF_FLAG_RECOMPUTE | ENF_FLAG_OUT_BF16 | ENF_FLAG_FROZEN_RELU))
+      return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_SELF_BLOCK does not combine with RECOMPUTE / OUT_BF16 / FROZEN_RELU");
+  }
   if ((D->flags & ENF_FLAG_OUT_BF16) && (!(D->flags & ENF_FLAG_FORWARD_ONLY) || !enf_thin_supported(D->d, D->O)))
     return fail(ENF_ERR_UNSUPPORTED, "ENF_FLAG_OUT_BF16 needs ENF_FLAG_FORWARD_ONLY and num_out <= 4");
   if ((D->flags & ENF_FLAG_FROZEN_RELU) && D->precision != ENF_PREC_FP32)
@@ -85,9 +110,7 @@ int validate(const EnfDesc* D, EnfRecordLayout* rl) {
 
 // tensor-core backward wherever the tensor-core forward runs (d in {64, 128}, H <= 2): a backward on the fp32 kernels behind a
 // 16-bit-operand forward mixes two different roundings of the same activations (measured: 2e-2 on single weight-gradient leaves)
-bool use_tc_bwd(const EnfDesc& D) {
-  return D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H) && enf_pairs_bwd_tc_supported(D.d, D.H);
-}
+bool use_tc_bwd(const EnfDesc& D) { return tc_fwd_on(D) && enf_pairs_bwd_tc_supported(D.d, D.H); }
 
 // fields per backward chunk: everything O(B*C*Z) that only lives between the pair kernels of one chunk is sized by this.
 // Default (stash) mode: one chunk = the whole batch.
@@ -117,7 +140,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
     // again, so it reuses that one): a backward leaves the forward state intact and can be repeated
     if (train && !tc_both) { Y.add("W3T", BZ * H * d2); Y.add("dWeff", BZ * H * d2); }
   }
-  if (D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H)) {
+  if (tc_fwd_on(D)) {
     // operand images: rows of max(d, 64) 16-bit features (d = 32 keeps the 128-byte row pitch), counted in floats
     const size_t dimg = d * (d < 64 ? 64 : d) / 2;
     Y.add("img_q_w1", dimg); Y.add("img_v_w1", dimg); Y.add("img_Wp", dimg); Y.add("img_W3", BZ * H * dimg);
@@ -150,6 +173,7 @@ Layout make_layout(const EnfDesc& D, const EnfRecordLayout& rl) {
   if (!train) return Y;
   Y.add("s0", BC * Hd); Y.add("s1", BC * Hd); Y.add("d_o2p", BC * d); Y.add("d_o1p", BC * d);
   Y.add("dbeff", BZ * Hd); Y.add("dk", BZ * Hd); Y.add("dv0", BZ * Hd); Y.add("dahat", BZ * d); Y.add("da0", BZ * d);
+  if (D.flags & ENF_FLAG_SELF_BLOCK) { Y.add("da0x", BZ * d); Y.add("g_xi", BC * ENF_F_XI); }
   // ---- accumulators, zeroed at the start of each bwd ----
   Y.acc_begin = Y.total;
   Y.add("g_W3", BZ * H * d2); Y.add("g_b3", BZ * Hd); Y.add("g_U", BZ * Hd); Y.add("g_kappa", BZ * H);
@@ -262,7 +286,7 @@ EnfPairParams pair_params(const EnfDesc& D, const EnfRecordLayout& rl, const Enf
   return p;
 }
 
-bool check_weights(const EnfWeights* w);
+bool check_weights(const EnfDesc& D, const EnfWeights* w);
 
 // parameters of the tensor-core pair forward; `stash`: also write the backward's operand stash (that_img / dgr / trstd)
 EnfPairTcParams tc_fwd_params(const EnfDesc& D, const EnfRecordLayout& rl, const EnfWeights& w, const Ctx& c, const EnfPairParams& pp,
@@ -307,19 +331,22 @@ void shift_fields(EnfPairTcBwdParams& tp, const EnfDesc& D, int b0, int nb) {
 // argument checks shared by enf_xattn_fwd and enf_xattn_bwd
 int check_call(const EnfDesc& D, const EnfWeights* w, const float* x, int64_t x_batch_stride, const float* p, const float* a,
                const float* sigma, void* workspace) {
-  if (!w || !x || !p || !a || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
-  if (!check_weights(w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
+  const bool self = (D.flags & ENF_FLAG_SELF_BLOCK) != 0;
+  if (!w || (!x && !self) || !p || !a || !workspace) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
+  if (!check_weights(D, w)) return fail(ENF_ERR_NULL_POINTER, "EnfWeights has a NULL leaf");
   if (D.use_window && !sigma) return fail(ENF_ERR_NULL_POINTER, "sigma is NULL but use_window is set (the reference asserts the same)");
-  if (x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
+  if (!self && x_batch_stride != 0 && x_batch_stride != (int64_t)D.C * D.Dx) return fail(ENF_ERR_BAD_DESC, "x_batch_stride must be 0 or C*Dx");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(ENF_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)"); }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ENF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
   return ENF_OK;
 }
 
-bool check_weights(const EnfWeights* w) {
+bool check_weights(const EnfDesc& D, const EnfWeights* w) {
   const float* const* p = reinterpret_cast<const float* const*>(w);
-  for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) if (!p[i]) return false;
+  size_t n[ENF_NUM_WEIGHT_LEAVES];
+  leaf_sizes(D, 1, n);
+  for (int i = 0; i < ENF_NUM_WEIGHT_LEAVES; ++i) if (!p[i] && n[i]) return false;      // leaves the call does not use may be NULL
   return true;
 }
 
@@ -397,7 +424,7 @@ int enf_xattn_chunk_for_cap(const EnfDesc* desc, size_t cap_bytes) {
 int enf_xattn_dispatch(const EnfDesc* desc, int* fwd_tc, int* bwd_tc) {
   int rc = validate(desc, nullptr);
   if (rc != ENF_OK) return rc;
-  const bool f = desc->precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(desc->d, desc->H);
+  const bool f = tc_fwd_on(*desc);
   if (fwd_tc) *fwd_tc = f ? 1 : 0;
   if (bwd_tc) *bwd_tc = (f && use_tc_bwd(*desc) && !(desc->flags & ENF_FLAG_FORWARD_ONLY)) ? 1 : 0;
   return ENF_OK;
@@ -427,8 +454,9 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   const EnfDesc& D = *desc;
   if (!out) return fail(ENF_ERR_NULL_POINTER, "NULL argument");
   if ((rc = check_call(D, w, x, x_batch_stride, p, a, sigma, workspace)) != ENF_OK) return rc;
-  const bool use_tc = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);   // other shapes: fp32 kernels
+  const bool use_tc = tc_fwd_on(D);   // other shapes (and latent self-attention steps): fp32 kernels
   const bool train = !(D.flags & ENF_FLAG_FORWARD_ONLY);
+  const bool self = (D.flags & ENF_FLAG_SELF_BLOCK) != 0, no_stem = (D.flags & ENF_FLAG_NO_STEM) != 0;
   Layout Y = make_layout(D, rl);
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small: see enf_xattn_workspace_bytes");
 
@@ -436,7 +464,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   cudaStream_t st = c.st;
   const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
   const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
-  const int Bx = x_batch_stride == 0 ? 1 : D.B;
+  const int Bx = (x_batch_stride == 0 && !self) ? 1 : D.B;
   // ---- W: fold weights --------------------------------------------------------------------------
   c.begin_group();
   c.gemm(d, Hd, d, enf_mat(w->q_wf, d), enf_mat(w->wq, Hd), enf_mat(c.f("A_q"), Hd));
@@ -450,7 +478,16 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.end_group();
   // tail fold (exact algebra, tests/folded_model.py): mixer Dense_1, out_proj and the block FFN's Dense_0 are three
   // linear maps in a row:  e1 = nbar W_A + b_A,  W_A = blockdiag(M2g) wo fb_w1,  b_A = (tile(c2g) wo + bo) fb_w1 + fb_b1
-  {
+  if (self) {
+    // latent self-attention step (project_heads, residual): mixer Dense_1 and out_proj fold into  y = nbar P1 + b1,
+    // P1 = blockdiag(M2g) wo (Hd, d),  b1 = tile(c2g) wo + bo (d); the residual sits between this and the FFN
+    EnfGemmOpts ob; ob.batch = H;
+    c.gemm(d, d, d, enf_mat(c.f("M2g"), d), enf_mat(w->wo, d, 1, (int64_t)d * d), enf_mat(c.f("P1"), d, 1, (int64_t)d * d), ob);
+    if (cudaMemcpyAsync(c.f("b1"), w->bo, d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(ENF_ERR_CUDA, "copy of out_proj bias failed");
+    for (int h = 0; h < H; ++h)
+      c.gemm(1, d, d, enf_mat(c.f("c2g"), d), enf_mat(w->wo + (int64_t)h * d * d, d), enf_mat(c.f("b1"), d), opt_acc());
+  } else {
     EnfGemmOpts ob; ob.batch = H;
     c.gemm(d, Hd, d, enf_mat(c.f("M2g"), d), enf_mat(w->wo, Hd, 1, (int64_t)d * Hd), enf_mat(c.f("P1"), Hd, 1, (int64_t)d * Hd), ob);
     if (cudaMemcpyAsync(c.f("b1"), w->bo, Hd * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -473,10 +510,16 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   }
 
   // ---- L: per-latent folds ----------------------------------------------------------------------
-  c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
+  if (self) c.launches += enf_launch_pose_record(st, D.invariant_kind, D.Dx, rl.P, rl.I, BZ, p, c.f("lam"));
+  else c.launches += enf_launch_latent_record(st, D, p, c.f("lam"));
   if (D.flags & ENF_FLAG_FROZEN_RELU)      // second pose set: the relu pattern's expansion point
     c.launches += enf_launch_latent_record(st, D, p + BZ * rl.P, c.f("lam_mask"));
-  c.gemm((int)BZ, d, L, enf_mat(a, L), enf_mat(w->stem_w, d), enf_mat(c.f("a0"), d), opt_bias(w->stem_b));
+  if (no_stem) {
+    if (cudaMemcpyAsync(c.f("a0"), a, BZ * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(ENF_ERR_CUDA, "copy of the hidden latent state failed");
+  } else {
+    c.gemm((int)BZ, d, L, enf_mat(a, L), enf_mat(w->stem_w, d), enf_mat(c.f("a0"), d), opt_bias(w->stem_b));
+  }
   c.launches += enf_launch_ln_fwd(st, c.f("a0"), BZ, d, w->ln_attn_g, w->ln_attn_b, c.f("acore"), c.f("ahat"), c.f("arstd"), 0);
   c.begin_group();
   c.gemm((int)BZ, Hd, d, enf_mat(c.f("ahat"), d), enf_mat(w->wk, Hd), enf_mat(c.f("k"), Hd), opt_bias(w->bk));
@@ -494,7 +537,8 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm((int)(BZ * H), d, d, enf_mat(c.f("beff"), d), enf_mat(w->mx_w1, d), enf_mat(c.f("b3"), d), opt_bias(w->mx_b1));
 
   // ---- X, P ---------------------------------------------------------------------------------------
-  c.launches += enf_launch_query_features(st, D, x, x_batch_stride, Bx, c.f("xi"));
+  if (self) c.launches += enf_launch_pose_features(st, D.invariant_kind, D.Dx, rl.P, BZ, p, c.f("xi"));      // x = p
+  else c.launches += enf_launch_query_features(st, D, x, x_batch_stride, Bx, c.f("xi"));
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
   int nl;
   if (use_tc) {
@@ -524,6 +568,15 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
 
   // ---- Q: per-query tail ----------------------------------------------------------------------------
   const int out_bf16 = (D.flags & ENF_FLAG_OUT_BF16) ? 1 : 0;
+  if (self) {
+    // a_res = a' + (nbar P1 + b1) ; FFN(a_res) = Dense_1(LN(gelu(Dense_0(a_res)))) ; out = gelu(a' + FFN)   (nef.py:62-64, 225-226)
+    c.gemm((int)BC, d, Hd, enf_mat(c.f("nbar"), Hd), enf_mat(c.f("P1"), d), enf_mat(c.f("o2p"), d), opt_bias(c.f("b1")));
+    c.launches += enf_launch_add(st, c.f("o2p"), c.f("o2p"), c.f("a0"), BC * d);
+    c.gemm((int)BC, d, d, enf_mat(c.f("o2p"), d), enf_mat(w->fb_w1, d), enf_mat(c.f("e1"), d), opt_bias(w->fb_b1));
+    c.launches += enf_launch_ln_fwd(st, c.f("e1"), BC, d, w->fb_g, w->fb_beta, c.f("e3c"), c.f("e3"), c.f("erstd"), 1);
+    c.gemm((int)BC, d, d, enf_mat(c.f("e3"), d), enf_mat(w->fb_w2, d), enf_mat(c.f("fo"), d), opt_bias(w->fb_b2));
+    c.launches += enf_launch_add_gelu(st, c.f("o1p"), out, c.f("a0"), c.f("fo"), BC * d);
+  } else {
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("nbar"), Hd), enf_mat(c.f("W_A"), Hd), enf_mat(c.f("e1"), Hd),
          with_lo(opt_bias(c.f("b_A")), use_tc ? c.f("lo_W_A") : nullptr));
   c.launches += enf_launch_ln_fwd(st, c.f("e1"), BC, Hd, w->fb_g, w->fb_beta, c.f("e3c"), c.f("e3"), c.f("erstd"), 1);
@@ -547,6 +600,7 @@ int enf_xattn_fwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     if (enf_thin_supported(d, O)) c.launches += enf_launch_thin_out(st, c.f("o2p"), w->m2_w, w->m2_b, out, BC, d, O, 1, out_bf16);
     else { o.bias = w->m2_b; c.gemm((int)BC, O, d, enf_mat(c.f("o2p"), d), enf_mat(w->m2_w, O), enf_mat(out, O), o); }
   }
+  }   // !self
   if (c.gemm_failed) return fail(ENF_ERR_CUDA, "a tensor-core stage GEMM could not be configured");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ENF_ERR_CUDA, std::string("CUDA error while enqueueing fwd: ") + cudaGetErrorString(e));
@@ -578,13 +632,14 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   Layout Y = make_layout(D, rl);
   if (workspace_bytes < Y.total * sizeof(float)) return fail(ENF_ERR_WORKSPACE, "workspace too small");
 
-  const bool tc_fwd = D.precision == ENF_PREC_BF16 && enf_pairs_fwd_tc_supported(D.d, D.H);
+  const bool tc_fwd = tc_fwd_on(D);
   const bool tc_bwd = tc_fwd && use_tc_bwd(D);
+  const bool self = (D.flags & ENF_FLAG_SELF_BLOCK) != 0, no_stem = (D.flags & ENF_FLAG_NO_STEM) != 0;
   Ctx c; c.st = (cudaStream_t)stream; c.ws = (float*)workspace; c.Y = &Y; c.tc = tc_fwd;
   cudaStream_t st = c.st;
   const int d = D.d, H = D.H, Hd = H * d, L = D.L, O = D.O;
   const int64_t BZ = (int64_t)D.B * D.Z, BC = (int64_t)D.B * D.C;
-  const int Bx = x_batch_stride == 0 ? 1 : D.B;
+  const int Bx = (x_batch_stride == 0 && !self) ? 1 : D.B;
   auto G = [&](const char* leaf) { return c.f((std::string("gw_") + leaf).c_str()); };
   auto colsum = [&](const float* Gm, int64_t M, int N, float* out) { c.launches += enf_launch_colsum(st, Gm, M, N, N, out, nullptr, 0); };
 
@@ -596,6 +651,29 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   // and of the latent stage are skipped, only the chain towards dp / da / dsigma is evaluated
   const bool wg = dW != nullptr;
   auto LO = [&](const char* name) { return tc_fwd ? c.f(name) : (const float*)nullptr; };
+  if (self) {
+    // backward of  out = gelu(a' + fo), fo = Dense_1(LN(gelu(Dense_0(a_res)))), a_res = a' + nbar P1 + b1
+    c.launches += enf_launch_mul_gelu_grad(st, c.f("d_o1p"), d_out, c.f("o1p"), BC * d);                        // d(a' + fo)
+    if (wg) {
+      c.gemm(d, d, (int)BC, enf_mat(c.f("e3"), 1, d), enf_mat(c.f("d_o1p"), d), enf_mat(G("fb_w2"), d), opt_acc());
+      colsum(c.f("d_o1p"), BC, d, G("fb_b2"));
+    }
+    c.gemm((int)BC, d, d, enf_mat(c.f("d_o1p"), d), enf_mat(w->fb_w2, 1, d), enf_mat(c.f("s1"), d));                // de3
+    c.launches += enf_launch_ln_bwd(st, c.f("s1"), c.f("e3c"), c.f("erstd"), w->fb_g, c.f("e1"), BC, d, c.f("s1"),
+                                    wg ? G("fb_g") : nullptr, wg ? G("fb_beta") : nullptr, 1, 0, 0);                 // de1 (in place)
+    if (wg) {
+      c.gemm(d, d, (int)BC, enf_mat(c.f("o2p"), 1, d), enf_mat(c.f("s1"), d), enf_mat(G("fb_w1"), d), opt_acc());
+      colsum(c.f("s1"), BC, d, G("fb_b1"));
+    }
+    c.gemm((int)BC, d, d, enf_mat(c.f("s1"), d), enf_mat(w->fb_w1, 1, d), enf_mat(c.f("d_o2p"), d));                // d a_res
+    c.launches += enf_launch_add(st, c.f("da0x"), c.f("d_o1p"), c.f("d_o2p"), BC * d);                             // both residuals -> a'
+    if (wg) {
+      c.gemm(Hd, d, (int)BC, enf_mat(c.f("nbar"), 1, Hd), enf_mat(c.f("d_o2p"), d), enf_mat(c.f("dP1"), d));
+      if (cudaMemsetAsync(c.f("db1"), 0, d * sizeof(float), st) != cudaSuccess) return fail(ENF_ERR_CUDA, "memset failed");
+      colsum(c.f("d_o2p"), BC, d, c.f("db1"));
+    }
+    c.gemm((int)BC, Hd, d, enf_mat(c.f("d_o2p"), d), enf_mat(c.f("P1"), 1, d), enf_mat(c.f("s0"), Hd));               // dnbar
+  } else {
   {
     // wgrad A operands: gelu of the stored pre-activation (fp32 mode: applied on load; tensor-core mode: the
     // activated copies written by the forward)
@@ -643,6 +721,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   }
   c.gemm((int)BC, Hd, Hd, enf_mat(c.f("s1"), Hd), enf_mat(c.f("W_A"), 1, Hd), enf_mat(c.f("s0"), Hd),
          with_lo(EnfGemmOpts(), LO("lo_W_A")));                                                                  // dnbar
+  }   // !self
 
   // ---- P backward --------------------------------------------------------------------------------------
   EnfPairParams pp = pair_params(D, rl, *w, c, D.use_window ? sigma : nullptr, Bx == 1 ? 0 : (int64_t)D.C * ENF_F_XI);
@@ -707,6 +786,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     pp.g_Wp = c.f("gf_Wp"); pp.g_bp = c.f("gf_bp");
     pp.g_W3 = c.f("g_W3"); pp.g_b3 = c.f("g_b3"); pp.g_U = c.f("g_U"); pp.g_kappa = c.f("g_kappa");
     pp.g_lam = c.f("g_lam"); pp.g_sigma = c.f("g_sigma");
+    pp.g_xi = self ? c.f("g_xi") : nullptr;
     prof_mark(1, 0, st);
     nl = enf_launch_pairs_bwd_simt(st, d, pp);
     prof_mark(1, 1, st);
@@ -751,12 +831,23 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
   c.gemm((int)BZ, d, Hd, enf_mat(c.f("dv0"), Hd), enf_mat(w->wv, 1, Hd), enf_mat(c.f("dahat"), d), opt_acc());
   c.launches += enf_launch_ln_bwd(st, c.f("dahat"), c.f("acore"), c.f("arstd"), w->ln_attn_g, nullptr, BZ, d, c.f("da0"),
                                   wg ? G("ln_attn_g") : nullptr, wg ? G("ln_attn_b") : nullptr, 0);
-  if (wg) {
-    c.gemm(L, d, (int)BZ, enf_mat(a, 1, L), enf_mat(c.f("da0"), d), enf_mat(G("stem_w"), d), opt_acc());
-    colsum(c.f("da0"), BZ, d, G("stem_b"));
+  if (self) c.launches += enf_launch_add(st, c.f("da0"), c.f("da0"), c.f("da0x"), BZ * d);      // + the two residual paths
+  if (no_stem) {
+    if (cudaMemcpyAsync(da, c.f("da0"), BZ * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(ENF_ERR_CUDA, "copy of da failed");
+  } else {
+    if (wg) {
+      c.gemm(L, d, (int)BZ, enf_mat(a, 1, L), enf_mat(c.f("da0"), d), enf_mat(G("stem_w"), d), opt_acc());
+      colsum(c.f("da0"), BZ, d, G("stem_b"));
+    }
+    c.gemm((int)BZ, L, d, enf_mat(c.f("da0"), d), enf_mat(w->stem_w, 1, d), enf_mat(da, L));
   }
-  c.gemm((int)BZ, L, d, enf_mat(c.f("da0"), d), enf_mat(w->stem_w, 1, d), enf_mat(da, L));
-  c.launches += enf_launch_latent_record_bwd(st, D, p, c.f("g_lam"), dp);
+  if (self) {      // the poses in both roles: latent side through Lam, query side through xi
+    c.launches += enf_launch_pose_record_bwd(st, D.invariant_kind, D.Dx, rl.P, rl.I, rl.win_kind, BZ, p, c.f("g_lam"), dp);
+    c.launches += enf_launch_pose_features_bwd(st, D.invariant_kind, D.Dx, rl.P, BZ, p, c.f("g_xi"), dp);
+  } else {
+    c.launches += enf_launch_latent_record_bwd(st, D, p, c.f("g_lam"), dp);
+  }
   if (dsigma) {
     if (cudaMemcpyAsync(dsigma, c.f("g_sigma"), BZ * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return fail(ENF_ERR_CUDA, "copy of dsigma failed");
@@ -767,9 +858,11 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     // tail fold: W_A = P1 fb_w1, b_A = b1 fb_w1 + fb_b1, P1 = blockdiag(M2g) wo, b1 = tile(c2g) wo + bo
     // every product of this group reads only finished accumulators (gf_*) and weights, and writes its own leaf
     c.begin_group();
-    c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), 1, Hd), enf_mat(c.f("gf_W_A"), Hd), enf_mat(G("fb_w1"), Hd));
-    c.gemm(Hd, Hd, Hd, enf_mat(c.f("gf_W_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("dP1"), Hd));
-    c.gemm(1, Hd, Hd, enf_mat(c.f("gf_b_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("db1"), Hd));
+    if (!self) {
+      c.gemm(Hd, Hd, Hd, enf_mat(c.f("P1"), 1, Hd), enf_mat(c.f("gf_W_A"), Hd), enf_mat(G("fb_w1"), Hd));
+      c.gemm(Hd, Hd, Hd, enf_mat(c.f("gf_W_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("dP1"), Hd));
+      c.gemm(1, Hd, Hd, enf_mat(c.f("gf_b_A"), Hd), enf_mat(w->fb_w1, 1, Hd), enf_mat(c.f("db1"), Hd));
+    }
     c.gemm(d, d, Hd, enf_mat(c.f("gf_A_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_wf"), d));
     c.gemm(d, Hd, d, enf_mat(w->q_wf, 1, d), enf_mat(c.f("gf_A_q"), Hd), enf_mat(G("wq"), Hd));
     c.gemm(1, d, Hd, enf_mat(c.f("gf_c_q"), Hd), enf_mat(w->wq, 1, Hd), enf_mat(G("q_bf"), d));
@@ -778,6 +871,19 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     c.gemm(1, d, d, enf_mat(c.f("gf_bp"), d), enf_mat(w->fv_w1, 1, d), enf_mat(G("v_bf"), d));
     c.gemm(1, d, 2 * Hd, enf_mat(c.f("gf_b2g"), 2 * Hd), enf_mat(w->fv_w2, 1, 2 * Hd), enf_mat(G("fv_beta"), d));
     c.end_group();
+    if (self) {
+      // P1_h = M2g wo_h (d, d per head), b1 = bo + sum_h c2g wo_h
+      const int64_t hb = (int64_t)d * d;
+      EnfGemmOpts ob; ob.batch = H;
+      c.gemm(d, d, d, enf_mat(c.f("M2g"), 1, d), enf_mat(c.f("dP1"), d, 1, hb), enf_mat(G("wo"), d, 1, hb), ob);
+      for (int h = 0; h < H; ++h) c.launches += enf_launch_add_outer(st, G("wo") + h * hb, d, c.f("c2g"), c.f("db1"), d, d);
+      c.begin_group();
+      for (int h = 0; h < H; ++h) {
+        c.gemm(d, d, d, enf_mat(c.f("dP1") + h * hb, d), enf_mat(w->wo + h * hb, 1, d), enf_mat(c.f("gf_M2g"), d), opt_acc());
+        c.gemm(1, d, d, enf_mat(c.f("db1"), d), enf_mat(w->wo + h * hb, 1, d), enf_mat(c.f("gf_c2g"), d), opt_acc());
+      }
+      c.end_group();
+    } else {
     c.launches += enf_launch_add_outer(st, G("fb_w1"), Hd, c.f("b1"), c.f("gf_b_A"), Hd, Hd);
     {
       const int64_t hb = (int64_t)d * Hd;        // one head's block of rows of wo / P1
@@ -791,6 +897,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
       }
       c.end_group();
     }
+    }   // !self
     c.launches += enf_launch_add_outer(st, G("wq"), Hd, w->q_bf, c.f("gf_c_q"), d, Hd);
     c.launches += enf_launch_add_outer(st, G("fv_w1"), d, w->v_bf, c.f("gf_bp"), d, d);
     c.launches += enf_launch_rowdot(st, w->fv_w2, c.f("gf_W2g"), G("fv_g"), d, 2 * Hd);
@@ -813,7 +920,7 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
       else if (!strcmp(nm, "fv_b2")) src = c.f("gf_b2g");
       else if (!strcmp(nm, "mx_b2")) src = c.f("gf_c2g");
       else if (!strcmp(nm, "bo")) src = c.f("db1");
-      else if (!strcmp(nm, "fb_b1")) src = c.f("gf_b_A");
+      else if (!strcmp(nm, "fb_b1") && !self) src = c.f("gf_b_A");
       t.src[i] = src; t.dst[i] = dst[i]; t.n[i] = (int)n[i];
       if ((int)n[i] > maxn) maxn = (int)n[i];
     }

@@ -130,7 +130,7 @@ int enf_launch_latent_record_bwd(cudaStream_t st, const EnfDesc& d, const float*
 int enf_launch_pose_features(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, float* xi);
 int enf_launch_pose_features_bwd(cudaStream_t st, int kind, int Dx, int P, int64_t total, const float* p, const float* dxi, float* dp);   // dp +=
 int enf_launch_pose_record(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, float* lam);
-int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, const float* dlam, float* dp);   // dp =
+int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int win_kind, int64_t total, const float* p, const float* dlam, float* dp);   // dp =
 int enf_launch_weff(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
                     float* Weff, float* beff, int round_weff = 0);
 int enf_launch_weff_bwd(cudaStream_t st, const EnfDesc& d, const float* W2g, const float* b2g, const float* v0,
@@ -140,6 +140,10 @@ int enf_launch_rowdot(cudaStream_t st, const float* A, const float* Bm, float* o
 int enf_launch_mul_rows(cudaStream_t st, float* out, const float* A, const float* g, int rows, int cols,
                         const float* add_outer_u, const float* add_outer_v);
 int enf_launch_transpose(cudaStream_t st, const float* in, float* out, int rows, int cols, int batch);
+// out = a + b ; pre = a + b, out = gelu(pre) ; out (+)= g * gelu'(pre)
+int enf_launch_add(cudaStream_t st, float* out, const float* a, const float* b, int64_t n);
+int enf_launch_add_gelu(cudaStream_t st, float* pre, float* out, const float* a, const float* b, int64_t n);
+int enf_launch_mul_gelu_grad(cudaStream_t st, float* out, const float* g, const float* pre, int64_t n);
 
 int enf_launch_weight_image(cudaStream_t st, const float* Wt, void* img, float* cw, int N, int K, int batch, int residual = 0);
 // image of W^T built from the untransposed W [batch][K][N] (no fp32 transpose pass)
@@ -166,6 +170,7 @@ struct EnfPairParams {
   const float* slog;                         // [B,Z,C,H] logits saved by the tensor-core forward (or null: recompute)
   float* g_q_w1; float* g_q_b1; float* g_v_w1; float* g_v_b1; float* g_Wp; float* g_bp;   // accumulated (atomics)
   float* g_W3; float* g_b3; float* g_U; float* g_kappa; float* g_lam; float* g_sigma;      // per-latent, accumulated
+  float* g_xi;                               // [B,C,8] cotangent of the query records (self-attention blocks only), else null
 };
 int enf_launch_pairs_fwd_simt(cudaStream_t st, int d, const EnfPairParams& p);
 int enf_launch_pairs_bwd_simt(cudaStream_t st, int d, const EnfPairParams& p);

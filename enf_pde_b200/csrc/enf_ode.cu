@@ -605,7 +605,7 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
                                                                            W + Y.xi, W + Y.g_lam);
   ode_inv_bwd_xi_kernel<<<nblocks(d.m * ENF_F_XI, 256), 256, 0, st>>>(d.I, d.Z, d.row_kind, d.nsq, d.m * ENF_F_XI, W + Y.inv, W + Y.g_inv,
                                                                       W + Y.lam, W + Y.xi, W + Y.g_xi);
-  R.launches += enf_launch_pose_record_bwd(st, d.kind, d.Dx, d.P, d.I, d.m, p, W + Y.g_lam, gp);
+  R.launches += enf_launch_pose_record_bwd(st, d.kind, d.Dx, d.P, d.I, ENF_WIN_NONE, d.m, p, W + Y.g_lam, gp);
   R.launches += enf_launch_pose_features_bwd(st, d.kind, d.Dx, d.P, d.m, p, W + Y.g_xi, gp);
   ode_add_gpe_kernel<<<nblocks(d.m, 256), 256, 0, st>>>(d.P, d.npos, d.nori, d.m, W + Y.gpe, gp);
   R.launches += 8;

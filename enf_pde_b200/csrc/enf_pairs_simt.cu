@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
   }
   __syncthreads();
 
+  float gxi[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // threads < TM: cotangent of the row's query record (P.g_xi only)
   for (int z = 0; z < P.Z; ++z) {
     const int64_t bz = (int64_t)b * P.Z + z;
     pair_chain_common<D, true>(P, S, bz, Gq, H1q, Gv, H1v, Tpre, That, Ws, MQ, MV, bufM);
@@ -593,6 +594,21 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
 #pragma unroll
       for (int r = 0; r < ENF_R_LAM; ++r) S.dq[t * 8 + r] = dq[r];
       S.dsig[t] = dsg;
+      if (P.g_xi) {
+        // cotangent of this row's QUERY record (self-attention: the queries are poses too): DOT rows are bilinear
+        // in (Lam, xi); squared-distance rows (and the non-periodic window row) are sum_f (Lam_f - xi_f)^2
+        const int nrows = P.I + (P.win_row >= 0 ? 1 : 0);
+        for (int r = 0; r < nrows; ++r) {
+          const float* L = S.lam + r * ENF_F_XI;
+          const bool sq = r < P.I ? (P.row_kind != ENF_ROW_DOT) : (P.win_kind == ENF_WIN_NP);
+          if (sq) {
+            for (int f = 0; f < 3; ++f) if (f < P.nsq) gxi[f] = fmaf(-2.f * dq[r], L[f] - S.xi[t * 8 + f], gxi[f]);
+          } else {
+#pragma unroll
+            for (int f = 0; f < 8; ++f) gxi[f] = fmaf(dq[r], L[f], gxi[f]);
+          }
+        }
+      }
     }
     __syncthreads();
     if (tid < ENF_LAM_SIZE) {
@@ -606,6 +622,11 @@ __global__ void __launch_bounds__(NT, 1) pairs_bwd_kernel(EnfPairParams P) {
       atomicAdd(P.g_sigma + bz, v);
     }
     __syncthreads();
+  }
+  if (P.g_xi && tid < nv) {
+    float* o = P.g_xi + ((int64_t)b * P.C + c0 + tid) * ENF_F_XI;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) o[f] = gxi[f];
   }
 }
 

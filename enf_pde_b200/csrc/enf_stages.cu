@@ -100,8 +100,8 @@ __global__ void latent_record_kernel(int kind, int Dx, int P, int I, int64_t tot
       float o0, o1; sincosf(pr[2], &o1, &o0);
       L[0][0] = o0; L[0][1] = o1; L[0][2] = -(pr[0] * o0 + pr[1] * o1);
       L[1][0] = -o1; L[1][1] = o0; L[1][2] = pr[0] * o1 - pr[1] * o0;
-      if (sa) { L[2][3] = o0; L[2][4] = o1; }        // Ponita2D's third invariant (no window row: I = 3 fills the slot)
-      else { L[W][0] = pr[0]; L[W][1] = pr[1]; }
+      if (sa) { L[2][3] = o0; L[2][4] = o1; }        // Ponita2D's third invariant (then I = 3 and the window row is row 3)
+      L[W][0] = pr[0]; L[W][1] = pr[1];
     } break;
     case ENF_INV_POLAR_PERIODIC:
       sph_unit(pr[0], pr[1], L[0]);
@@ -264,6 +264,20 @@ __global__ void query_features_bwd_kernel(int kind, int Dx, int P, int64_t total
     } break;
   }
   for (int i = 0; i < P; ++i) dp[t * P + i] += g[i];
+}
+
+// ---- elementwise glue of the self-attention blocks (residual adds, the gelu between blocks; nef.py:62-64, 225-226) ------
+__global__ void add_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = a[t] + b[t];
+}
+__global__ void add_gelu_kernel(float* __restrict__ pre, float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { const float v = a[t] + b[t]; pre[t] = v; out[t] = enf_gelu(v); }
+}
+__global__ void mul_gelu_grad_kernel(float* __restrict__ out, const float* __restrict__ g, const float* __restrict__ pre, int64_t n) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = g[t] * enf_gelu_grad(pre[t]);
 }
 
 // ---- LayerNorm rows (flax: eps 1e-6, var = E[x^2]-E[x]^2), optional gelu on the input --------------
@@ -707,6 +721,19 @@ int enf_launch_ln_bwd(cudaStream_t st, const float* dy, const float* core, const
   return 1;
 }
 
+int enf_launch_add(cudaStream_t st, float* out, const float* a, const float* b, int64_t n) {
+  add_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, a, b, n);
+  return 1;
+}
+int enf_launch_add_gelu(cudaStream_t st, float* pre, float* out, const float* a, const float* b, int64_t n) {
+  add_gelu_kernel<<<blocks_for(n, 256), 256, 0, st>>>(pre, out, a, b, n);
+  return 1;
+}
+int enf_launch_mul_gelu_grad(cudaStream_t st, float* out, const float* g, const float* pre, int64_t n) {
+  mul_gelu_grad_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, g, pre, n);
+  return 1;
+}
+
 int enf_launch_query_features(cudaStream_t st, const EnfDesc& d, const float* x, int64_t xbs, int Bx, float* xi) {
   int64_t total = (int64_t)Bx * d.C;
   query_features_kernel<<<blocks_for(total, 256), 256, 0, st>>>(d.invariant_kind, d.Dx, d.C, total, x, xbs, xi, d.Dx, 0);
@@ -727,8 +754,8 @@ int enf_launch_pose_record(cudaStream_t st, int kind, int Dx, int P, int I, int6
   latent_record_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, I, total, p, lam, 1);
   return 1;
 }
-int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int64_t total, const float* p, const float* dlam, float* dp) {
-  latent_record_bwd_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, I, ENF_WIN_NONE, total, p, dlam, dp, 1);
+int enf_launch_pose_record_bwd(cudaStream_t st, int kind, int Dx, int P, int I, int win_kind, int64_t total, const float* p, const float* dlam, float* dp) {
+  latent_record_bwd_kernel<<<blocks_for(total, 128), 128, 0, st>>>(kind, Dx, P, I, win_kind, total, p, dlam, dp, 1);
   return 1;
 }
 

@@ -42,11 +42,12 @@ def _unflatten(flat):
     return out
 
 
-def params_to_leaves(variables) -> list:
-    """Flax-style tree -> the 46 leaves in EnfWeights order."""
+def params_to_leaves(variables, paths=None) -> list:
+    """Flax-style tree -> the 46 leaves in EnfWeights order (None for leaves the call does not use, see _lib.leaf_paths)."""
     flat = _flatten(variables["params"] if "params" in variables else variables)
+    paths = _lib.LEAF_PATHS if paths is None else paths
     try:
-        return [flat[_lib.LEAF_PATHS[n]] for n in _lib.LEAVES]
+        return [None if paths[n] is None else flat[paths[n]] for n in _lib.LEAVES]
     except KeyError as e:
         raise KeyError(f"parameter tree is missing {e}; expected the tree produced by nef.init") from None
 
@@ -88,9 +89,11 @@ class _XAttnFunction(torch.autograd.Function):
             ctx.n_extra = 1
             ctx.p_shape = tuple(p.shape)
             p = torch.stack([_as_f32(p, "p"), _as_f32(p_mask, "relu_mask_pose")]).contiguous()
-        x = _as_f32(x, "x"); p = _as_f32(p, "p"); a = _as_f32(a, "a")
+        p = _as_f32(p, "p"); a = _as_f32(a, "a")
+        x = p if x is None else _as_f32(x, "x")          # latent self-attention step: the queries are the poses
         sigma = None if sigma is None else _as_f32(sigma, "gaussian_window_size")
-        leaves = [_as_f32(t, n) for t, n in zip(leaves, _lib.LEAVES)]
+        ctx.leaf_mask = [t is not None for t in leaves]
+        leaves = [None if t is None else _as_f32(t, n) for t, n in zip(leaves, _lib.LEAVES)]
         nbytes = lib.enf_xattn_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             raise _lib.EnfLibraryError("bad problem description: " + lib.enf_last_error().decode())
@@ -99,7 +102,7 @@ class _XAttnFunction(torch.autograd.Function):
         # allocation at the same address can never pass for this forward
         weakref.finalize(ws, lib.enf_workspace_release, ctypes.c_void_p(ws.data_ptr()))
         out_dtype = torch.bfloat16 if desc.flags & _lib.FLAG_OUT_BF16 else torch.float32
-        out = torch.empty(desc.B, desc.C, desc.O, dtype=out_dtype, device=x.device)
+        out = torch.empty(desc.B, desc.C, desc.O, dtype=out_dtype, device=p.device)
         w = _weights_struct(leaves)
         stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         xbs = 0 if x_shared else desc.C * desc.Dx
@@ -109,7 +112,7 @@ class _XAttnFunction(torch.autograd.Function):
         _lib.check(rc, "enf_xattn_fwd")
         ctx.desc_kw, ctx.xbs, ctx.ws, ctx.nbytes = desc_kw, xbs, ws, nbytes
         ctx.has_sigma = sigma is not None
-        ctx.save_for_backward(x, p, a, *([sigma] if sigma is not None else []), *leaves)
+        ctx.save_for_backward(x, p, a, *([sigma] if sigma is not None else []), *[t for t in leaves if t is not None])
         ctx.launches_fwd = lib.enf_last_launch_count()
         _XAttnFunction.last_launches = [ctx.launches_fwd, 0]
         ctx.forward_only = bool(desc_kw.get("flags", 0) & _lib.FLAG_FORWARD_ONLY)
@@ -125,11 +128,12 @@ class _XAttnFunction(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         x, p, a = saved[:3]
         sigma = saved[3] if ctx.has_sigma else None
-        leaves = saved[4:] if ctx.has_sigma else saved[3:]
+        it = iter(saved[4:] if ctx.has_sigma else saved[3:])
+        leaves = [next(it) if used else None for used in ctx.leaf_mask]
         desc = _lib.EnfDesc(**ctx.desc_kw)
         d_out = _as_f32(d_out, "d_out")
         need_w = any(ctx.needs_input_grad[5:5 + len(leaves)])
-        grads = [torch.empty_like(t) for t in leaves] if need_w else None
+        grads = [None if t is None else torch.empty_like(t) for t in leaves] if need_w else None
         dp = torch.empty(ctx.p_shape, dtype=p.dtype, device=p.device) if ctx.n_extra else torch.empty_like(p)
         da = torch.empty_like(a)
         dsigma = torch.empty_like(sigma) if sigma is not None else None
@@ -162,9 +166,10 @@ class EquivariantCrossAttentionNeF:
                  condition_value_transform: bool = True, use_gaussian_window: bool = True,
                  precision: str = "fp32", recompute: bool = False, chunk_fields: int = 0,
                  workspace_cap_bytes: Optional[int] = None, out_bf16: bool = False):
-        if num_layers != 0:
-            raise NotImplementedError("latent self-attention blocks (num_layers > 0) are not on the accelerated path; "
-                                      "every shipped config of the reference uses num_layers: 0")
+        if num_layers < 0:
+            raise ValueError("num_layers must be >= 0")
+        if num_layers > 0 and self_attn_invariant is None:
+            raise ValueError("num_layers > 0 needs the self-attention invariant (get_sa_invariant)")
         if embedding_type != "rff":
             raise ValueError(f"Unknown embedding type: {embedding_type}." if embedding_type not in ("ffn", "polynomial")
                              else f"embedding_type '{embedding_type}' is not on the accelerated path (configs use 'rff')")
@@ -196,6 +201,8 @@ class EquivariantCrossAttentionNeF:
         if a.shape[-1] != L:
             raise ValueError(f"a has latent_dim {a.shape[-1]}, module was built with {L}")
 
+        fq, fv = self.embedding_freq_multiplier
+
         def normal(shape, std):
             return torch.randn(shape, generator=g) * std
 
@@ -211,15 +218,25 @@ class EquivariantCrossAttentionNeF:
             return {"Dense_0": dense(n_in, n_hid), "LayerNorm_0": {"scale": torch.ones(n_hid), "bias": torch.zeros(n_hid)},
                     "Dense_1": dense(n_hid, n_out)}
 
-        def rff(std):                # rff.py:35-40,55-60,83
+        def rff(std, I=I):           # rff.py:35-40,55-60,83
             return {"encoding": {"coefficients": normal((I, d // 2), std)},
                     "layers_0": {"linear": {"kernel": normal((d, d), math.sqrt(2.0 / d)), "bias": normal((d,), 1e-6)}},
                     "linear_final": {"kernel": (torch.rand(d, d, generator=g) * 2 - 1) * math.sqrt(6.0 / d),
                                      "bias": normal((d,), 1e-6)}}
 
         fq, fv = self.embedding_freq_multiplier
+        def self_block():            # residual=True, project_heads=True (equivariant_cross_attention_nef.py:159-167, 35-37, 68-70)
+            Is = 3 if self.self_attn_invariant.invariant_type == "ponita" else self.self_attn_invariant.dim
+            return {"layer_norm_attn": {"scale": torch.ones(d), "bias": torch.zeros(d)},
+                    "attn": {"invariant_embedding_query": rff(fq, Is), "invariant_embedding_value": rff(fv, Is),
+                             "inv_emb_to_q": dense(d, H * d), "a_to_k": dense(d, H * d), "a_to_v": dense(d, H * d),
+                             "inv_emb_to_v": ffn(d, d, 2 * H * d), "inv_emb_cond_mixer": ffn(d, d, d),
+                             "out_proj": dense(H * d, d)},
+                    "pointwise_ffn": ffn(d, d, d)}
+
         tree = {
             "latent_stem": dense(L, d),
+            **{f"self_attention_blocks_{i}": self_block() for i in range(self.num_layers)},
             "cross_attention_blocks_0": {
                 "layer_norm_attn": {"scale": torch.ones(d), "bias": torch.zeros(d)},
                 "attn": {
@@ -257,7 +274,26 @@ class EquivariantCrossAttentionNeF:
         desc = dict(B=B, C=C, Z=Z, d=self.num_hidden, H=self.num_heads, L=self.latent_dim, O=self.num_out, Dx=Dx,
                     invariant_kind=_lib.INVARIANT_KINDS[inv.invariant_type], use_window=int(self.use_gaussian_window),
                     precision=self.precision, flags=0)
-        leaves = params_to_leaves(variables)
+        if self.num_layers > 0:
+            # latent self-attention steps first (equivariant_cross_attention_nef.py:223-226): a <- gelu(a + block_i(p, p, a)); each is one
+            # call of the same C entry points with ENF_FLAG_SELF_BLOCK; the first applies latent_stem, the decode call below none
+            if relu_mask_pose is not None or self.recompute:
+                raise NotImplementedError("relu_mask_pose / recompute are not combined with num_layers > 0")
+            if self.self_attn_invariant.invariant_type != inv.invariant_type:
+                raise ValueError("self- and cross-attention invariants must come from the same cfg.nef.invariant_type")
+            grad_on = torch.is_grad_enabled()
+            for i in range(self.num_layers):
+                sdesc = dict(desc, C=Z, O=self.num_hidden, L=(self.latent_dim if i == 0 else self.num_hidden),
+                             flags=_lib.FLAG_SELF_BLOCK | (0 if i == 0 else _lib.FLAG_NO_STEM))
+                sl = params_to_leaves(variables, _lib.leaf_paths(f"self_attention_blocks_{i}", with_stem=(i == 0), with_mlp=False))
+                if not (grad_on and any(t is not None and t.requires_grad for t in (p, a, sigma, *sl))):
+                    sdesc["flags"] |= _lib.FLAG_FORWARD_ONLY
+                a = _XAttnFunction.apply((sdesc, False), None, p, a, sigma, *sl)
+            desc["L"] = self.num_hidden
+            desc["flags"] |= _lib.FLAG_NO_STEM
+            leaves = params_to_leaves(variables, _lib.leaf_paths("cross_attention_blocks_0", with_stem=False, with_mlp=True))
+        else:
+            leaves = params_to_leaves(variables)
         if relu_mask_pose is not None:
             if tuple(relu_mask_pose.shape) != tuple(p.shape):
                 raise ValueError("relu_mask_pose must have the shape of p")

@@ -77,7 +77,19 @@ enum EnfFlags {
    * difference of enf_xattn_bwd gradients along a latent direction, and freezing the pattern at the expansion point makes that
    * difference differentiate one linear branch of the relus -- exactly what reverse-over-reverse autodiff computes (relu'' = 0;
    * a plain finite difference would add the curvature concentrated at the kinks).  dp[B,Z,P] is the gradient w.r.t. p[0]. */
-  ENF_FLAG_FROZEN_RELU = 16
+  ENF_FLAG_FROZEN_RELU = 16,
+  /* The call is one LATENT SELF-ATTENTION step of the NeF (num_layers > 0: equivariant_cross_attention_nef.py:159-167, 223-226;
+   * EquivariantCrossAttentionBlock with residual = True, project_heads = True, :44-67), not the cross-attention decode:
+   *     out = gelu(a' + FFN(a' + out_proj(attn(x = p, p, LayerNorm(a')))))        a' = latent_stem(a) (or a, ENF_FLAG_NO_STEM)
+   * The queries are the latent poses themselves (C must equal Z; `x` is ignored and may be NULL), the invariant is the
+   * SELF-attention variant (get_sa_invariant: ENF_INV_PONITA means Ponita2D, 3 invariants), O must equal d and `out` is the
+   * next hidden latent state [B,Z,d].  Weight leaves of EnfWeights with this flag: wo is (H*d, d), bo (d), the pointwise FFN
+   * fb_* is d -> d -> d, m0_* / m1_* / m2_* are unused (may be NULL).  dp of enf_xattn_bwd carries the gradient through both roles
+   * of the poses (query and latent).  Always runs the fp32 kernels (B*Z*Z pairs: <= 2 % of a decode call). */
+  ENF_FLAG_SELF_BLOCK = 32,
+  /* `a` is already the hidden latent state [B,Z,d] (the output of a self-attention step): latent_stem is skipped, L must
+   * equal d, stem_w / stem_b are unused (may be NULL), da is [B,Z,d]. */
+  ENF_FLAG_NO_STEM = 64
 };
 
 enum EnfError {

@@ -11,8 +11,10 @@ from oracle import enf_ref as R
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names():
-    return sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "ref_*.npz")))
+def golden_names(sa=False):
+    """fixtures of the cross-attention path (num_layers = 0); sa=True: those with latent self-attention blocks."""
+    names = sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "ref_*.npz")))
+    return [n for n in names if n.startswith("sa") == sa]
 
 
 def load_golden(name, dtype=torch.float64):

@@ -19,10 +19,11 @@ TOL = TOL_FP32
 def _nef_for(cfg, precision="fp32"):
     import enf_pde_b200 as E
     import types
-    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg.invariant_type, num_in=cfg.num_in))
+    ns = types.SimpleNamespace(invariant_type=cfg.invariant_type, num_in=cfg.num_in)
+    inv = E.get_ca_invariant(ns)
     return E.EquivariantCrossAttentionNeF(
-        num_hidden=cfg.num_hidden, num_heads=cfg.num_heads, num_layers=0, num_out=cfg.num_out, latent_dim=cfg.latent_dim,
-        cross_attn_invariant=inv, self_attn_invariant=inv, embedding_type="rff",
+        num_hidden=cfg.num_hidden, num_heads=cfg.num_heads, num_layers=cfg.num_layers, num_out=cfg.num_out, latent_dim=cfg.latent_dim,
+        cross_attn_invariant=inv, self_attn_invariant=E.get_sa_invariant(ns), embedding_type="rff",
         embedding_freq_multiplier=cfg.embedding_freq_multiplier, condition_value_transform=True,
         use_gaussian_window=cfg.use_gaussian_window, precision=precision)
 
@@ -66,6 +67,36 @@ def test_golden_through_public_api(name):
     errs, worst, ok = compare(chk, out, dp, da, ds, R.tree_flatten(g["params"]), TOL, use_window=cfg.use_gaussian_window)
     assert ok, (errs, worst, chk.used_allowance)
     assert rms_err(out, rec["out"]) < TOL and rms_err(dp, chk.ref[2]) < 10 * TOL and rms_err(da, chk.ref[3]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(sa=True))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_self_attention_blocks_against_reference_fixtures(name, precision):
+    """num_layers > 0: latent self-attention steps (ENF_FLAG_SELF_BLOCK, fp32 kernels, poses in both roles) followed by
+    the cross-attention decode without stem, against the reference's own outputs and the oracle's gradients.  In tensor-core
+    precision mode only the decode call changes kernels (d = 16 fixtures: fp32 kernels either way)."""
+    cfg, params, _, rec = load_golden(name)
+    case = (params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
+    chk = Checker(cfg, case)
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, *case, precision=precision)
+    assert rel_err(out, rec["out"]) < TOL
+    errs, worst, ok = compare(chk, out, dp, da, ds, R.tree_flatten(g["params"]), TOL, use_window=cfg.use_gaussian_window)
+    print(name, precision, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst, chk.used_allowance)
+    assert ok, (errs, worst, chk.used_allowance)
+
+
+def test_self_attention_blocks_at_real_hidden_size():
+    """two self-attention steps + decode at the Navier-Stokes sizes (d = 128, H = 2, 64 latents; reduced queries): the decode call runs
+    the tcgen05 kernels on a hidden latent state produced by the fp32 self-attention steps."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1), num_layers=2)
+    data = make_case(cfg, 2, 150, 64, seed=11)
+    for precision, tol, tol_leaf in (("fp32", TOL_FP32, TOL_FP32), ("bf16", TOL_TC, TOL_TC_LEAF)):
+        chk = Checker(cfg, data)
+        out, g, dp, da, ds = _api_fwd_bwd(cfg, *data, precision=precision)
+        errs, worst, ok = compare(chk, out, dp, da, ds, R.tree_flatten(g["params"]), tol, tol_leaf)
+        print(precision, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst, chk.used_allowance)
+        assert ok, (precision, errs, worst)
 
 
 CASES = [
@@ -166,8 +197,8 @@ def test_error_paths():
         nef.apply(P, f(x), f(p)[:, :, :1], f(a), f(sigma))         # wrong pose width
     with pytest.raises(RuntimeError):
         nef.apply(P, x.float(), f(p), f(a), f(sigma))              # CPU tensor: no CPU path
-    with pytest.raises(NotImplementedError):
-        E.EquivariantCrossAttentionNeF(32, 2, 1, 1, 8, nef.cross_attn_invariant)   # num_layers > 0
+    with pytest.raises(ValueError):
+        E.EquivariantCrossAttentionNeF(32, 2, 1, 1, 8, nef.cross_attn_invariant)   # num_layers > 0 needs the self-attention invariant
 
 
 TOL_BF16 = TOL_TC     # BASELINE.json's bf16/tf32 bucket

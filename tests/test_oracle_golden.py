@@ -7,7 +7,7 @@ from oracle import enf_ref as R
 from helpers import golden_names, load_golden, rel_err
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names(sa=True))
 def test_forward_matches_reference_source(name):
     cfg, params, _, rec = load_golden(name)
     out = R.nef_apply(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"])
@@ -15,7 +15,7 @@ def test_forward_matches_reference_source(name):
     assert rel_err(out, rec["out"]) < 1e-11        # both float64
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names(sa=True))
 def test_autograd_matches_reference_finite_differences(name):
     cfg, params, direction, rec = load_golden(name)
     out, dtheta, dp, da, dsigma = R.fwd_bwd(cfg, params, rec["x"], rec["p"], rec["a"], rec["sigma"], rec["cot"])
@@ -34,8 +34,9 @@ def test_autograd_matches_reference_finite_differences(name):
             assert float(g.abs().max()) == 0.0
 
 
-def test_param_tree_names_match_reference_module_structure():
-    cfg, params, _, _ = load_golden("rel_pos_periodic")
+@pytest.mark.parametrize("name", ["rel_pos_periodic", "sa2_ponita", "sa1_latitude_periodic"])
+def test_param_tree_names_match_reference_module_structure(name):
+    cfg, params, _, _ = load_golden(name)
     ours = R.tree_flatten(R.nef_init(cfg)["params"])
     theirs = R.tree_flatten(params["params"])
     assert sorted(ours) == sorted(theirs)
