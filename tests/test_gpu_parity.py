@@ -293,11 +293,11 @@ def test_forward_only_matches_training_forward(precision):
     assert rc == -7, lib.enf_last_error()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 4e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_TC)])
 def test_first_order_inner_loop_against_oracle(precision, tol):
     """enf_pde_b200.inner_loop (first-order part) vs the oracle's restatement of PDETrainer.inner_loop
     (pde_trainer.py:122-235): 3 Meta-SGD steps on per-step query subsets, per-key learning rates, gradients x B, the
-    latents-only backward of the C ABI (dW = NULL).  Tolerances: twice the single-call buckets (errors compound over steps)."""
+    latents-only backward of the C ABI (dW = NULL).  Tolerances: the single-call buckets (measured after 3 steps: 1e-5 / 1.3e-3)."""
     import enf_pde_b200 as E
     cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="ponita",
                       embedding_freq_multiplier=(0.05, 0.05))
