@@ -212,3 +212,21 @@ def test_ode_host_mirror_matches_reference_structure():
     assert float(ours["ponita/readout_vec_rel/kernel"].abs().max()) < 1e-2        # variance_scaling(1e-6)
     with pytest.raises(NotImplementedError):
         E.PonitaODEGen(16, 2, 4, 1, inv, 8, 3, 2, kernel_size=0.5)
+
+
+def test_self_block_flags_are_validated():
+    """ENF_FLAG_SELF_BLOCK / ENF_FLAG_NO_STEM (latent self-attention steps): shape contract checked without a GPU."""
+    lib = E.load_library()
+    ok = dict(B=2, C=8, Z=8, d=32, H=2, L=6, O=32, Dx=2, invariant_kind=4, use_window=1, precision=1, flags=_lib.FLAG_SELF_BLOCK)
+    size = lambda **o: lib.enf_xattn_workspace_bytes(ctypes.byref(_lib.EnfDesc(**{**ok, **o})))
+    assert size() > 0
+    assert _lib.dispatch(_lib.EnfDesc(**ok)) == (False, False)                       # always the fp32 kernels
+    assert size(C=9) == 0 and b"C == Z" in lib.enf_last_error()                      # the queries are the latents
+    assert size(O=1) == 0
+    assert size(flags=_lib.FLAG_SELF_BLOCK | _lib.FLAG_NO_STEM) == 0 and b"L must equal d" in lib.enf_last_error()
+    assert size(flags=_lib.FLAG_SELF_BLOCK | _lib.FLAG_NO_STEM, L=32) > 0
+    assert size(flags=_lib.FLAG_SELF_BLOCK | _lib.FLAG_RECOMPUTE) == 0
+    assert size(flags=_lib.FLAG_NO_STEM, C=100, O=1, L=32) > 0                      # the decode call after self-attention steps
+    # leaves a self-attention step does not use may be NULL; the ones it uses may not
+    paths = _lib.leaf_paths("self_attention_blocks_1", with_stem=False, with_mlp=False)
+    assert paths["stem_w"] is None and paths["m2_w"] is None and paths["wo"] == "self_attention_blocks_1/attn/out_proj/kernel"
