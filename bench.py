@@ -394,7 +394,8 @@ def main():
     inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
     nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True,
                                          cfg["window"], precision=args.precision,
-                                         recompute=args.recompute, chunk_fields=args.chunk_fields, out_bf16=args.out_bf16)
+                                         recompute=args.recompute, chunk_fields=args.chunk_fields, out_bf16=args.out_bf16,
+                                         forward_chunk_fields=(args.chunk_fields or 96) if args.forward_only else 0)
     gen = torch.Generator().manual_seed(1234 + rank)
     p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])
     p_h = p_h + 0.02 * torch.randn(p_h.shape, generator=gen)
@@ -522,6 +523,7 @@ def main():
     I = inv.dim
     f_alg, f_ref = flops_per_pair(cfg, I)
     pairs = B * C * Z
+    B_launch = min(B, nef.forward_chunk_fields) if (args.forward_only and nef.forward_chunk_fields > 0) else B   # fields per pair-kernel launch
     desc = _lib.EnfDesc(B=B, C=C, Z=Z, d=cfg["d"], H=cfg["H"], L=cfg["L"], O=cfg["O"], Dx=cfg["num_in"],
                         invariant_kind=_lib.INVARIANT_KINDS[cfg["invariant_type"]], use_window=int(cfg["window"]),
                         precision=nef.precision, flags=(_lib.FLAG_FORWARD_ONLY if args.forward_only else 0))
@@ -534,7 +536,7 @@ def main():
     dom_is_bwd = not args.forward_only
     dom_tc = bwd_tc if dom_is_bwd else fwd_tc
     dom_ms = bwd_avg if dom_is_bwd else fwd_avg
-    dom_flop = (2.0 if dom_is_bwd else 1.0) * f_alg * pairs
+    dom_flop = (2.0 if dom_is_bwd else 1.0) * f_alg * (B_launch * C * Z)
     achieved = dom_flop / (dom_ms * 1e-3) / 1e12 if dom_ms == dom_ms else None
     tag = f"<{cfg['d']},{cfg['H']}>"
     if dom_is_bwd:
@@ -566,7 +568,7 @@ def main():
                 "frac_of_bound_pipe_whole_step": (pt[max(pt, key=pt.get)] / (ms / args.steps * 1e-3)) if dom_tc else None,
                 "algorithmic_flop_per_launch": dom_flop, "kernel_ms_avg": dom_ms,
                 "kernel_share_of_step": dom_ms * args.steps / ms if dom_ms == dom_ms else None,
-                "fwd_kernel_ms_avg": fwd_avg, "fwd_achieved": (f_alg * pairs / (fwd_avg * 1e-3) / 1e12) if fwd_ms else None,
+                "fwd_kernel_ms_avg": fwd_avg, "fwd_achieved": (f_alg * (B_launch * C * Z) / (fwd_avg * 1e-3) / 1e12) if fwd_ms else None,
                 "whole_step_achieved": step_flop / (ms / args.steps * 1e-3) / 1e12,
                 "whole_step_frac": step_flop / (ms / args.steps * 1e-3) / 1e12 / peak,
                 "note": ("tcgen05 kind::f16 MMAs (fp16 operands, fp32 accumulate in TMEM)" if dom_tc else "arithmetic of this kernel is fp32 FMA")
@@ -594,7 +596,7 @@ def main():
                        "parallelism": f"dp{world} over {partition}",
                        "dispatch": {"pair_fwd": "tcgen05" if fwd_tc else "fp32-fma", "pair_bwd": None if args.forward_only else ("tcgen05" if bwd_tc else "fp32-fma")},
                        "mode": "forward-only" if args.forward_only else ("recompute" if args.recompute else "stash"),
-                       "chunk_fields": chunk_used if args.recompute else None,
+                       "chunk_fields": chunk_used if args.recompute else None, "forward_chunk_fields": (nef.forward_chunk_fields or None),
                        "workspace_bytes": workspace_bytes,
                        "l2": f"per-step working set ({workspace_bytes / 2**30:.2f} GiB workspace) >> 126 MB L2; no explicit flush",
                        "step": ("fwd (no_grad)" if args.forward_only else "fwd + bwd incl. all weight grads")

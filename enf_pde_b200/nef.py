@@ -165,7 +165,7 @@ class EquivariantCrossAttentionNeF:
                  embedding_type: str = "rff", embedding_freq_multiplier=(0.05, 0.1),
                  condition_value_transform: bool = True, use_gaussian_window: bool = True,
                  precision: str = "fp32", recompute: bool = False, chunk_fields: int = 0,
-                 workspace_cap_bytes: Optional[int] = None, out_bf16: bool = False):
+                 workspace_cap_bytes: Optional[int] = None, out_bf16: bool = False, forward_chunk_fields: int = 0):
         if num_layers < 0:
             raise ValueError("num_layers must be >= 0")
         if num_layers > 0 and self_attn_invariant is None:
@@ -190,6 +190,9 @@ class EquivariantCrossAttentionNeF:
         self.recompute = bool(recompute) or workspace_cap_bytes is not None
         self.chunk_fields, self.workspace_cap_bytes = int(chunk_fields), workspace_cap_bytes
         self.out_bf16 = bool(out_bf16)       # forward-only calls return bfloat16 (ENF_FLAG_OUT_BF16, num_out <= 4)
+        # forward-only calls (validation roll-outs decode B*T fields at once, _base_pde_trainer.py:446-457) walk the fields in
+        # chunks of this many, so the workspace is that of one chunk whatever B*T is (0: one call)
+        self.forward_chunk_fields = int(forward_chunk_fields)
 
     # -- nef.init(key, x, p, a, window) (pde_trainer.py:99-102) -----------------------------------------
     def init(self, key, x, p, a, gaussian_window_size=None):
@@ -304,6 +307,15 @@ class EquivariantCrossAttentionNeF:
             desc["flags"] |= _lib.FLAG_FORWARD_ONLY
             if self.out_bf16:
                 desc["flags"] |= _lib.FLAG_OUT_BF16
+            n = self.forward_chunk_fields
+            if 0 < n < B and self.num_layers == 0:
+                outs = []
+                for b0 in range(0, B, n):
+                    sl = slice(b0, min(B, b0 + n))
+                    cd = dict(desc, B=sl.stop - sl.start)
+                    outs.append(_XAttnFunction.apply((cd, x_shared), x_arg if x_shared else x_arg[sl], p[sl], a[sl],
+                                                     None if sigma is None else sigma[sl], *leaves))
+                return torch.cat(outs, dim=0)
         elif self.recompute:
             desc["flags"] |= _lib.FLAG_RECOMPUTE
             desc["chunk_fields"] = self.chunk_fields

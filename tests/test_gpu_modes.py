@@ -192,3 +192,21 @@ def test_second_order_outer_gradient_against_oracle(optimize_window):
     fo_err = max(leaf_errs(R.tree_flatten(g_fo["params"]), want).values())
     print("first-order estimate misses by", f"{fo_err:.2e}")
     assert fo_err > 2e-2
+
+
+def test_forward_only_field_chunks_are_bit_identical():
+    """forward_chunk_fields: validation roll-outs decode B*T fields in chunks (workspace of one chunk); same bits as one call."""
+    cfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
+                      embedding_freq_multiplier=(0.05, 0.1))
+    params, x, p, a, sigma, _ = make_case(cfg, 7, 300, 16, seed=31)
+    P = R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous(), params)
+    with torch.no_grad():
+        whole = _nef(cfg, "bf16").apply(P, f32(x), f32(p), f32(a), f32(sigma))
+        from enf_pde_b200.nef import _XAttnFunction
+        ws_whole = _XAttnFunction.last_ws[2]
+        parts = _nef(cfg, "bf16", forward_chunk_fields=3).apply(P, f32(x), f32(p), f32(a), f32(sigma))      # 3 + 3 + 1 fields
+        ws_part = _XAttnFunction.last_ws[2]
+        shared = _nef(cfg, "bf16", forward_chunk_fields=2).apply(P, f32(x[:1]).expand(7, -1, -1), f32(p), f32(a), f32(sigma))
+        shared_ref = _nef(cfg, "bf16").apply(P, f32(x[:1]).expand(7, -1, -1), f32(p), f32(a), f32(sigma))
+    assert torch.equal(whole, parts) and torch.equal(shared, shared_ref)
+    assert ws_part < ws_whole
