@@ -37,7 +37,7 @@ def _oracle_grads(cfg, params, p, a, cot_p, cot_a):
     return dp.detach(), da.detach(), pp.grad, aa.grad, {k: v.grad for k, v in R.tree_flatten(P).items()}
 
 
-def _check(cfg, params, p, a, cot_p, cot_a, want=None):
+def _check(cfg, params, p, a, cot_p, cot_a, want=None, gp_floor=1e-5):
     dp_o, da_o, gp_o, ga_o, gth_o = _oracle_grads(cfg, params, p, a, cot_p, cot_a)
     model = _model(cfg)
     P = _cuda({"params": params})
@@ -45,7 +45,10 @@ def _check(cfg, params, p, a, cot_p, cot_a, want=None):
     dp, da, dw = model.apply(P, (pg, ag, torch.ones(p.shape[0], p.shape[1], 1, device="cuda")))
     assert dw.shape == (p.shape[0], p.shape[1], 1) and float(dw.abs().max()) == 0.0
     ((dp * f32(cot_p)).sum() + (da * f32(cot_a)).sum()).backward()
-    errs = dict(dp=rel_err(dp.detach(), dp_o), da=rel_err(da.detach(), da_o), gp=rel_err(pg.grad, gp_o), ga=rel_err(ag.grad, ga_o))
+    # max-norm relative error with an absolute floor: a single latent has dp/dt = 0 and d(invariant)/dp = 0 analytically (the
+    # query and latent roles cancel); float32 leaves ~1e-8 there, which is not a relative error of anything
+    rel = lambda got, ref, floor=1e-5: float((got.double().cpu() - ref).abs().max()) / max(float(ref.abs().max()), floor)
+    errs = dict(dp=rel(dp.detach(), dp_o), da=rel(da.detach(), da_o), gp=rel(pg.grad, gp_o, gp_floor), ga=rel(ag.grad, ga_o))
     if want is not None:        # the reference's own outputs
         errs["dp_ref"], errs["da_ref"] = rel_err(dp.detach(), want["dp"]), rel_err(da.detach(), want["da"])
     leaves = R.tree_flatten(P["params"])
@@ -86,7 +89,8 @@ def test_ode_real_shape_navier_stokes():
     cfg, params, p, a, g = _ns_case()
     cot_p = torch.randn(p.shape, generator=g, dtype=torch.float64)
     cot_a = torch.randn(a.shape, generator=g, dtype=torch.float64)
-    _check(cfg, params, p, a, cot_p, cot_a)
+    # a single latent: the pose gradient cancels to 0 analytically between O(1) terms; float32 leaves ~1e-8 of them
+    _check(cfg, params, p, a, cot_p, cot_a, gp_floor=1e-3 if Z == 1 else 1e-5)
 
 
 @pytest.mark.parametrize("method", ["euler", "rk4"])
@@ -157,3 +161,37 @@ def test_ode_latents_only_backward_and_errors():
     assert lib.enf_ode_workspace_bytes(ctypes.byref(bad)) == 0 and b"layers" in lib.enf_last_error()
     with pytest.raises(RuntimeError):
         model.apply(P, (rec["p"].float(), rec["a"].float(), None))          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ode_random_shapes(seed):
+    """ragged / degenerate sizes: one latent, Z not a multiple of the warp size, odd widths, degree 0..3, every invariant."""
+    import random
+    rnd = random.Random(1000 + seed)
+    inv = ["rel_pos_periodic", "ponita", "polar_periodic", "latitude_periodic", "rel_pos", "norm_rel_pos", "abs_pos", "ball"][seed % 8]
+    num_in = 3 if inv == "ball" else (rnd.choice([1, 2, 3]) if inv in ("rel_pos", "norm_rel_pos", "abs_pos") else 2)
+    cfg = O.OdeConfig(invariant_type=inv, num_in=num_in, num_hidden=rnd.choice([4, 12, 20, 36]), num_layers=rnd.choice([1, 2, 4]),
+                      latent_dim=rnd.choice([1, 3, 7]), basis_dim=rnd.choice([1, 5, 9]), degree=rnd.choice([0, 1, 2, 3]),
+                      widening_factor=rnd.choice([1, 3]))
+    B, Z = rnd.choice([1, 2, 5]), rnd.choice([1, 2, 33, 70])
+    g = torch.Generator().manual_seed(seed)
+    params = O.ode_init(cfg, seed=seed, readout_scale=1e6)
+    for k, v in R.tree_flatten(params).items():
+        if k.endswith("bias") or k.endswith("scale"):
+            v += 0.1 * torch.randn(v.shape, generator=g, dtype=torch.float64)
+    P = cfg.enf.pose_raw_dim
+    if inv in ("polar_periodic", "latitude_periodic", "ball"):
+        cols = [torch.rand(B, Z, generator=g, dtype=torch.float64) * 6.28, 0.2 + torch.rand(B, Z, generator=g, dtype=torch.float64) * 2.7]
+        cols += [torch.rand(B, Z, generator=g, dtype=torch.float64) for _ in range(P - 2)]
+        p = torch.stack(cols, -1)
+    else:
+        p = torch.rand(B, Z, P, generator=g, dtype=torch.float64) * 2 - 1
+    a = 1.0 + 0.3 * torch.randn(B, Z, cfg.latent_dim, generator=g, dtype=torch.float64)
+    r32 = lambda t: t.float().double()
+    params, p, a = R.tree_map(r32, params), r32(p), r32(a)
+    cot_p, cot_a = torch.randn(p.shape, generator=g, dtype=torch.float64), torch.randn(a.shape, generator=g, dtype=torch.float64)
+    print(inv, num_in, cfg, B, Z)
+    # (norm_rel_pos: d|p_r - p_s|/dp is undefined on the diagonal r = s -- the reference's jnp.linalg.norm gives NaN there; the
+    # oracle and the kernels both use 0)
+    # a single latent: the pose gradient cancels to 0 analytically between O(1) terms; float32 leaves ~1e-8 of them
+    _check(cfg, params, p, a, cot_p, cot_a, gp_floor=1e-3 if Z == 1 else 1e-5)
