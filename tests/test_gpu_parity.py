@@ -99,6 +99,28 @@ def test_self_attention_blocks_at_real_hidden_size():
         assert ok, (precision, errs, worst)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_self_attention_random_shapes(seed):
+    """ragged sizes through num_layers > 0: one latent, Z not a multiple of the 32-row tile, 1..4 heads, every window kind."""
+    import random
+    rnd = random.Random(500 + seed)
+    inv, grid = [("rel_pos_periodic", None), ("ponita", None), ("polar_periodic", (6, 3)), ("latitude_periodic", (6, 3)), ("ball", None),
+                 ("norm_rel_pos", None)][seed]
+    Z = 18 if grid else (rnd.choice([1, 9, 33, 49]) if inv == "ball" else rnd.choice([1, 9, 36, 49]))   # grid initialisers: squares
+    cfg = R.EnfConfig(num_in=3 if inv == "ball" else 2, num_hidden=rnd.choice([16, 32, 64]), num_heads=rnd.choice([1, 2, 3, 4]),
+                      num_out=rnd.choice([1, 3]), latent_dim=rnd.choice([1, 5, 16]), invariant_type=inv,
+                      embedding_freq_multiplier=(0.1, 0.2), use_gaussian_window=rnd.choice([True, True, False]),
+                      num_layers=rnd.choice([1, 2, 3]))
+    B, C = rnd.choice([1, 2, 3]), rnd.choice([1, 31, 64, 100])
+    data = make_case(cfg, B, C, Z, seed=seed, polar_grid=grid)
+    chk = Checker(cfg, data)
+    out, g, dp, da, ds = _api_fwd_bwd(cfg, *data)
+    errs, worst, ok = compare(chk, out, dp, da, ds, R.tree_flatten(g["params"]), TOL, use_window=cfg.use_gaussian_window)
+    print(inv, cfg.num_hidden, cfg.num_heads, cfg.num_layers, B, C, Z, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf:", worst,
+          chk.used_allowance)
+    assert ok, (errs, worst, chk.used_allowance)
+
+
 CASES = [
     # (name, cfg kwargs, B, C, Z, polar_grid)    sizes the fp64 oracle finishes in seconds
     ("ns_d128", dict(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=16, invariant_type="rel_pos_periodic",
