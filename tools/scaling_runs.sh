@@ -1,7 +1,7 @@
 #!/bin/bash
 # Strong-scaling and query-partition runs of bench.py on one 8-GPU box: results -> gpurun_out/r02_scaling.jsonl
 # usage (on the GPU box): bash tools/scaling_runs.sh
-out=gpurun_out/r02_scaling.jsonl
+out=${1:-gpurun_out/r02_scaling.jsonl}
 : > $out
 run() {   # n, extra args...
   n=$1; shift
