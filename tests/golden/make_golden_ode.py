@@ -42,6 +42,8 @@ CASES = {
     "rel_pos": dict(invariant_type="rel_pos", num_in=3, hidden=8, layers=1, L=3, basis=4, degree=2, widen=2, B=2, Z=3),
     "norm_rel_pos": dict(invariant_type="norm_rel_pos", num_in=2, hidden=8, layers=2, L=3, basis=4, degree=3, widen=2, B=1, Z=4),
     "abs_pos": dict(invariant_type="abs_pos", num_in=2, hidden=8, layers=1, L=3, basis=4, degree=2, widen=2, B=2, Z=4),
+    # config_ihc.yaml: the ball invariant between latent poses (x = p: Euler angles alpha, beta read as (phi, theta), gamma as the radius)
+    "ball": dict(invariant_type="ball", num_in=3, hidden=8, layers=2, L=4, basis=4, degree=2, widen=2, B=2, Z=5),
 }
 
 
@@ -54,6 +56,8 @@ def build_case(name, c, rng):
     B, Z, t = c["B"], c["Z"], c["invariant_type"]
     if t in ("polar_periodic", "latitude_periodic"):
         p = latent_utils.init_positions_polar(None, (B, Z, 2))
+    elif t == "ball":
+        p = latent_utils.init_positions_ball(None, (B, Z, 4))
     elif t == "ponita":
         p = np.concatenate([latent_utils.init_positions_grid(None, (B, Z, 2)),
                             latent_utils.init_ori_rotation_invariant_s2(None, (B, Z, 2))], -1)
@@ -118,7 +122,10 @@ def build_case(name, c, rng):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(abs(hash("ode" + name)) % (2 ** 32) if False else sum(map(ord, "ode" + name)))
         rec = build_case(name, c, rng)
         np.savez_compressed(os.path.join(HERE, f"ode_{name}.npz"), **rec)
