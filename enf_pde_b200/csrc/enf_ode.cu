@@ -20,7 +20,7 @@ namespace {
 
 struct Dims {
   int B, Z, L, Hd, Bd, NL, W, deg, Dx, kind;
-  int I, P, npos, nori, S, F, row_kind, nsq;
+  int I, P, npos, nori, S, F, Fp, row_kind, nsq;      // Fp: row stride of the feature matrices (F rounded up to 32)
   int64_t m, n;
 };
 
@@ -47,6 +47,7 @@ int validate(const EnfOdeDesc* D, Dims* o) {
   for (int t = 0; t <= d.deg; ++t) { pw *= d.I; F += pw; }
   if (F > 4096) return enf_set_error(ENF_ERR_UNSUPPORTED, "tensor-power feature width above 4096");
   d.F = (int)F;
+  d.Fp = (d.F + 31) / 32 * 32;
   d.m = (int64_t)d.B * d.Z; d.n = d.m * d.Z;
   if (d.n * (int64_t)(d.F > d.Hd ? d.F : d.Hd) > ((int64_t)1 << 40)) return enf_set_error(ENF_ERR_UNSUPPORTED, "B*Z*Z too large for one call");
   if (d.Z > 65535) return enf_set_error(ENF_ERR_UNSUPPORTED, "Z must be <= 65535");
@@ -62,7 +63,8 @@ struct Ws {
   int64_t lam, xi, inv, poly, h0p, h0, kbp, kb, am1, hin[ENF_ODE_MAX_LAYERS + 1];
   int64_t K[ENF_ODE_MAX_LAYERS], cv[ENF_ODE_MAX_LAYERS], core[ENF_ODE_MAX_LAYERS], ln[ENF_ODE_MAX_LAYERS], rstd[ENF_ODE_MAX_LAYERS],
       l1p[ENF_ODE_MAX_LAYERS], l1a[ENF_ODE_MAX_LAYERS];
-  int64_t scalar, hs, wpair;
+  int64_t scalar, hs, wpair, ptab;
+  int64_t w0p, w0lo, w1lo, cklo[ENF_ODE_MAX_LAYERS];      // zero-padded kb_w0 (Fp rows) and the low parts W - trunc_tf32(W) for the 3-term tf32 products
   // backward scratch
   int64_t g_scalar, g_ha, g_hb, g_l1, g_ln, g_c, g_K, g_kb, g_kbp, g_h0, g_poly, g_inv, gw, g_lam, g_xi, ssum, gpe, rosum;
   // solver scratch
@@ -72,7 +74,7 @@ struct Ws {
 Ws make_ws(const Dims& d) {
   Ws w;
   w.lam = w.take(d.m * ENF_LAM_SIZE); w.xi = w.take(d.m * ENF_F_XI);
-  w.inv = w.take(d.n * d.I); w.poly = w.take(d.n * d.F);
+  w.inv = w.take(d.n * d.I); w.poly = w.take(d.n * d.Fp);
   w.h0p = w.take(d.n * d.Hd); w.h0 = w.take(d.n * d.Hd); w.kbp = w.take(d.n * d.Bd); w.kb = w.take(d.n * d.Bd);
   w.am1 = w.take(d.m * d.L);
   for (int l = 0; l <= d.NL; ++l) w.hin[l] = w.take(d.m * d.Hd);
@@ -80,10 +82,12 @@ Ws make_ws(const Dims& d) {
     w.K[l] = w.take(d.n * d.Hd); w.cv[l] = w.take(d.m * d.Hd); w.core[l] = w.take(d.m * d.Hd); w.ln[l] = w.take(d.m * d.Hd);
     w.rstd[l] = w.take(d.m); w.l1p[l] = w.take(d.m * d.W); w.l1a[l] = w.take(d.m * d.W);
   }
-  w.scalar = w.take(d.m * d.S); w.hs = w.take(d.m * 2); w.wpair = w.take(d.n * 2);
+  w.scalar = w.take(d.m * d.S); w.hs = w.take(d.m * 2); w.wpair = w.take(d.n * 2); w.ptab = w.take(d.Fp);
+  w.w0p = w.take((int64_t)d.Fp * d.Hd); w.w0lo = w.take((int64_t)d.Fp * d.Hd); w.w1lo = w.take((int64_t)d.Hd * d.Bd);
+  for (int l = 0; l < d.NL; ++l) w.cklo[l] = w.take((int64_t)d.Bd * d.Hd);
   w.g_scalar = w.take(d.m * d.S); w.g_ha = w.take(d.m * d.Hd); w.g_hb = w.take(d.m * d.Hd); w.g_l1 = w.take(d.m * d.W);
   w.g_ln = w.take(d.m * d.Hd); w.g_c = w.take(d.m * d.Hd); w.g_K = w.take(d.n * d.Hd); w.g_kb = w.take(d.n * d.Bd);
-  w.g_kbp = w.take(d.n * d.Bd); w.g_h0 = w.take(d.n * d.Hd); w.g_poly = w.take(d.n * d.F); w.g_inv = w.take(d.n * d.I);
+  w.g_kbp = w.take(d.n * d.Bd); w.g_h0 = w.take(d.n * d.Hd); w.g_poly = w.take(d.n * d.Fp); w.g_inv = w.take(d.n * d.I);
   w.gw = w.take(d.n * 2); w.g_lam = w.take(d.m * ENF_LAM_SIZE); w.g_xi = w.take(d.m * ENF_F_XI); w.ssum = w.take(d.m * 2);
   w.gpe = w.take(d.m * 8); w.rosum = w.take(2 * (d.I + d.Hd));
   for (int i = 0; i < 4; ++i) { w.kp[i] = w.take(d.m * d.P); w.ka[i] = w.take(d.m * d.L); }
@@ -111,11 +115,31 @@ __global__ void ode_am1_kernel(const float* __restrict__ a, float* __restrict__ 
   if (t < total) am1[t] = a[t] - 1.f;
 }
 
-// invariants of every pair row and their tensor powers [u, u (x) u, ...] (PolynomialFeatures, ponita_ode_g.py:22-27).
-// One warp per pair row; lanes stride over the F features (coalesced stores).
-__global__ void __launch_bounds__(256) ode_inv_poly_kernel(int I, int F, int deg, int row_kind, int nsq, int Z, int64_t n,
+// kb_w0 [F][Hd] -> zero-padded copy [Fp][Hd] (the tensor-core GEMMs take whole 32-feature blocks)
+__global__ void ode_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n_src, int64_t n_dst) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_dst) dst[t] = t < n_src ? src[t] : 0.f;
+}
+
+// Digit table of the tensor-power features (PolynomialFeatures, ponita_ode_g.py:22-27): feature e of level k (k + 1 factors) is
+// prod_t u[digit_t(e)]; entry = k | digit_0 << 4 | digit_1 << 8 | ... (digits < 8).  Built once per call: the pair kernels then
+// decode a word with shifts instead of dividing by the runtime invariant width per feature.
+__global__ void ode_poly_table_kernel(int I, int F, uint32_t* __restrict__ tab) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= F) return;
+  int idx = e, size = I, k = 0;
+  while (idx >= size) { idx -= size; size *= I; ++k; }
+  uint32_t w = (uint32_t)k;
+  for (int t = 0; t <= k; ++t) { w |= (uint32_t)(idx % I) << (4 + 4 * t); idx /= I; }
+  tab[e] = w;
+}
+
+// invariants of every pair row and their tensor powers [u, u (x) u, ...].  One warp per pair row; lanes stride over the F
+// features (coalesced stores).
+__global__ void __launch_bounds__(256) ode_inv_poly_kernel(int I, int F, int Fp, int row_kind, int nsq, int Z, int64_t n,
                                                            const float* __restrict__ lam, const float* __restrict__ xi,
-                                                           float* __restrict__ inv, float* __restrict__ poly) {
+                                                           const uint32_t* __restrict__ tab, float* __restrict__ inv,
+                                                           float* __restrict__ poly) {
   __shared__ float su[8][8];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * 8 + wl;
@@ -128,41 +152,62 @@ __global__ void __launch_bounds__(256) ode_inv_poly_kernel(int I, int F, int deg
     inv[row * I + lane] = u;
   }
   __syncwarp();
-  for (int e = lane; e < F; e += 32) {
-    int idx = e, size = I, k = 0;
-    while (idx >= size) { idx -= size; size *= I; ++k; }
-    float prod = 1.f;
-    for (int t = 0; t <= k; ++t) { prod *= su[wl][idx % I]; idx /= I; }
-    poly[row * F + e] = prod;
+  const float* u = su[wl];
+  for (int e = lane; e < Fp; e += 32) {
+    float prod = 0.f;                              // columns F .. Fp - 1: zero padding (the row stride is a multiple of 32)
+    if (e < F) {
+      const uint32_t w = __ldg(tab + e);
+      const int k = w & 15;
+      prod = u[(w >> 4) & 7];
+      if (k > 0) prod *= u[(w >> 8) & 7];
+      if (k > 1) prod *= u[(w >> 12) & 7];
+      if (k > 2) prod *= u[(w >> 16) & 7];
+      if (k > 3) prod *= u[(w >> 20) & 7];
+      if (k > 4) prod *= u[(w >> 24) & 7];
+    }
+    poly[row * Fp + e] = prod;
   }
 }
 
-// g_inv[row][i] += sum_e g_poly[row][e] d(poly_e)/d(u_i)
-__global__ void __launch_bounds__(256) ode_poly_bwd_kernel(int I, int F, int64_t n, const float* __restrict__ inv,
-                                                           const float* __restrict__ g_poly, float* __restrict__ g_inv) {
+// g_inv[row][i] += sum_e g_poly[row][e] d(poly_e)/d(u_i): per feature, the product of the other factors (prefix x suffix) goes
+// to the digit's slot of a per-warp shared accumulator (shared atomics: at most 6 distinct addresses per warp)
+__global__ void __launch_bounds__(256) ode_poly_bwd_kernel(int I, int F, int Fp, int64_t n, const float* __restrict__ inv,
+                                                           const float* __restrict__ g_poly, const uint32_t* __restrict__ tab,
+                                                           float* __restrict__ g_inv) {
   __shared__ float su[8][8];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * 8 + wl;
   if (row >= n) return;
-  if (lane < I) su[wl][lane] = inv[row * I + lane];
+  if (lane < 8) su[wl][lane] = lane < I ? inv[row * I + lane] : 0.f;
   __syncwarp();
+  const float* u = su[wl];
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int e = lane; e < F; e += 32) {
-    int idx = e, size = I, k = 0;
-    while (idx >= size) { idx -= size; size *= I; ++k; }
-    const float g = g_poly[row * F + e];
-    int dig[6];
-    for (int t = 0; t <= k; ++t) { dig[t] = idx % I; idx /= I; }
-    for (int t = 0; t <= k; ++t) {
-      float part = g;
-      for (int t2 = 0; t2 <= k; ++t2) if (t2 != t) part *= su[wl][dig[t2]];
+    const uint32_t w = __ldg(tab + e);
+    const int k = w & 15;
+    const float g = g_poly[row * Fp + e];
+    int dg[6]; float f[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) if (dig[t] == i) acc[i] += part;
+    for (int t = 0; t < 6; ++t) { dg[t] = (w >> (4 + 4 * t)) & 7; f[t] = t <= k ? u[dg[t]] : 1.f; }
+    // suffix products: suf[t] = prod_{t' > t} f[t']
+    float suf[6];
+    suf[5] = 1.f;
+#pragma unroll
+    for (int t = 4; t >= 0; --t) suf[t] = suf[t + 1] * f[t + 1];
+    float pre = g;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      if (t <= k) {
+        const float part = pre * suf[t];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[i] += dg[t] == i ? part : 0.f;
+      }
+      pre *= f[t];
     }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    float v = warp_sum(acc[i]);
+    const float v = warp_sum(acc[i]);
     if (lane == 0 && i < I) g_inv[row * I + i] += v;
   }
 }
@@ -437,6 +482,8 @@ struct Run {
   }
 };
 EnfGemmOpts o_bias(const float* b, float* gelu_out = nullptr) { EnfGemmOpts o; o.bias = b; o.gelu_out = gelu_out; return o; }
+// 3-term tf32 tensor-core product when the shape allows (b_lo: the weight's low part, laid out like the weight)
+EnfGemmOpts o_tc(EnfGemmOpts o, const float* b_lo) { o.tc = 1; o.b_lo = b_lo; return o; }
 EnfGemmOpts o_acc() { EnfGemmOpts o; o.accumulate = 1; return o; }
 EnfGemmOpts o_dgelu(const float* pre) { EnfGemmOpts o; o.mul_gelu_grad = pre; return o; }
 
@@ -460,15 +507,33 @@ int forward(const Dims& d, const Ws& Y, const EnfOdeWeights& w, const float* p, 
   float* W = R.ws;
   R.launches += enf_launch_pose_record(st, d.kind, d.Dx, d.P, d.I, d.m, p, W + Y.lam);
   R.launches += enf_launch_pose_features(st, d.kind, d.Dx, d.P, d.m, p, W + Y.xi);
-  ode_inv_poly_kernel<<<nblocks(d.n, 8), 256, 0, st>>>(d.I, d.F, d.deg, d.row_kind, d.nsq, d.Z, d.n, W + Y.lam, W + Y.xi, W + Y.inv, W + Y.poly);
+  uint32_t* ptab = reinterpret_cast<uint32_t*>(W + Y.ptab);
+  ode_poly_table_kernel<<<nblocks(d.F, 128), 128, 0, st>>>(d.I, d.F, ptab);
+  ode_inv_poly_kernel<<<nblocks(d.n, 8), 256, 0, st>>>(d.I, d.F, d.Fp, d.row_kind, d.nsq, d.Z, d.n, W + Y.lam, W + Y.xi, ptab, W + Y.inv, W + Y.poly);
+  // The pair-row Dense layers run on the tf32 tensor-core kernels as 3-term split products (fp32-level accuracy,
+  // enf_gemm_tc.cu) when the shapes allow (hidden, basis multiples of 32, >= 128 pair rows), else on the fp32 kernel: the
+  // low parts W - trunc_tf32(W) of the weights they multiply by, and kb_w0 zero-padded to whole 32-feature blocks
+  ode_pad_rows_kernel<<<nblocks((int64_t)d.Fp * d.Hd, 256), 256, 0, st>>>(w.kb_w0, W + Y.w0p, (int64_t)d.F * d.Hd, (int64_t)d.Fp * d.Hd);
+  {
+    EnfSplitList sl;
+    int c = 0;
+    auto add = [&](const float* src, float* dst, int64_t n) {
+      sl.src[c] = src; sl.dst[c] = dst; sl.n[c] = (int)n; ++c;
+      if (c == 8) { sl.count = c; R.launches += enf_launch_split_lo(st, sl); c = 0; }
+    };
+    add(W + Y.w0p, W + Y.w0lo, (int64_t)d.Fp * d.Hd);
+    add(w.kb_w1, W + Y.w1lo, (int64_t)d.Hd * d.Bd);
+    for (int l = 0; l < d.NL; ++l) add(w.layer[l].conv_k, W + Y.cklo[l], (int64_t)d.Bd * d.Hd);
+    if (c) { sl.count = c; R.launches += enf_launch_split_lo(st, sl); }
+  }
   // kernel basis: Dense -> gelu -> Dense -> gelu (ponita_ode_g.py:107-109)
-  R.gemm(d.n, d.Hd, d.F, enf_mat(W + Y.poly, d.F), enf_mat(w.kb_w0, d.Hd), enf_mat(W + Y.h0p, d.Hd), o_bias(w.kb_b0, W + Y.h0));
-  R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.h0, d.Hd), enf_mat(w.kb_w1, d.Bd), enf_mat(W + Y.kbp, d.Bd), o_bias(w.kb_b1, W + Y.kb));
+  R.gemm(d.n, d.Hd, d.Fp, enf_mat(W + Y.poly, d.Fp), enf_mat(W + Y.w0p, d.Hd), enf_mat(W + Y.h0p, d.Hd), o_tc(o_bias(w.kb_b0, W + Y.h0), W + Y.w0lo));
+  R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.h0, d.Hd), enf_mat(w.kb_w1, d.Bd), enf_mat(W + Y.kbp, d.Bd), o_tc(o_bias(w.kb_b1, W + Y.kb), W + Y.w1lo));
   ode_am1_kernel<<<nblocks(d.m * d.L, 256), 256, 0, st>>>(a, W + Y.am1, d.m * d.L);
   R.gemm(d.m, d.Hd, d.L, enf_mat(W + Y.am1, d.L), enf_mat(w.stem_w, d.Hd), enf_mat(W + Y.hin[0], d.Hd));
   for (int l = 0; l < d.NL; ++l) {
     const EnfOdeLayer& y = w.layer[l];
-    R.gemm(d.n, d.Hd, d.Bd, enf_mat(W + Y.kb, d.Bd), enf_mat(y.conv_k, d.Hd), enf_mat(W + Y.K[l], d.Hd));
+    R.gemm(d.n, d.Hd, d.Bd, enf_mat(W + Y.kb, d.Bd), enf_mat(y.conv_k, d.Hd), enf_mat(W + Y.K[l], d.Hd), o_tc(EnfGemmOpts(), W + Y.cklo[l]));
     ode_conv_fwd_kernel<<<nblocks(d.m * d.Hd, 256), 256, 0, st>>>(d.Z, d.Hd, d.m * d.Hd, W + Y.hin[l], W + Y.K[l], y.conv_b, W + Y.cv[l]);
     R.launches += enf_launch_ln_fwd(st, W + Y.cv[l], d.m, d.Hd, y.ln_g, y.ln_b, W + Y.core[l], W + Y.ln[l], W + Y.rstd[l], 0);
     R.gemm(d.m, d.W, d.Hd, enf_mat(W + Y.ln[l], d.Hd), enf_mat(y.l1_w, d.W), enf_mat(W + Y.l1p[l], d.W), o_bias(y.l1_b, W + Y.l1a[l]));
@@ -556,7 +621,6 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
   }
   if (wg) ode_ro_scatter_kernel<<<nblocks(d.I + d.Hd, 128), 128, 0, st>>>(d.I + d.Hd, W + Y.rosum, dW->ro_rel, d.nori ? dW->ro_ori : nullptr);
   // ---- interaction layers, last to first; g_kb accumulates the kernel-basis cotangent over the layers -------------------------
-  zero(W + Y.g_kb, d.n * d.Bd);
   for (int l = d.NL - 1; l >= 0; --l) {
     const EnfOdeLayer& y = w->layer[l];
     // linear_2
@@ -579,7 +643,10 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
     ode_conv_bwd_k_kernel<<<nblocks(d.n * d.Hd, 256), 256, 0, st>>>(d.Z, d.Hd, d.n * d.Hd, W + Y.g_c, W + Y.hin[l], W + Y.g_K);
     ode_conv_bwd_h_kernel<<<nblocks(d.m * d.Hd, 256), 256, 0, st>>>(d.Z, d.Hd, d.m * d.Hd, W + Y.g_c, W + Y.K[l], g_h2);
     if (wg) R.gemm(d.Bd, d.Hd, (int)d.n, enf_mat(W + Y.kb, 1, d.Bd), enf_mat(W + Y.g_K, d.Hd), enf_mat(dW->layer[l].conv_k, d.Hd), o_acc());
-    R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kb, d.Bd), o_acc());
+    if (l == d.NL - 1)      // the first contribution overwrites (tensor-core product), the others accumulate
+      R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kb, d.Bd), o_tc(EnfGemmOpts(), W + Y.cklo[l]));
+    else
+      R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kb, d.Bd), o_acc());
     float* t = g_h; g_h = g_h2; g_h2 = t;
     R.launches += 2;
   }
@@ -593,13 +660,18 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
     R.gemm(d.Hd, d.Bd, (int)d.n, enf_mat(W + Y.h0, 1, d.Hd), enf_mat(W + Y.g_kbp, d.Bd), enf_mat(dW->kb_w1, d.Bd), o_acc());
     R.launches += enf_launch_colsum(st, W + Y.g_kbp, d.n, d.Bd, d.Bd, dW->kb_b1, nullptr, 0);
   }
-  R.gemm(d.n, d.Hd, d.Bd, enf_mat(W + Y.g_kbp, d.Bd), enf_mat(w->kb_w1, 1, d.Bd), enf_mat(W + Y.g_h0, d.Hd), o_dgelu(W + Y.h0p));
+  R.gemm(d.n, d.Hd, d.Bd, enf_mat(W + Y.g_kbp, d.Bd), enf_mat(w->kb_w1, 1, d.Bd), enf_mat(W + Y.g_h0, d.Hd), o_tc(o_dgelu(W + Y.h0p), W + Y.w1lo));
   if (wg) {
-    R.gemm(d.F, d.Hd, (int)d.n, enf_mat(W + Y.poly, 1, d.F), enf_mat(W + Y.g_h0, d.Hd), enf_mat(dW->kb_w0, d.Hd), o_acc());
+    R.gemm(d.F, d.Hd, (int)d.n, enf_mat(W + Y.poly, 1, d.Fp), enf_mat(W + Y.g_h0, d.Hd), enf_mat(dW->kb_w0, d.Hd), o_acc());
     R.launches += enf_launch_colsum(st, W + Y.g_h0, d.n, d.Hd, d.Hd, dW->kb_b0, nullptr, 0);
   }
-  R.gemm(d.n, d.F, d.Hd, enf_mat(W + Y.g_h0, d.Hd), enf_mat(w->kb_w0, 1, d.Hd), enf_mat(W + Y.g_poly, d.F));
-  ode_poly_bwd_kernel<<<nblocks(d.n, 8), 256, 0, st>>>(d.I, d.F, d.n, W + Y.inv, W + Y.g_poly, W + Y.g_inv);
+  // cotangent of the features, in column blocks of <= 256 (the tensor-core kernel's widest tile); padded columns come out 0
+  for (int c0 = 0; c0 < d.Fp; c0 += 256) {
+    const int nc = d.Fp - c0 < 256 ? d.Fp - c0 : 256;
+    R.gemm(d.n, nc, d.Hd, enf_mat(W + Y.g_h0, d.Hd), enf_mat(W + Y.w0p + (int64_t)c0 * d.Hd, 1, d.Hd), enf_mat(W + Y.g_poly + c0, d.Fp),
+           o_tc(EnfGemmOpts(), W + Y.w0lo + (int64_t)c0 * d.Hd));
+  }
+  ode_poly_bwd_kernel<<<nblocks(d.n, 8), 256, 0, st>>>(d.I, d.F, d.Fp, d.n, W + Y.inv, W + Y.g_poly, reinterpret_cast<const uint32_t*>(W + Y.ptab), W + Y.g_inv);
   // ---- invariants -> poses (sender side through Lam, receiver side through xi), read-out position terms ------------------------
   ode_inv_bwd_lam_kernel<<<nblocks(d.m * ENF_LAM_SIZE, 256), 256, 0, st>>>(d.I, d.Z, d.row_kind, d.m * ENF_LAM_SIZE, W + Y.inv, W + Y.g_inv,
                                                                            W + Y.xi, W + Y.g_lam);
