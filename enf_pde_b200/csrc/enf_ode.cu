@@ -645,8 +645,10 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
     if (wg) R.gemm(d.Bd, d.Hd, (int)d.n, enf_mat(W + Y.kb, 1, d.Bd), enf_mat(W + Y.g_K, d.Hd), enf_mat(dW->layer[l].conv_k, d.Hd), o_acc());
     if (l == d.NL - 1)      // the first contribution overwrites (tensor-core product), the others accumulate
       R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kb, d.Bd), o_tc(EnfGemmOpts(), W + Y.cklo[l]));
-    else
-      R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kb, d.Bd), o_acc());
+    else {                  // into g_kbp (free until the kernel-basis stage), then added: keeps the product on the tensor-core kernel
+      R.gemm(d.n, d.Bd, d.Hd, enf_mat(W + Y.g_K, d.Hd), enf_mat(y.conv_k, 1, d.Hd), enf_mat(W + Y.g_kbp, d.Bd), o_tc(EnfGemmOpts(), W + Y.cklo[l]));
+      R.launches += enf_launch_add(st, W + Y.g_kb, W + Y.g_kb, W + Y.g_kbp, d.n * d.Bd);
+    }
     float* t = g_h; g_h = g_h2; g_h2 = t;
     R.launches += 2;
   }
