@@ -747,8 +747,10 @@ int enf_xattn_bwd(const EnfDesc* desc, const EnfWeights* w, const float* x, int6
     { const char* e = getenv("ENF_DEBUG_NOSPLIT"); tp.debug_nosplit = (e && e[0] == '1') ? 1 : 0; }
     tp.dthat = reinterpret_cast<__half*>(c.f("dthat")); tp.ds = c.f("ds_tc"); tp.duv = c.f("duv");
     tp.g_W3 = c.f("g_W3"); tp.g_b3 = c.f("g_b3");
-    tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");
-    tp.g_Wp = c.f("gf_Wp"); tp.g_bp = c.f("gf_bp");
+    if (wg) {        // latents-only backward: kernels B / C skip the shared-weight gradient MMAs and their flush
+      tp.g_q_w1 = G("q_w1"); tp.g_q_b1 = G("q_b1"); tp.g_v_w1 = G("v_w1"); tp.g_v_b1 = G("v_b1");
+      tp.g_Wp = c.f("gf_Wp"); tp.g_bp = c.f("gf_bp");
+    }
     tp.g_U = c.f("g_U"); tp.g_kappa = c.f("g_kappa"); tp.g_lam = c.f("g_lam"); tp.g_sigma = c.f("g_sigma");
     prof_mark(1, 0, st);
     // once per backward: the power-of-two gradient scale, the fp16 cotangent of nbar in kernel A's load order, Dg

@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(QCfg<D, H>::NTALL, D <= 64 ? 2 : 1) pairs_bwd_
           issue_rowsum<D>(tS2, aGlo, aS, C::ABLK, ct > 0);           // dU (per item)
           issue_dgrad<D>(tT, aDz, aW, C::ABLK, C::WBLK, 0);          // d gamma_q (S3 waits for it)
           tc::mma_commit(bar_d);
-          issue_wgrad<D>(tW, aGhi, aDz, C::ABLK, it > 0);            // dW1_q (per CTA)
-          issue_rowsum<D>(tS1, aDz, aS, C::ABLK, it > 0);            // db1q (per CTA)
+          if (P.g_q_w1) {                                            // latents-only backward (dW = NULL): no shared-weight gradients
+            issue_wgrad<D>(tW, aGhi, aDz, C::ABLK, it > 0);          // dW1_q (per CTA)
+            issue_rowsum<D>(tS1, aDz, aS, C::ABLK, it > 0);          // db1q (per CTA)
+          }
           if (ct + 1 < ntiles) {
             issue_proj(tP, aU, aOm, HD);
             tc::mma_commit(bar_p);
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(QCfg<D, H>::NTALL, D <= 64 ? 2 : 1) pairs_bwd_
   // ---- CTA flush: shared-weight gradients --------------------------------------------------------------------------------
   __syncthreads();
   tc::tc_fence_after();
-  if (it > 0 && main_thr) {
+  if (it > 0 && main_thr && P.g_q_w1) {
     float v[32];
     tc::tmem_ld32(tW + my_t, v);
     tc::tmem_ld_wait();

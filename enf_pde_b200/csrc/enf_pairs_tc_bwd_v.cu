@@ -361,9 +361,11 @@ __global__ void __launch_bounds__(VCfg<D>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_v_k
         tc::tc_fence_after();
         issue_dgrad<D>(tT, aDt, aWp, C::ABLK, C::WBLK, 0);          // d h1v
         tc::mma_commit(bar_g3);
-        issue_wgrad<D>(tWp, aX, aDt, C::ABLK, it > 0);              // dW' (per CTA)
-        issue_colsum<D>(tS1, aDt, aOne, C::ABLK, it > 0);           // db' (per CTA)
-        tc::mma_commit(bar_g3b);
+        if (P.g_Wp) {                                       // latents-only backward (dW = NULL): no shared-weight gradients
+          issue_wgrad<D>(tWp, aX, aDt, C::ABLK, it > 0);            // dW' (per CTA)
+          issue_colsum<D>(tS1, aDt, aOne, C::ABLK, it > 0);         // db' (per CTA)
+        }
+        tc::mma_commit(bar_g3b);                                    // (without them: fires with the dgrad, which reads dtpre too)
         if (ct + 1 < ntiles) {                             // phases of the next tile (sU was written before the barrier)
           issue_proj(tP, aU, aOm, HD);
           tc::mma_commit(bar_p);
@@ -392,8 +394,10 @@ __global__ void __launch_bounds__(VCfg<D>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_v_k
         tc::tc_fence_after();
         issue_dgrad<D>(tT, aDt, aW, C::ABLK, C::WBLK, 0);           // d gamma_v
         tc::mma_commit(bar_g4);
-        issue_wgrad<D>(tW1, aGhi, aDt, C::ABLK, it > 0);            // dW1_v (per CTA)
-        issue_colsum<D>(tS2, aDt, aOne, C::ABLK, it > 0);           // db1v (per CTA)
+        if (P.g_Wp) {
+          issue_wgrad<D>(tW1, aGhi, aDt, C::ABLK, it > 0);          // dW1_v (per CTA)
+          issue_colsum<D>(tS2, aDt, aOne, C::ABLK, it > 0);         // db1v (per CTA)
+        }
       }
       // ---- S3: d gamma_v -> dproj (my 16 frequencies: sin columns j, cos columns HD + j) ---------------------------
       tc::mbar_wait(bar_g4, par);
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(VCfg<D>::NT, D == 32 ? 2 : 1) pairs_bwd_tc_v_k
   }
   __syncthreads();
   tc::tc_fence_after();
-  if (it > 0) {
+  if (it > 0 && P.g_Wp) {
     const int wrow = wgrad_row<D>(row, lq, lane);      // accumulator row (input feature) of this thread
     float* dst[2] = {P.g_Wp, P.g_v_w1};
     const uint32_t src[2] = {tWp, tW1};

@@ -210,3 +210,22 @@ def test_forward_only_field_chunks_are_bit_identical():
         shared_ref = _nef(cfg, "bf16").apply(P, f32(x[:1]).expand(7, -1, -1), f32(p), f32(a), f32(sigma))
     assert torch.equal(whole, parts) and torch.equal(shared, shared_ref)
     assert ws_part < ws_whole
+
+
+@pytest.mark.parametrize("hidden,heads", [(128, 2), (64, 2), (32, 3)])
+def test_latents_only_backward_matches_full_backward(hidden, heads):
+    """dW = NULL (Meta-SGD inner steps, ODE phase): the tcgen05 backward kernels B / C skip the shared-weight gradient MMAs and their
+    flush; the latent gradients are the full backward's (up to the order of the float atomics that reduce them over tiles)."""
+    inv = "ball" if hidden == 32 else "rel_pos_periodic"
+    cfg = R.EnfConfig(num_in=3 if inv == "ball" else 2, num_hidden=hidden, num_heads=heads, num_out=1, latent_dim=16, invariant_type=inv,
+                      embedding_freq_multiplier=(0.05, 0.1))
+    params, x, p, a, sigma, d_out = make_case(cfg, 2, 300, 16, seed=41)
+    nef = _nef(cfg, "bf16")
+    grads = []
+    for with_weights in (True, False):
+        P = R.tree_map(lambda t: t.to("cuda", torch.float32).contiguous().requires_grad_(with_weights), params)
+        pg, ag, sg = (f32(t).requires_grad_(True) for t in (p, a, sigma))
+        nef.apply(P, f32(x), pg, ag, sg).backward(f32(d_out))
+        grads.append((pg.grad, ag.grad, sg.grad))
+    for full, lat in zip(*grads):
+        assert rel_err(lat, full) < 1e-5
