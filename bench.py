@@ -304,6 +304,69 @@ def ode_line(args):
     print(json.dumps(line))
 
 
+def meta_line(args):
+    """`--meta`: one first-order Meta-SGD training step of PDETrainer (pde_trainer.py:122-235, 237-288) at the config's full
+    size: K = 3 inner steps (nef.apply + latents-only backward + SGD update of p, a per field) from the shared latents, then the
+    reconstruction loss of the adapted latents and its backward with all weight gradients.  4 forward + 4 backward passes over
+    all B x C queries per step; the metric counts the B x C queries once per step."""
+    import torch
+    import enf_pde_b200 as E
+    cfg = dict(CONFIGS[args.config])
+    assert torch.cuda.is_available(), "bench.py --meta needs a CUDA device"
+    dev = torch.device("cuda", 0)
+    inv = E.get_ca_invariant(types.SimpleNamespace(invariant_type=cfg["invariant_type"], num_in=cfg["num_in"]))
+    nef = E.EquivariantCrossAttentionNeF(cfg["d"], cfg["H"], 0, cfg["O"], cfg["L"], inv, inv, "rff", cfg["freq"], True, cfg["window"],
+                                         precision=args.precision)
+    B, Z, K = cfg["B"], cfg["Z"], 3
+    gen = torch.Generator().manual_seed(99)
+    p_h, a_h, s_h = E.init_latents(inv, B, Z, cfg["L"], polar_grid=cfg["polar_grid"])
+    from enf_pde_b200.latents import make_coords
+    x_d = make_coords(inv, cfg["grid"]).contiguous().to(dev)
+    C = x_d.shape[0]
+    img = torch.randn(B, C, cfg["O"], generator=gen).to(dev)
+    variables = nef.init(0, x_d[None].cpu(), p_h.to(dev), a_h.to(dev), s_h.to(dev))
+    leaves = E.params_to_leaves(variables)
+    for t in leaves:
+        t.requires_grad_(True)
+    lrs = {"p_pos": torch.tensor([1.0]), "p_ori": torch.tensor([1.0]), "a": torch.full((cfg["L"],), 5.0), "gaussian_window": torch.tensor([0.0])}
+    masks = [torch.arange(C, device=dev) for _ in range(K + 1)]       # every query at every step (the reference sub-samples to fit memory)
+    p_d, a_d = p_h.to(dev), a_h.to(dev)
+    s_d = s_h.to(dev) if cfg["window"] else None
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        loss, _ = E.inner_loop(nef, variables, x_d, img, p_d, a_d, s_d, lrs, K, masks=masks)
+        loss.backward()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    with ClockSampler(0) as sampler:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    f_alg, _ = flops_per_pair(cfg, inv.dim)
+    flop = (K + 1) * 3.0 * (f_alg * B * C * Z + flops_per_query_tail(cfg) * B * C)
+    peaks = read_peaks()
+    ach = flop / (ms * 1e-3) / 1e12
+    print(json.dumps({"metric": "coord-queries/sec (first-order Meta-SGD training step: 3 inner steps + outer fwd+bwd)", "value": B * C / (ms * 1e-3),
+                      "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05) + f32",
+                      "data": "synthetic", "loss": float(loss.detach()),
+                      "config": {"workload": f"{args.config}: {cfg['label']}", "B": B, "C": C, "Z": Z, "d": cfg["d"], "H": cfg["H"], "inner_steps": K,
+                                 "passes": "4 forward + 3 latents-only backward + 1 full backward over all B x C queries"},
+                      "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                                   "traffic": None, "algorithmic_flop_per_step": flop,
+                                   "note": "contract FLOPs of 4 forward + 4 backward passes (the latents-only backward's skipped weight-gradient products are still counted)"},
+                      "clocks": sampler.summary()}))
+
+
 def model_ws_mb(model, p, a):
     import ctypes
     from enf_pde_b200 import ode
@@ -330,11 +393,15 @@ def main():
     ap.add_argument("--out-bf16", action="store_true", help="forward-only: bfloat16 decoded field (ENF_FLAG_OUT_BF16)")
     ap.add_argument("--recompute", action="store_true", help="bounded-memory training: ENF_FLAG_RECOMPUTE")
     ap.add_argument("--chunk-fields", type=int, default=0)
+    ap.add_argument("--meta", action="store_true",
+                    help="first-order Meta-SGD training step line (SURVEY 8f-1): K = 3 latents-only inner steps + the outer fwd+bwd")
     ap.add_argument("--ode", action="store_true",
                     help="latent ODE model line (SURVEY 8f-3): PonitaODEGen fwd + bwd at config_navier_stokes.yaml's `node:` sizes")
     args = ap.parse_args()
     if args.ode:
         return ode_line(args)
+    if args.meta:
+        return meta_line(args)
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
