@@ -39,6 +39,7 @@
 #include <type_traits>
 
 #include "../../include/enf_b200.h"
+#include "../../include/enf_ode_b200.h"
 #include "xla/ffi/api/c_api.h"
 #include "xla/ffi/api/ffi.h"
 
@@ -138,6 +139,88 @@ ffi::Error BwdImpl(cudaStream_t stream, F32 x, F32 p, F32 a, F32 sigma, ffi::Buf
                 "enf_xattn_bwd");
 }
 
+// ---- latent ODE model (include/enf_ode_b200.h): ode_model.apply(params, (p, a, window)) and its vector-Jacobian product -------
+// (experiments/fitting/ode_models/ponita_ode_g.py:229-257; call sites pde_trainer.py:381,433,582).
+// Operands   fwd: p f32[B,Z,P], a f32[B,Z,L], <leaves in EnfOdeWeights order: 5 + 8 * layers + 2 (+1 with an orientation)>
+//            bwd: p, a, workspace, g_dp, g_da, <the same leaves>
+// Results    fwd: dp_dt f32[B,Z,P], da_dt f32[B,Z,L], workspace u8[enf_ode_workspace_bytes]
+//            bwd: workspace (aliased to operand 2), <leaf gradients>, gp f32[B,Z,P], ga f32[B,Z,L]
+// Attributes: hidden, basis, layers, widen, degree, Dx, invariant_kind (i32).
+ffi::Error describe_ode(const F32& p, const F32& a, int32_t hidden, int32_t basis, int32_t layers, int32_t widen, int32_t degree,
+                        int32_t Dx, int32_t invariant_kind, EnfOdeDesc* desc, bool* has_ori) {
+  std::memset(desc, 0, sizeof(*desc));
+  auto pd = p.dimensions(), ad = a.dimensions();
+  if (pd.size() != 3 || ad.size() != 3 || ad[0] != pd[0] || ad[1] != pd[1])
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode: expected p[B,Z,P], a[B,Z,L]");
+  desc->B = (int32_t)pd[0]; desc->Z = (int32_t)pd[1]; desc->L = (int32_t)ad[2];
+  desc->hidden = hidden; desc->basis = basis; desc->layers = layers; desc->widen = widen; desc->degree = degree;
+  desc->Dx = Dx; desc->invariant_kind = invariant_kind;
+  if (pd[2] != enf_pose_dim(invariant_kind, Dx)) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode: pose width does not match the invariant");
+  if (layers < 1 || layers > ENF_ODE_MAX_LAYERS) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode: layers out of range");
+  *has_ori = invariant_kind == ENF_INV_PONITA;
+  return ffi::Error::Success();
+}
+
+// leaves arrive in EnfOdeWeights order: kb_w0, kb_b0, kb_w1, kb_b1, stem_w, 8 per layer, ro_scalar, ro_rel [, ro_ori]
+template <class Struct, class Args>
+ffi::Error collect_ode_leaves(Args& args, size_t first, int layers, bool has_ori, Struct* out) {
+  std::memset(out, 0, sizeof(*out));
+  // both structs are dense arrays of pointers (const float* / float*): fill them slot by slot
+  auto** head = reinterpret_cast<float**>(out);
+  auto** layer0 = head + 5;
+  auto** tail = head + 5 + 8 * ENF_ODE_MAX_LAYERS;
+  static_assert(sizeof(Struct) == sizeof(float*) * ENF_ODE_NUM_WEIGHT_LEAVES, "EnfOdeWeights / EnfOdeWeightGrads are dense pointer arrays");
+  const int n = 5 + 8 * layers + 2 + (has_ori ? 1 : 0);
+  for (int i = 0; i < n; ++i) {
+    auto buf = args.template get<F32>(first + i);
+    if (!buf.has_value()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode: leaf " + std::to_string(i) + " is not f32");
+    float* ptr;
+    if constexpr (std::is_same_v<Args, ffi::RemainingRets>) ptr = (*buf)->typed_data();
+    else ptr = const_cast<float*>(buf->typed_data());
+    if (i < 5) head[i] = ptr;
+    else if (i < 5 + 8 * layers) layer0[i - 5] = ptr;       // EnfOdeLayer[] is a dense array of 8 pointers each
+    else tail[i - 5 - 8 * layers] = ptr;
+  }
+  return ffi::Error::Success();
+}
+
+ffi::Error OdeFwdImpl(cudaStream_t stream, F32 p, F32 a, ffi::RemainingArgs leaves, ffi::ResultBuffer<ffi::F32> dp_dt,
+                      ffi::ResultBuffer<ffi::F32> da_dt, ffi::ResultBuffer<ffi::U8> workspace, int32_t hidden, int32_t basis,
+                      int32_t layers, int32_t widen, int32_t degree, int32_t Dx, int32_t invariant_kind) {
+  EnfOdeDesc desc;
+  bool has_ori;
+  if (auto e = describe_ode(p, a, hidden, basis, layers, widen, degree, Dx, invariant_kind, &desc, &has_ori); e.failure()) return e;
+  if ((int)leaves.size() != 5 + 8 * layers + 2 + (has_ori ? 1 : 0)) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode_fwd: wrong number of weight leaves");
+  EnfOdeWeights w;
+  if (auto e = collect_ode_leaves(leaves, 0, layers, has_ori, &w); e.failure()) return e;
+  const size_t need = enf_ode_workspace_bytes(&desc);
+  if (need == 0) return status(ENF_ERR_BAD_DESC, "enf_ode_workspace_bytes");
+  if ((size_t)workspace->element_count() < need) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode_fwd: workspace result too small");
+  return status(enf_ode_fwd(&desc, &w, p.typed_data(), a.typed_data(), dp_dt->typed_data(), da_dt->typed_data(), workspace->typed_data(),
+                            (size_t)workspace->element_count(), (enf_stream_t)stream), "enf_ode_fwd");
+}
+
+ffi::Error OdeBwdImpl(cudaStream_t stream, F32 p, F32 a, ffi::Buffer<ffi::U8> workspace, F32 g_dp, F32 g_da, ffi::RemainingArgs leaves,
+                      ffi::ResultBuffer<ffi::U8> workspace_out, ffi::RemainingRets grads, int32_t hidden, int32_t basis, int32_t layers,
+                      int32_t widen, int32_t degree, int32_t Dx, int32_t invariant_kind) {
+  EnfOdeDesc desc;
+  bool has_ori;
+  if (auto e = describe_ode(p, a, hidden, basis, layers, widen, degree, Dx, invariant_kind, &desc, &has_ori); e.failure()) return e;
+  const int n = 5 + 8 * layers + 2 + (has_ori ? 1 : 0);
+  if ((int)leaves.size() != n || (int)grads.size() != n + 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode_bwd: wrong number of leaves / gradients");
+  if (workspace_out->typed_data() != workspace.typed_data())
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode_bwd: the workspace result must alias the workspace operand (input_output_aliases={2: 0})");
+  EnfOdeWeights w;
+  EnfOdeWeightGrads gw;
+  if (auto e = collect_ode_leaves(leaves, 0, layers, has_ori, &w); e.failure()) return e;
+  if (auto e = collect_ode_leaves(grads, 0, layers, has_ori, &gw); e.failure()) return e;
+  auto gp = grads.get<F32>(n), ga = grads.get<F32>(n + 1);
+  if (!gp.has_value() || !ga.has_value()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "enf_ode_bwd: latent gradients must be f32");
+  return status(enf_ode_bwd(&desc, &w, p.typed_data(), a.typed_data(), g_dp.typed_data(), g_da.typed_data(), &gw, (*gp)->typed_data(),
+                            (*ga)->typed_data(), workspace_out->typed_data(), (size_t)workspace_out->element_count(), (enf_stream_t)stream),
+                "enf_ode_bwd");
+}
+
 }  // namespace
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnFwd, FwdImpl,
@@ -181,6 +264,34 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfXattnBwd, BwdImpl,
                                   .Attr<int32_t>("precision")
                                   .Attr<int32_t>("flags")
                                   .Attr<int32_t>("chunk_fields"));
+
+#define ENF_ODE_ATTRS() \
+  .Attr<int32_t>("hidden").Attr<int32_t>("basis").Attr<int32_t>("layers").Attr<int32_t>("widen").Attr<int32_t>("degree") \
+  .Attr<int32_t>("Dx").Attr<int32_t>("invariant_kind")
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfOdeFwd, OdeFwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<F32>()   // p
+                                  .Arg<F32>()   // a
+                                  .RemainingArgs()
+                                  .Ret<F32>()                    // dp/dt
+                                  .Ret<F32>()                    // da/dt
+                                  .Ret<ffi::Buffer<ffi::U8>>()   // workspace
+                                  ENF_ODE_ATTRS());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(EnfOdeBwd, OdeBwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<F32>()                    // p
+                                  .Arg<F32>()                    // a
+                                  .Arg<ffi::Buffer<ffi::U8>>()   // workspace of the matching forward
+                                  .Arg<F32>()                    // cotangent of dp/dt
+                                  .Arg<F32>()                    // cotangent of da/dt
+                                  .RemainingArgs()
+                                  .Ret<ffi::Buffer<ffi::U8>>()   // workspace, aliased to operand 2
+                                  .RemainingRets()
+                                  ENF_ODE_ATTRS());
 
 #else   // no jaxlib headers: nothing to build (see the header comment)
 

@@ -42,6 +42,8 @@ def _register():
     shim = ctypes.CDLL(_SHIM)
     jax.ffi.register_ffi_target("enf_xattn_fwd", jax.ffi.pycapsule(shim.EnfXattnFwd), platform="CUDA")
     jax.ffi.register_ffi_target("enf_xattn_bwd", jax.ffi.pycapsule(shim.EnfXattnBwd), platform="CUDA")
+    jax.ffi.register_ffi_target("enf_ode_fwd", jax.ffi.pycapsule(shim.EnfOdeFwd), platform="CUDA")
+    jax.ffi.register_ffi_target("enf_ode_bwd", jax.ffi.pycapsule(shim.EnfOdeBwd), platform="CUDA")
     _registered = True
 
 
@@ -101,3 +103,49 @@ def make_enf_apply(num_hidden, num_heads, num_out, latent_dim, invariant_type, n
 
     enf_apply.defvjp(vjp_fwd, vjp_bwd)
     return enf_apply
+
+
+def make_ode_apply(num_hidden, num_layers, latent_dim, invariant_type, num_in, basis_dim, degree, widening_factor):
+    """Returns ode_apply(leaves, p, a) -> (dp/dt, da/dt), differentiable once in leaves, p, a: the body of
+    `ode_model.apply(params, (p, a, window))` for PonitaODEGen (ponita_ode_g.py:229-257; the window's derivative is zeros_like(window),
+    which the caller adds).  `leaves`: the arrays of `params['ponita']` in EnfOdeWeights order (`enf_pde_b200.ode.leaf_paths`).
+    Reference-side use (pde_trainer.py:381,433,582):  f=lambda z, t: (*ode_apply(leaves, z[0], z[1]), jnp.zeros_like(z[2]))"""
+    _register()
+    from . import ode as _ode
+    lib = _ode._load()
+    kind = _lib.INVARIANT_KINDS[invariant_type]
+    attrs = dict(hidden=np.int32(num_hidden), basis=np.int32(basis_dim), layers=np.int32(num_layers), widen=np.int32(widening_factor),
+                 degree=np.int32(degree), Dx=np.int32(num_in), invariant_kind=np.int32(kind))
+
+    def ws_bytes(B, Z):
+        desc = _ode.EnfOdeDesc(B=B, Z=Z, L=latent_dim, hidden=num_hidden, basis=basis_dim, layers=num_layers, widen=widening_factor,
+                               degree=degree, Dx=num_in, invariant_kind=kind)
+        n = lib.enf_ode_workspace_bytes(ctypes.byref(desc))
+        if n == 0:
+            raise ValueError(lib.enf_last_error().decode())
+        return n
+
+    def fwd_call(leaves, p, a):
+        shapes = (jax.ShapeDtypeStruct(p.shape, jnp.float32), jax.ShapeDtypeStruct(a.shape, jnp.float32),
+                  jax.ShapeDtypeStruct((ws_bytes(p.shape[0], p.shape[1]),), jnp.uint8))
+        return jax.ffi.ffi_call("enf_ode_fwd", shapes)(p, a, *leaves, **attrs)
+
+    @jax.custom_vjp
+    def ode_apply(leaves, p, a):
+        return fwd_call(leaves, p, a)[:2]
+
+    def vjp_fwd(leaves, p, a):
+        dp, da, ws = fwd_call(leaves, p, a)
+        return (dp, da), (ws, leaves, p, a)
+
+    def vjp_bwd(res, cot):
+        ws, leaves, p, a = res
+        g_dp, g_da = cot
+        shapes = [jax.ShapeDtypeStruct(ws.shape, jnp.uint8)] + [jax.ShapeDtypeStruct(l.shape, jnp.float32) for l in leaves]
+        shapes += [jax.ShapeDtypeStruct(p.shape, jnp.float32), jax.ShapeDtypeStruct(a.shape, jnp.float32)]
+        outs = jax.ffi.ffi_call("enf_ode_bwd", tuple(shapes), input_output_aliases={2: 0})(p, a, ws, g_dp, g_da, *leaves, **attrs)[1:]
+        n = len(leaves)
+        return (list(outs[:n]), outs[n], outs[n + 1])
+
+    ode_apply.defvjp(vjp_fwd, vjp_bwd)
+    return ode_apply
