@@ -5,6 +5,6 @@ from .invariant import (BaseInvariant, get_ca_invariant, get_sa_invariant, Ponit
                         RelativePositionPolarPeriodic, RelativeLatitudePeriodic, BallInvariant, BallLatInvariant)
 from .nef import EquivariantCrossAttentionNeF, params_to_leaves, leaves_to_params, last_launch_counts   # noqa: F401
 from .latents import init_latents, make_coords   # noqa: F401
-from .ode import PonitaODEGen, solve_latent_ode   # noqa: F401
+from .ode import PonitaODEGen, MLPODE, solve_latent_ode   # noqa: F401
 from .meta import inner_loop, outer_step_gradients   # noqa: F401
 from ._lib import EnfLibraryError, load as load_library   # noqa: F401

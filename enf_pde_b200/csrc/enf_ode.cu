@@ -743,3 +743,144 @@ int enf_ode_solve(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p
 }
 
 }  // extern "C"
+
+// ---- MLPODE (mlp_ode.py:5-42) -----------------------------------------------------------------------------------------------
+namespace {
+struct MDims { int P, L, Hd, In; int64_t m; };
+struct MWs {
+  int64_t total = 0;
+  int64_t take(int64_t n) { int64_t o = total; total += (n + 63) / 64 * 64; return o; }
+  int64_t in, pre[2][3], act[2][3], g0, g1, g_in, g_in2;
+};
+int mlp_validate(const EnfMlpOdeDesc* D, MDims* o) {
+  if (!D) return enf_set_error(ENF_ERR_NULL_POINTER, "desc is NULL");
+  if (D->B <= 0 || D->Z <= 0 || D->L <= 0 || D->hidden <= 0) return enf_set_error(ENF_ERR_BAD_DESC, "B, Z, L, hidden must be positive");
+  if (D->P != 2) return enf_set_error(ENF_ERR_UNSUPPORTED, "MLPODE emits a 2-component pose derivative (mlp_ode.py:27): P must be 2");
+  if (D->reserved[0] || D->reserved[1] || D->reserved[2]) return enf_set_error(ENF_ERR_BAD_DESC, "reserved fields must be 0");
+  o->P = D->P; o->L = D->L; o->Hd = D->hidden; o->In = D->P + D->L; o->m = (int64_t)D->B * D->Z;
+  return ENF_OK;
+}
+MWs mlp_ws(const MDims& d) {
+  MWs w;
+  w.in = w.take(d.m * d.In);
+  for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) { w.pre[k][l] = w.take(d.m * d.Hd); w.act[k][l] = w.take(d.m * d.Hd); }
+  w.g0 = w.take(d.m * d.Hd); w.g1 = w.take(d.m * d.Hd); w.g_in = w.take(d.m * d.In); w.g_in2 = w.take(d.m * d.In);
+  return w;
+}
+// in = [p | a - 1]  (mlp_ode.py:35,38)
+__global__ void mlpode_concat_kernel(int P, int L, int64_t m, const float* __restrict__ p, const float* __restrict__ a, float* __restrict__ in) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int In = P + L;
+  if (t >= m * In) return;
+  const int64_t r = t / In; const int c = (int)(t % In);
+  in[t] = c < P ? p[r * P + c] : a[r * L + (c - P)] - 1.f;
+}
+__global__ void mlpode_split_kernel(int P, int L, int64_t m, const float* __restrict__ g_in, float* __restrict__ gp, float* __restrict__ ga) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int In = P + L;
+  if (t >= m * In) return;
+  const int64_t r = t / In; const int c = (int)(t % In);
+  if (c < P) gp[r * P + c] = g_in[t]; else ga[r * L + (c - P)] = g_in[t];
+}
+int mlp_check(const EnfMlpOdeWeights* w, const void* workspace) {
+  if (!w) return enf_set_error(ENF_ERR_NULL_POINTER, "weights are NULL");
+  for (int l = 0; l < 4; ++l) if (!w->a_w[l] || !w->a_b[l] || !w->p_w[l] || !w->p_b[l]) return enf_set_error(ENF_ERR_NULL_POINTER, "a weight leaf is NULL");
+  if (!workspace || ((uintptr_t)workspace & 255)) return enf_set_error(ENF_ERR_WORKSPACE, "workspace is NULL or not 256-byte aligned");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return enf_set_error(ENF_ERR_NO_DEVICE, "no CUDA device");
+  return ENF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+size_t enf_mlpode_workspace_bytes(const EnfMlpOdeDesc* desc) {
+  MDims d;
+  if (mlp_validate(desc, &d) != ENF_OK) return 0;
+  return (size_t)mlp_ws(d).total * sizeof(float);
+}
+
+int enf_mlpode_fwd(const EnfMlpOdeDesc* desc, const EnfMlpOdeWeights* w, const float* p, const float* a, float* dp_dt, float* da_dt,
+                   void* workspace, size_t workspace_bytes, enf_stream_t stream) {
+  MDims d;
+  int rc = mlp_validate(desc, &d);
+  if (rc != ENF_OK) return rc;
+  if (!p || !a || !dp_dt || !da_dt) return enf_set_error(ENF_ERR_NULL_POINTER, "NULL argument");
+  if ((rc = mlp_check(w, workspace)) != ENF_OK) return rc;
+  MWs Y = mlp_ws(d);
+  if (workspace_bytes < (size_t)Y.total * sizeof(float)) return enf_set_error(ENF_ERR_WORKSPACE, "workspace too small: see enf_mlpode_workspace_bytes");
+  Run R; R.st = (cudaStream_t)stream; R.ws = (float*)workspace;
+  float* W = R.ws;
+  mlpode_concat_kernel<<<nblocks(d.m * d.In, 256), 256, 0, R.st>>>(d.P, d.L, d.m, p, a, W + Y.in);
+  for (int k = 0; k < 2; ++k) {                 // 0: mlp_a -> da/dt (L), 1: mlp_p -> dp/dt (2)
+    const float* const* wk = k == 0 ? w->a_w : w->p_w;
+    const float* const* bk = k == 0 ? w->a_b : w->p_b;
+    const int nout = k == 0 ? d.L : 2;
+    R.gemm(d.m, d.Hd, d.In, enf_mat(W + Y.in, d.In), enf_mat(wk[0], d.Hd), enf_mat(W + Y.pre[k][0], d.Hd), o_bias(bk[0], W + Y.act[k][0]));
+    for (int l = 1; l < 3; ++l)
+      R.gemm(d.m, d.Hd, d.Hd, enf_mat(W + Y.act[k][l - 1], d.Hd), enf_mat(wk[l], d.Hd), enf_mat(W + Y.pre[k][l], d.Hd), o_bias(bk[l], W + Y.act[k][l]));
+    R.gemm(d.m, nout, d.Hd, enf_mat(W + Y.act[k][2], d.Hd), enf_mat(wk[3], nout), enf_mat(k == 0 ? da_dt : dp_dt, nout), o_bias(bk[3]));
+  }
+  if (R.failed) return enf_set_error(ENF_ERR_CUDA, "a GEMM of MLPODE could not be configured");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return enf_set_error(ENF_ERR_CUDA, (std::string("CUDA error while enqueueing enf_mlpode_fwd: ") + cudaGetErrorString(e)).c_str());
+  return ENF_OK;
+}
+
+int enf_mlpode_bwd(const EnfMlpOdeDesc* desc, const EnfMlpOdeWeights* w, const float* p, const float* a, const float* g_dp, const float* g_da,
+                   const EnfMlpOdeWeightGrads* dW, float* gp, float* ga, void* workspace, size_t workspace_bytes, enf_stream_t stream) {
+  MDims d;
+  int rc = mlp_validate(desc, &d);
+  if (rc != ENF_OK) return rc;
+  if (!p || !a || !g_dp || !g_da || !gp || !ga) return enf_set_error(ENF_ERR_NULL_POINTER, "NULL argument");
+  if ((rc = mlp_check(w, workspace)) != ENF_OK) return rc;
+  MWs Y = mlp_ws(d);
+  if (workspace_bytes < (size_t)Y.total * sizeof(float)) return enf_set_error(ENF_ERR_WORKSPACE, "workspace too small");
+  Run R; R.st = (cudaStream_t)stream; R.ws = (float*)workspace;
+  cudaStream_t st = R.st;
+  float* W = R.ws;
+  const bool wg = dW != nullptr;
+  auto zero = [&](float* ptr, int64_t n) { cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
+  for (int k = 0; k < 2; ++k) {
+    const float* const* wk = k == 0 ? w->a_w : w->p_w;
+    float* const* gwk = wg ? (k == 0 ? dW->a_w : dW->p_w) : nullptr;
+    float* const* gbk = wg ? (k == 0 ? dW->a_b : dW->p_b) : nullptr;
+    const int nout = k == 0 ? d.L : 2;
+    const float* g_out = k == 0 ? g_da : g_dp;
+    if (wg) {
+      for (int l = 0; l < 4; ++l) if (!gwk[l] || !gbk[l]) return enf_set_error(ENF_ERR_NULL_POINTER, "a weight-gradient leaf is NULL");
+      zero(gwk[0], (int64_t)d.In * d.Hd); zero(gwk[1], (int64_t)d.Hd * d.Hd); zero(gwk[2], (int64_t)d.Hd * d.Hd); zero(gwk[3], (int64_t)d.Hd * nout);
+      zero(gbk[0], d.Hd); zero(gbk[1], d.Hd); zero(gbk[2], d.Hd); zero(gbk[3], nout);
+      R.gemm(d.Hd, nout, (int)d.m, enf_mat(W + Y.act[k][2], 1, d.Hd), enf_mat(g_out, nout), enf_mat(gwk[3], nout), o_acc());
+      R.launches += enf_launch_colsum(st, g_out, d.m, nout, nout, gbk[3], nullptr, 0);
+    }
+    float* g = W + Y.g0;
+    float* g2 = W + Y.g1;
+    R.gemm(d.m, d.Hd, nout, enf_mat(g_out, nout), enf_mat(wk[3], 1, nout), enf_mat(g, d.Hd), o_dgelu(W + Y.pre[k][2]));
+    for (int l = 2; l >= 1; --l) {
+      if (wg) {
+        R.gemm(d.Hd, d.Hd, (int)d.m, enf_mat(W + Y.act[k][l - 1], 1, d.Hd), enf_mat(g, d.Hd), enf_mat(gwk[l], d.Hd), o_acc());
+        R.launches += enf_launch_colsum(st, g, d.m, d.Hd, d.Hd, gbk[l], nullptr, 0);
+      }
+      R.gemm(d.m, d.Hd, d.Hd, enf_mat(g, d.Hd), enf_mat(wk[l], 1, d.Hd), enf_mat(g2, d.Hd), o_dgelu(W + Y.pre[k][l - 1]));
+      float* t = g; g = g2; g2 = t;
+    }
+    if (wg) {
+      R.gemm(d.In, d.Hd, (int)d.m, enf_mat(W + Y.in, 1, d.In), enf_mat(g, d.Hd), enf_mat(gwk[0], d.Hd), o_acc());
+      R.launches += enf_launch_colsum(st, g, d.m, d.Hd, d.Hd, gbk[0], nullptr, 0);
+    }
+    if (k == 0) {
+      R.gemm(d.m, d.In, d.Hd, enf_mat(g, d.Hd), enf_mat(wk[0], 1, d.Hd), enf_mat(W + Y.g_in, d.In));
+    } else {                                    // second MLP: add to the first one's input cotangent
+      R.gemm(d.m, d.In, d.Hd, enf_mat(g, d.Hd), enf_mat(wk[0], 1, d.Hd), enf_mat(W + Y.g_in2, d.In));
+      R.launches += enf_launch_add(st, W + Y.g_in, W + Y.g_in, W + Y.g_in2, d.m * d.In);
+    }
+  }
+  mlpode_split_kernel<<<nblocks(d.m * d.In, 256), 256, 0, st>>>(d.P, d.L, d.m, W + Y.g_in, gp, ga);
+  if (R.failed) return enf_set_error(ENF_ERR_CUDA, "a GEMM of the MLPODE backward could not be configured");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return enf_set_error(ENF_ERR_CUDA, (std::string("CUDA error while enqueueing enf_mlpode_bwd: ") + cudaGetErrorString(e)).c_str());
+  return ENF_OK;
+}
+
+}  // extern "C"

@@ -39,7 +39,16 @@ class EnfOdeWeights(ctypes.Structure):
                 [(n, ctypes.c_void_p) for n in _TAIL])
 
 
-EXPORTS = ("enf_ode_workspace_bytes", "enf_ode_fwd", "enf_ode_bwd", "enf_ode_solve")
+class EnfMlpOdeDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "Z", "P", "L", "hidden")] + [("reserved", ctypes.c_int32 * 3)]
+
+
+class EnfMlpOdeWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * 4) for n in ("a_w", "a_b", "p_w", "p_b")]
+
+
+EXPORTS = ("enf_ode_workspace_bytes", "enf_ode_fwd", "enf_ode_bwd", "enf_ode_solve", "enf_mlpode_workspace_bytes", "enf_mlpode_fwd",
+           "enf_mlpode_bwd")
 _bound = False
 
 
@@ -57,6 +66,13 @@ def _load():
         lib.enf_ode_bwd.argtypes = [D, W, vp, vp, vp, vp, W, vp, vp, vp, ctypes.c_size_t, vp]
         lib.enf_ode_solve.restype = ctypes.c_int
         lib.enf_ode_solve.argtypes = [D, W, vp, vp, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, vp, vp, vp, ctypes.c_size_t, vp]
+        MD, MW = ctypes.POINTER(EnfMlpOdeDesc), ctypes.POINTER(EnfMlpOdeWeights)
+        lib.enf_mlpode_workspace_bytes.restype = ctypes.c_size_t
+        lib.enf_mlpode_workspace_bytes.argtypes = [MD]
+        lib.enf_mlpode_fwd.restype = ctypes.c_int
+        lib.enf_mlpode_fwd.argtypes = [MD, MW, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        lib.enf_mlpode_bwd.restype = ctypes.c_int
+        lib.enf_mlpode_bwd.argtypes = [MD, MW, vp, vp, vp, vp, MW, vp, vp, vp, ctypes.c_size_t, vp]
         _bound = True
     return lib
 
@@ -234,6 +250,102 @@ class PonitaODEGen:
             _lib.check(rc, "enf_ode_solve")
             w_traj = None if window is None else window[:, None].expand(B, num_steps + 1, *window.shape[1:]).contiguous()
         return p_traj, a_traj, w_traj
+
+
+_MLP_PATHS = [f"mlp_{k}/layers_{i}/{leaf}" for k in "ap" for leaf in ("kernel", "bias") for i in (0, 2, 4, 6)]   # a_w, a_b, p_w, p_b
+
+
+def _mlp_struct(leaves):
+    w = EnfMlpOdeWeights()
+    it = iter(leaves)
+    for name in ("a_w", "a_b", "p_w", "p_b"):
+        arr = getattr(w, name)
+        for i in range(4):
+            arr[i] = next(it).data_ptr()
+    return w
+
+
+class _MlpOdeFunction(torch.autograd.Function):
+    """enf_mlpode_fwd / enf_mlpode_bwd on torch's current stream."""
+
+    @staticmethod
+    def forward(ctx, desc_kw, p, a, *leaves):
+        lib = _load()
+        desc = EnfMlpOdeDesc(**desc_kw)
+        p, a = _as_f32(p, "p"), _as_f32(a, "a")
+        leaves = [_as_f32(t, "ode parameter") for t in leaves]
+        nbytes = lib.enf_mlpode_workspace_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            raise _lib.EnfLibraryError("bad MLPODE description: " + lib.enf_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
+        dp = torch.empty(p.shape[0], p.shape[1], 2, device=p.device)
+        da = torch.empty_like(a)
+        w = _mlp_struct(leaves)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        with torch.cuda.device(p.device):
+            rc = lib.enf_mlpode_fwd(ctypes.byref(desc), ctypes.byref(w), _ptr(p), _ptr(a), _ptr(dp), _ptr(da), _ptr(ws), nbytes, stream)
+        _lib.check(rc, "enf_mlpode_fwd")
+        ctx.desc_kw, ctx.ws, ctx.nbytes = desc_kw, ws, nbytes
+        ctx.save_for_backward(p, a, *leaves)
+        return dp, da
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_dp, g_da):
+        lib = _load()
+        desc = EnfMlpOdeDesc(**ctx.desc_kw)
+        p, a, *leaves = ctx.saved_tensors
+        g_dp = _as_f32(g_dp if g_dp is not None else torch.zeros(p.shape[0], p.shape[1], 2, device=p.device), "g_dp")
+        g_da = _as_f32(g_da if g_da is not None else torch.zeros_like(a), "g_da")
+        need_w = any(ctx.needs_input_grad[3:])
+        grads = [torch.empty_like(t) for t in leaves] if need_w else None
+        gp, ga = torch.empty_like(p), torch.empty_like(a)
+        w = _mlp_struct(leaves)
+        gw = _mlp_struct(grads) if need_w else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        with torch.cuda.device(p.device):
+            rc = lib.enf_mlpode_bwd(ctypes.byref(desc), ctypes.byref(w), _ptr(p), _ptr(a), _ptr(g_dp), _ptr(g_da),
+                                    ctypes.byref(gw) if need_w else None, _ptr(gp), _ptr(ga), _ptr(ctx.ws), ctx.nbytes, stream)
+        _lib.check(rc, "enf_mlpode_bwd")
+        return (None, gp, ga) + (tuple(grads) if need_w else (None,) * len(leaves))
+
+
+class MLPODE:
+    """experiments/fitting/ode_models/mlp_ode.py:5-42 (`cfg.node.name: mlp` of get_model_pde): same constructor fields (num_layers is
+    unused by the reference too: both MLPs have three hidden layers), `init` / `apply` on the latent tuple."""
+
+    def __init__(self, num_hidden: int, num_layers: int, scalar_num_out: int, vec_num_out: int):
+        if vec_num_out != 1:
+            raise NotImplementedError("vec_num_out must be 1 (the pose derivative has 2 * vec_num_out components and is added to 2-D poses)")
+        self.num_hidden, self.num_layers, self.scalar_num_out, self.vec_num_out = num_hidden, num_layers, scalar_num_out, vec_num_out
+
+    def init(self, rng, latents, device=None) -> Dict:
+        p, a = latents[0], latents[1]
+        device = device if device is not None else (p.device if torch.is_tensor(p) else "cuda")
+        g = rng if isinstance(rng, torch.Generator) else torch.Generator().manual_seed(int(rng))
+        n_in, H = p.shape[-1] + a.shape[-1], self.num_hidden
+
+        def dense(i, o):        # flax default: lecun-normal kernel, zero bias
+            x = torch.empty(i, o)
+            torch.nn.init.trunc_normal_(x, 0.0, 1.0, -2.0, 2.0, generator=g)
+            return {"kernel": (x * (math.sqrt(1.0 / i) / 0.87962566103423978)).to(device), "bias": torch.zeros(o, device=device)}
+
+        mlp = lambda out: {"layers_0": dense(n_in, H), "layers_2": dense(H, H), "layers_4": dense(H, H), "layers_6": dense(H, out)}
+        return {"params": {"mlp_a": mlp(self.scalar_num_out), "mlp_p": mlp(2 * self.vec_num_out)}}
+
+    def apply(self, variables, latents):
+        p, a, window = latents
+        flat = _flatten(variables["params"] if "params" in variables else variables)
+        try:
+            leaves = [flat[k] for k in _MLP_PATHS]
+        except KeyError as e:
+            raise KeyError(f"MLPODE parameter tree is missing {e}") from None
+        B, Z, P = p.shape
+        desc = dict(B=B, Z=Z, P=P, L=self.scalar_num_out, hidden=self.num_hidden)
+        dp, da = _MlpOdeFunction.apply(desc, p, a, *leaves)
+        return dp, da, (None if window is None else torch.zeros_like(window))
+
+    __call__ = apply
 
 
 def solve_latent_ode(f, latents, t0, tf, h, method="rk4", stop_gradient=False):

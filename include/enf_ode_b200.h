@@ -90,6 +90,28 @@ int enf_ode_bwd(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p, 
 int enf_ode_solve(const EnfOdeDesc* desc, const EnfOdeWeights* w, const float* p0, const float* a0, int32_t num_steps, float h,
                   int32_t method, float* p_traj, float* a_traj, void* workspace, size_t workspace_bytes, enf_stream_t stream);
 
+/* ---- MLPODE (cfg.node.name == "mlp"; experiments/fitting/ode_models/mlp_ode.py:5-42): two 4-layer MLPs (Dense -> gelu x3 -> Dense) on
+ * concat(p, a - 1) per latent; derivative_p_pos has 2 * vec_num_out = 2 components (the model is written for 2-D positional poses,
+ * P == 2), derivative_a has L.  Not equivariant: the ablation baseline of the reference's factory (experiments/fitting/__init__.py:41-47). */
+typedef struct EnfMlpOdeDesc {
+  int32_t B, Z;            /* latent sets, latents per set                         */
+  int32_t P;               /* raw pose width (must be 2: the output is added to p) */
+  int32_t L;               /* latent_dim (scalar_num_out)                          */
+  int32_t hidden;          /* cfg.node.num_hidden                                  */
+  int32_t reserved[3];     /* must be 0                                            */
+} EnfMlpOdeDesc;
+/* mlp_a/layers_{0,2,4,6} and mlp_p/layers_{0,2,4,6}: kernels (in, out) row-major, biases */
+typedef struct EnfMlpOdeWeights { const float *a_w[4], *a_b[4], *p_w[4], *p_b[4]; } EnfMlpOdeWeights;
+typedef struct EnfMlpOdeWeightGrads { float *a_w[4], *a_b[4], *p_w[4], *p_b[4]; } EnfMlpOdeWeightGrads;
+
+size_t enf_mlpode_workspace_bytes(const EnfMlpOdeDesc* desc);
+int enf_mlpode_fwd(const EnfMlpOdeDesc* desc, const EnfMlpOdeWeights* w, const float* p, const float* a, float* dp_dt, float* da_dt,
+                   void* workspace, size_t workspace_bytes, enf_stream_t stream);
+/* VJP on the workspace of a matching enf_mlpode_fwd; dW NULL skips the weight gradients; every output is overwritten. */
+int enf_mlpode_bwd(const EnfMlpOdeDesc* desc, const EnfMlpOdeWeights* w, const float* p, const float* a, const float* g_dp_dt,
+                   const float* g_da_dt, const EnfMlpOdeWeightGrads* dW, float* gp, float* ga, void* workspace, size_t workspace_bytes,
+                   enf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ Unfused PyTorch restatement (fp64 for checking) of, paths relative to /root/refe
   experiments/fitting/ode_models/ponita_ode_g.py:53-87    SepGconv   ('bsc,brsc->brc' over a bias-free Dense of the kernel basis)
   experiments/fitting/ode_models/ponita_ode_g.py:90-198   PonitaGen  (kernel basis MLP, a_stem, read-outs; kernel_size "global")
   experiments/fitting/ode_models/ponita_ode_g.py:201-257  PonitaODEGen (a - 1, angle derivative = last scalar channel, d sigma = 0)
+  experiments/fitting/ode_models/mlp_ode.py:5-42          MLPODE (the factory's non-equivariant baseline)
   experiments/fitting/trainers/trainer_utils/solvers.py:73-162  tree-mapped Euler / RK4 steps and the trajectory loop
   enf/steerable_attention/invariant/__init__.py:13-45     get_sa_invariant (self-attention variants: `ponita` -> Ponita2D)
 Third-party semantics restated as in oracle/enf_ref.py (flax Dense / LayerNorm eps 1e-6 fast variance, gelu tanh form).
@@ -111,6 +112,17 @@ def ponita_ode(cfg: OdeConfig, params: Dict, p, a):
         vec = vec + ((inv2 @ P["readout_vec_ori"]["kernel"]) * p_ori).mean(dim=-2)
         return torch.cat([vec, scalar[..., -1:]], dim=-1), scalar[..., :-1]          # :239-244
     return vec, scalar
+
+
+def mlp_ode(params: Dict, p, a):
+    """MLPODE.__call__ (experiments/fitting/ode_models/mlp_ode.py:30-42): (derivative_p_pos (B,Z,2), derivative_a (B,Z,L))."""
+    x = torch.cat([p, a - 1.0], dim=-1)                          # :35, :38
+
+    def mlp(t, x):
+        for i in (0, 2, 4):
+            x = R.gelu_tanh(R.dense(x, t[f"layers_{i}"]))
+        return R.dense(x, t["layers_6"])
+    return mlp(params["mlp_p"], x), mlp(params["mlp_a"], x)
 
 
 def ode_step(cfg: OdeConfig, params, state, h, method):

@@ -121,8 +121,57 @@ def build_case(name, c, rng):
     return rec
 
 
+def build_mlp_case(rng):
+    """MLPODE (experiments/fitting/ode_models/mlp_ode.py), the `node.name: mlp` option of get_model_pde."""
+    from experiments.fitting.ode_models.mlp_ode import MLPODE
+    B, Z, L, hidden = 2, 5, 6, 12
+    model = MLPODE(num_hidden=hidden, num_layers=3, scalar_num_out=L, vec_num_out=1)
+    p = rng.uniform(-1, 1, (B, Z, 2))
+    a = 1.0 + rng.standard_normal((B, Z, L)) * 0.5
+    sigma = np.full((B, Z, 1), 0.3)
+    variables = model.init(jax.random.PRNGKey(11), (p[:1], a[:1], sigma[:1]))
+    flat = flatten(variables["params"])
+    for k in flat:
+        if k.endswith("bias"):
+            flat[k] = flat[k] + rng.standard_normal(flat[k].shape) * 0.1
+
+    def f(p_, a_, flat_):
+        dp, da, dw = model.apply({"params": unflatten(flat_)}, (p_, a_, sigma))
+        assert np.all(dw == 0)
+        return dp, da
+
+    dp, da = f(p, a, flat)
+    cot_p, cot_a = rng.standard_normal(dp.shape), rng.standard_normal(da.shape)
+    fun = lambda p_, a_, fl: float(np.sum(f(p_, a_, fl)[0] * cot_p) + np.sum(f(p_, a_, fl)[1] * cot_a))
+    eps = 1e-6
+
+    def fd(arr, setter):
+        g = np.zeros_like(arr)
+        it = np.nditer(arr, flags=["multi_index"])
+        for _ in it:
+            i = it.multi_index
+            hi = arr.copy(); hi[i] += eps
+            lo = arr.copy(); lo[i] -= eps
+            g[i] = (setter(hi) - setter(lo)) / (2 * eps)
+        return g
+
+    gp, ga = fd(p, lambda v: fun(v, a, flat)), fd(a, lambda v: fun(p, v, flat))
+    direction = {k: rng.standard_normal(v.shape) for k, v in flat.items()}
+    dth = (fun(p, a, {k: flat[k] + eps * direction[k] for k in flat}) - fun(p, a, {k: flat[k] - eps * direction[k] for k in flat})) / (2 * eps)
+    rec = dict(p=p, a=a, sigma=sigma, dp=dp, da=da, cot_p=cot_p, cot_a=cot_a, gp=gp, ga=ga, dtheta_dir=np.float64(dth))
+    for k, v in flat.items():
+        rec["param:" + k] = v
+        rec["dir:" + k] = direction[k]
+    rec["meta"] = np.array(repr(dict(hidden=hidden, L=L, B=B, Z=Z)))
+    return rec
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if not only or "mlp" in only:
+        rec = build_mlp_case(np.random.default_rng(4242))
+        np.savez_compressed(os.path.join(HERE, "mlpode.npz"), **rec)
+        print("mlpode dp", rec["dp"].shape, "da", rec["da"].shape, sorted(k[6:] for k in rec if k.startswith("param:"))[:4])
     for name, c in CASES.items():
         if only and name not in only:
             continue

@@ -174,7 +174,7 @@ def test_ode_abi_exports_and_layouts():
     from enf_pde_b200 import ode
     lib = ode._load()
     header = open(os.path.join(ROOT, "include", "enf_ode_b200.h")).read()
-    declared = set(re.findall(r"\b(enf_ode_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(enf_(?:mlp)?ode_[a-z_0-9]+)\s*\(", header))
     assert declared == set(ode.EXPORTS), declared ^ set(ode.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), sym
@@ -188,6 +188,10 @@ def test_ode_abi_exports_and_layouts():
     for bad in (dict(layers=0), dict(layers=9), dict(degree=6), dict(B=0), dict(invariant_kind=42), dict(Dx=3), dict(hidden=0)):
         assert lib.enf_ode_workspace_bytes(ctypes.byref(ode.EnfOdeDesc(**{**ok, **bad}))) == 0, bad
         assert lib.enf_last_error()
+    assert ctypes.sizeof(ode.EnfMlpOdeDesc) == 32 and ctypes.sizeof(ode.EnfMlpOdeWeights) == 16 * 8
+    mok = dict(B=2, Z=8, P=2, L=16, hidden=64)
+    assert lib.enf_mlpode_workspace_bytes(ctypes.byref(ode.EnfMlpOdeDesc(**mok))) > 0
+    assert lib.enf_mlpode_workspace_bytes(ctypes.byref(ode.EnfMlpOdeDesc(**{**mok, "P": 3}))) == 0      # 2-component pose derivative
     # compute entry points refuse NULL arguments before touching the device
     d = ode.EnfOdeDesc(**ok)
     assert lib.enf_ode_fwd(ctypes.byref(d), None, None, None, None, None, None, 0, None) == -3

@@ -200,3 +200,27 @@ def test_ode_random_shapes(seed):
     # oracle and the kernels both use 0)
     # a single latent: the pose gradient cancels to 0 analytically between O(1) terms; float32 leaves ~1e-8 of them
     _check(cfg, params, p, a, cot_p, cot_a, gp_floor=1e-3 if Z == 1 else 1e-5)
+
+
+def test_mlpode_against_reference_fixture():
+    """MLPODE (`node.name: mlp`): the library's two MLPs + vector-Jacobian product vs the reference-source fixture and the oracle."""
+    import enf_pde_b200 as E
+    from test_oracle_ode_golden import _load_mlp
+    meta, params, _, rec = _load_mlp()
+    Po = R.tree_map(lambda t: t.clone().requires_grad_(True), params)
+    po, ao = rec["p"].clone().requires_grad_(True), rec["a"].clone().requires_grad_(True)
+    dpo, dao = O.mlp_ode(Po, po, ao)
+    ((dpo * rec["cot_p"]).sum() + (dao * rec["cot_a"]).sum()).backward()
+    model = E.MLPODE(meta["hidden"], 3, meta["L"], 1)
+    P = _cuda({"params": params})
+    pg, ag = f32(rec["p"]).requires_grad_(True), f32(rec["a"]).requires_grad_(True)
+    dp, da, dw = model.apply(P, (pg, ag, f32(rec["sigma"])))
+    assert float(dw.abs().max()) == 0.0
+    ((dp * f32(rec["cot_p"])).sum() + (da * f32(rec["cot_a"])).sum()).backward()
+    errs = dict(dp=rel_err(dp.detach(), rec["dp"]), da=rel_err(da.detach(), rec["da"]), gp=rel_err(pg.grad, po.grad), ga=rel_err(ag.grad, ao.grad))
+    go, gc = R.tree_flatten(Po), R.tree_flatten(P["params"])
+    leaf = {k: rel_err(gc[k].grad, go[k].grad) for k in go}
+    print({k: f"{v:.2e}" for k, v in errs.items()}, max(leaf.values()))
+    assert all(v < TOL for v in errs.values()) and max(leaf.values()) < TOL_LEAF, (errs, leaf)
+    ours = R.tree_flatten(model.init(0, (rec["p"], rec["a"], rec["sigma"]), device="cpu")["params"])
+    assert sorted(ours) == sorted(R.tree_flatten(params)) and all(tuple(ours[k].shape) == tuple(v.shape) for k, v in R.tree_flatten(params).items())

@@ -49,3 +49,30 @@ def test_ode_param_tree_names_match_reference_module_structure():
     assert sorted(ours) == sorted(theirs)
     for k in ours:
         assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
+
+
+def _load_mlp():
+    import ast, os
+    import numpy as np
+    from helpers import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "mlpode.npz"))
+    t = lambda k: torch.tensor(z[k], dtype=torch.float64)
+    params = R.tree_unflatten({k[6:]: t(k) for k in z.files if k.startswith("param:")})
+    direction = R.tree_unflatten({k[4:]: t(k) for k in z.files if k.startswith("dir:")})
+    rec = {k: t(k) for k in ("p", "a", "sigma", "dp", "da", "cot_p", "cot_a", "gp", "ga")}
+    rec["dtheta_dir"] = float(z["dtheta_dir"])
+    return ast.literal_eval(str(z["meta"])), params, direction, rec
+
+
+def test_mlpode_matches_reference_source():
+    """MLPODE (mlp_ode.py) restated in the oracle vs the reference's own module over the shim: outputs and FD gradients."""
+    meta, params, direction, rec = _load_mlp()
+    P = R.tree_map(lambda t: t.clone().requires_grad_(True), params)
+    p, a = rec["p"].clone().requires_grad_(True), rec["a"].clone().requires_grad_(True)
+    dp, da = O.mlp_ode(P, p, a)
+    assert rel_err(dp, rec["dp"]) < 1e-11 and rel_err(da, rec["da"]) < 1e-11
+    ((dp * rec["cot_p"]).sum() + (da * rec["cot_a"]).sum()).backward()
+    assert rel_err(p.grad, rec["gp"]) < 2e-6 and rel_err(a.grad, rec["ga"]) < 2e-6
+    fp, fd = R.tree_flatten(P), R.tree_flatten(direction)
+    ddir = sum(float((fp[k].grad * fd[k]).sum()) for k in fp)
+    assert abs(ddir - rec["dtheta_dir"]) < 2e-6 * max(1.0, abs(rec["dtheta_dir"]))
