@@ -224,3 +224,61 @@ def test_mlpode_against_reference_fixture():
     assert all(v < TOL for v in errs.values()) and max(leaf.values()) < TOL_LEAF, (errs, leaf)
     ours = R.tree_flatten(model.init(0, (rec["p"], rec["a"], rec["sigma"]), device="cpu")["params"])
     assert sorted(ours) == sorted(R.tree_flatten(params)) and all(tuple(ours[k].shape) == tuple(v.shape) for k, v in R.tree_flatten(params).items())
+
+
+@pytest.mark.parametrize("precision,tol,tol_leaf", [("fp32", 1e-4, 2e-4), ("bf16", 2e-3, 1e-2)])
+def test_ode_phase_loss_against_oracle(precision, tol, tol_leaf):
+    """The ODE-phase objective of the trainer (`ode_loss`, pde_trainer.py:412-479) end to end on the GPU path: initial latents ->
+    _solve_latent_ode (Euler, cfg.node.method) -> flatten (B, T) -> nef.apply on every frame -> mean squared error; gradients with
+    respect to the ODE parameters, the NeF parameters and the initial latents against autograd through the oracle's restatement of
+    the same graph.  fp32: both models in the 1e-4 bucket; bf16: the decode runs the tcgen05 kernels (d = 128)."""
+    import enf_pde_b200 as E
+    ecfg = R.EnfConfig(num_in=2, num_hidden=128, num_heads=2, num_out=1, latent_dim=8, invariant_type="rel_pos_periodic",
+                       embedding_freq_multiplier=(0.05, 0.1))
+    ocfg = O.OdeConfig(invariant_type="rel_pos_periodic", num_in=2, num_hidden=32, num_layers=2, latent_dim=8, basis_dim=16, degree=2,
+                       widening_factor=2)
+    B, Z, C, T, h = 2, 9, 150, 3, 0.5
+    nparams, x, p0, a0, sigma, _ = make_case_enf(ecfg, B, C, Z)
+    oparams = R.tree_map(lambda t: t.float().double(), O.ode_init(ocfg, seed=5, readout_scale=3e5))
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(B * (T + 1), C, 1, generator=g, dtype=torch.float64)
+
+    # oracle
+    Pn = R.tree_map(lambda t: t.clone().requires_grad_(True), nparams)
+    Po = R.tree_map(lambda t: t.clone().requires_grad_(True), oparams)
+    p_r, a_r = p0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+    pt, at, st = O.solve_latent_ode(ocfg, Po, (p_r, a_r, sigma), 0.0, T * h, h, "euler")
+    flat = lambda t: t.reshape(-1, *t.shape[2:])
+    xs = x[:1].expand(B * (T + 1), -1, -1)
+    loss_ref = ((R.nef_apply(ecfg, Pn, xs, flat(pt), flat(at), flat(st)) - y) ** 2).mean()
+    loss_ref.backward()
+
+    # GPU path
+    ns = types.SimpleNamespace(invariant_type="rel_pos_periodic", num_in=2)
+    nef = E.EquivariantCrossAttentionNeF(128, 2, 0, 1, 8, E.get_ca_invariant(ns), E.get_sa_invariant(ns), "rff", ecfg.embedding_freq_multiplier,
+                                         True, True, precision=precision)
+    model = _model(ocfg)
+    Gn, Go = _cuda(nparams), _cuda({"params": oparams})
+    pg, ag = f32(p0).requires_grad_(True), f32(a0).requires_grad_(True)
+    ptc, atc, stc = E.solve_latent_ode(lambda z, t: model.apply(Go, z), (pg, ag, f32(sigma)), 0.0, T * h, h, "euler")
+    out = nef.apply(Gn, f32(xs), flat(ptc), flat(atc), flat(stc))
+    loss = ((out - f32(y)) ** 2).mean()
+    loss.backward()
+
+    errs = dict(loss=abs(float(loss.detach()) - float(loss_ref)) / abs(float(loss_ref)), gp=rel_err(pg.grad, p_r.grad), ga=rel_err(ag.grad, a_r.grad))
+    leaf = {}
+    for name, got, want in (("ode", R.tree_flatten(Go["params"]), R.tree_flatten(Po)), ("nef", R.tree_flatten(Gn["params"]), R.tree_flatten(Pn["params"]))):
+        scale = max(float(v.grad.abs().max()) for v in want.values() if v.grad is not None)
+        for k, v in want.items():
+            if v.grad is None:                  # frozen RFF coefficients (stop_gradient, rff.py:90)
+                continue
+            leaf[name + ":" + k] = float((got[k].grad.double().cpu() - v.grad).abs().max()) / max(float(v.grad.abs().max()), 1e-3 * scale)
+    worst = max(leaf, key=leaf.get)
+    print(precision, {k: f"{v:.2e}" for k, v in errs.items()}, "worst leaf", worst, f"{leaf[worst]:.2e}")
+    assert all(v < tol for v in errs.values()), errs
+    assert leaf[worst] < tol_leaf, (worst, leaf[worst])
+
+
+def make_case_enf(cfg, B, C, Z):
+    from helpers import make_case
+    return make_case(cfg, B, C, Z, seed=23)
